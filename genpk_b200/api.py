@@ -1,0 +1,317 @@
+"""Python host side above the C ABI: same names, argument meaning and error
+behaviour as the reference's numerics interface (gen-pk.h:35-119).
+
+numpy arrays are host buffers; the `*_dev` methods of Context take raw device
+pointers (ints), e.g. ``torch_tensor.data_ptr()``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import check
+
+FLAG_FIXED_POINT = 0x1
+FLAG_TWO_FIELDS = 0x2
+FLAG_BINRULE_SOURCE = 0x4
+OPT_DEPOSIT, OPT_SCALE_BITS = 1, 2
+DEPOSIT_AUTO, DEPOSIT_DIRECT, DEPOSIT_SORTED, DEPOSIT_TILED = 0, 1, 2, 3
+STAGE_DEPOSIT, STAGE_FFT, STAGE_POWER, STAGE_SORT = 0, 1, 2, 3
+SYNTH_UNIFORM_RANDOM, SYNTH_LATTICE, SYNTH_CLUSTERED = 0, 1, 2
+FIELD_DIMS = 3072          # gen-pk.cpp:63
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+# ---- small host utilities of utils.cpp, kept for the per-type loop ------------------
+def nexttwo(n: int) -> int:
+    """Next power of two >= n (utils.cpp:35-42)."""
+    n = int(n) - 1
+    i = 1
+    while i < 32:
+        n |= n >> i
+        i <<= 1
+    return n + 1
+
+
+def grid_dims_for(npart_total) -> int:
+    """Grid rule of gen-pk.cpp:169-172: max over types of min(2*nexttwo((int)cbrt(N)), 3072)."""
+    dims = 0
+    for n in npart_total:
+        c = np.cbrt(float(n))
+        tmp = 2 * nexttwo(int(c)) if n > 0 else 2 * nexttwo(0)
+        dims = max(dims, min(tmp, FIELD_DIMS))
+    return dims
+
+
+def type_str(ptype: int) -> str:
+    """utils.cpp:57-72."""
+    return {0: "by", 1: "DM", 2: "nu", 4: "st"}.get(ptype, "xx")
+
+
+def print_pk(filename: str, nrbins: int, keffs, power, count) -> int:
+    """Three-column text output of utils.cpp:7-21 ("%e\\t%e\\t%d\\n" for non-empty bins)."""
+    try:
+        fd = open(filename, "w")
+    except OSError:
+        import sys
+        sys.stderr.write("Error opening file: %s\n" % filename)
+        return 0
+    with fd:
+        for i in range(nrbins):
+            if count[i]:
+                fd.write("%e\t%e\t%d\n" % (keffs[i], power[i], count[i]))
+    return nrbins
+
+
+# ---- reference-signature entry points (host buffers) -------------------------------
+def fieldize(boxsize, dims, out, segment_particles, positions, masses, mass, extra) -> int:
+    """fieldize() of fieldize.cpp:46 on the GPU: accumulates into the host grid `out`."""
+    lib = _lib.load()
+    positions = _f32(positions)
+    n = int(segment_particles)
+    assert positions.size >= 3 * n
+    assert out.dtype == np.float64 and out.flags.c_contiguous
+    assert out.size >= dims * dims * 2 * (dims // 2 + extra)
+    mp = None
+    if masses is not None:
+        masses = _f32(masses)
+        assert masses.size >= n
+        mp = masses.ctypes.data
+    rc = lib.genpk_fieldize(float(boxsize), int(dims), out.ctypes.data, n, positions.ctypes.data, mp, float(mass),
+                            int(extra))
+    check(rc, "genpk_fieldize")
+    return rc
+
+
+def invwindow(kx, ky, kz, n) -> float:
+    """invwindow() of fieldize.cpp:125."""
+    return _lib.load().genpk_invwindow(int(kx), int(ky), int(kz), int(n))
+
+
+def r2c_3d(dims, field) -> None:
+    """fftw_plan_dft_r2c_3d + fftw_execute of gen-pk.cpp:193,233, in place on a host buffer."""
+    assert field.dtype == np.float64 and field.flags.c_contiguous
+    assert field.size >= 2 * dims * dims * (dims // 2 + 1)
+    check(_lib.load().genpk_r2c_3d(int(dims), field.ctypes.data), "genpk_r2c_3d")
+
+
+def powerspectrum(dims, outfield, outfield2, nrbins, power, count, keffs, total_mass, total_mass2) -> int:
+    """powerspectrum() of powerspectrum.c:35; outfield2 may be the same array."""
+    lib = _lib.load()
+    a = outfield.view(np.float64).reshape(-1)
+    b = a if outfield2 is outfield or outfield2 is None else outfield2.view(np.float64).reshape(-1)
+    need = 2 * dims * dims * (dims // 2 + 1)
+    assert a.size >= need and b.size >= need and a.flags.c_contiguous and b.flags.c_contiguous
+    assert power.dtype == np.float64 and keffs.dtype == np.float64 and count.dtype == np.int32
+    rc = lib.genpk_powerspectrum(int(dims), a.ctypes.data, b.ctypes.data, int(nrbins), power.ctypes.data,
+                                 count.ctypes.data, keffs.ctypes.data, float(total_mass), float(total_mass2))
+    check(rc, "genpk_powerspectrum")
+    return rc
+
+
+# ---- handle API ----------------------------------------------------------------------
+class Context:
+    """One GPU, one grid (or x-slab of it) resident in HBM: zero -> deposit* -> fft -> power."""
+
+    def __init__(self, dims: int, device: int = -1, flags: int = 0, nranks: int = 1, rank: int = 0):
+        self.lib = _lib.load()
+        self.dims, self.nranks, self.rank, self.flags = int(dims), int(nranks), int(rank), int(flags)
+        if nranks == 1:
+            self.h = self.lib.genpk_create(self.dims, int(device), self.flags)
+        else:
+            self.h = self.lib.genpk_create_slab(self.dims, int(device), self.nranks, self.rank, self.flags)
+        if not self.h:
+            raise _lib.GenPKError("genpk_create failed: " + _lib.last_error())
+        self.nc = self.dims // 2 + 1
+        self.fd = 2 * self.nc
+        self.nx = self.dims // self.nranks
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.genpk_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # plumbing
+    def set_stream(self, cuda_stream: int):
+        check(self.lib.genpk_set_stream(self.h, cuda_stream), "genpk_set_stream")
+
+    def set_option(self, option: int, value: int):
+        check(self.lib.genpk_set_option(self.h, option, value), "genpk_set_option")
+
+    def set_deposit_mode(self, mode: int):
+        self.set_option(OPT_DEPOSIT, mode)
+
+    def set_scale_bits(self, bits: int):
+        self.set_option(OPT_SCALE_BITS, bits)
+
+    def synchronize(self):
+        check(self.lib.genpk_synchronize(self.h), "genpk_synchronize")
+
+    def stage_ms(self, stage: int) -> float:
+        ms = C.c_float(0)
+        check(self.lib.genpk_stage_ms(self.h, stage, C.byref(ms)), "genpk_stage_ms")
+        return ms.value
+
+    def stage_total_ms(self, stage: int):
+        """(sum of ms, number of recorded instances) since stage_reset()."""
+        ms, n = C.c_float(0), C.c_int64(0)
+        check(self.lib.genpk_stage_total_ms(self.h, stage, C.byref(ms), C.byref(n)), "genpk_stage_total_ms")
+        return ms.value, n.value
+
+    def stage_reset(self):
+        check(self.lib.genpk_stage_reset(self.h), "genpk_stage_reset")
+
+    def launch_count(self) -> int:
+        return self.lib.genpk_launch_count(self.h)
+
+    # the per-type step of gen-pk.cpp:208-234
+    def grid_zero(self, which: int = 0):
+        check(self.lib.genpk_grid_zero(self.h, which), "genpk_grid_zero")
+
+    def deposit(self, positions, masses=None, mass=1.0, boxsize=1.0, which: int = 0, n=None):
+        positions = _f32(positions)
+        n = positions.size // 3 if n is None else int(n)
+        mp = None
+        if masses is not None:
+            masses = _f32(masses)
+            assert masses.size >= n
+            mp = masses.ctypes.data
+        check(self.lib.genpk_deposit(self.h, which, positions.ctypes.data, mp, n, float(mass), float(boxsize), 0),
+              "genpk_deposit")
+
+    def deposit_dev(self, pos_ptr: int, n: int, mass_ptr: int = 0, mass=1.0, boxsize=1.0, which: int = 0):
+        check(self.lib.genpk_deposit(self.h, which, pos_ptr, mass_ptr or None, int(n), float(mass), float(boxsize), 1),
+              "genpk_deposit")
+
+    def deposit_host_ptr(self, pos_ptr: int, n: int, mass_ptr: int = 0, mass=1.0, boxsize=1.0, which: int = 0):
+        check(self.lib.genpk_deposit(self.h, which, pos_ptr, mass_ptr or None, int(n), float(mass), float(boxsize), 0),
+              "genpk_deposit")
+
+    def fft(self, which: int = 0):
+        check(self.lib.genpk_fft(self.h, which), "genpk_fft")
+
+    def power(self, nrbins=None, total_mass=1.0, total_mass2=None, a: int = 0, b: int = 0):
+        nrbins = self.dims if nrbins is None else int(nrbins)
+        total_mass2 = total_mass if total_mass2 is None else total_mass2
+        power = np.zeros(nrbins, np.float64)
+        count = np.zeros(nrbins, np.int32)
+        keffs = np.zeros(nrbins, np.float64)
+        check(self.lib.genpk_power(self.h, a, b, nrbins, power.ctypes.data, count.ctypes.data, keffs.ctypes.data,
+                                   float(total_mass), float(total_mass2)), "genpk_power")
+        return power, count, keffs
+
+    def pk_from_particles(self, positions, masses=None, mass=1.0, boxsize=1.0, total_mass=None, nrbins=None):
+        positions = _f32(positions)
+        n = positions.size // 3
+        nrbins = self.dims if nrbins is None else int(nrbins)
+        mp = None
+        if masses is not None:
+            masses = _f32(masses)
+            mp = masses.ctypes.data
+        if total_mass is None:
+            total_mass = float(np.sum(masses[:n], dtype=np.float64)) if masses is not None else mass * n
+        power = np.zeros(nrbins, np.float64)
+        count = np.zeros(nrbins, np.int32)
+        keffs = np.zeros(nrbins, np.float64)
+        check(self.lib.genpk_pk_from_particles(self.h, positions.ctypes.data, mp, n, float(mass), float(boxsize),
+                                               float(total_mass), nrbins, power.ctypes.data, count.ctypes.data,
+                                               keffs.ctypes.data), "genpk_pk_from_particles")
+        return power, count, keffs
+
+    # parity helpers
+    def grid_doubles(self) -> int:
+        return self.lib.genpk_grid_doubles(self.h)
+
+    def grid_download(self, which: int = 0) -> np.ndarray:
+        out = np.empty(self.grid_doubles(), np.float64)
+        check(self.lib.genpk_grid_download(self.h, which, out.ctypes.data), "genpk_grid_download")
+        return out
+
+    def grid_download_fixed(self, which: int = 0) -> np.ndarray:
+        out = np.empty(self.grid_doubles(), np.int64)
+        check(self.lib.genpk_grid_download_fixed(self.h, which, out.ctypes.data), "genpk_grid_download_fixed")
+        return out
+
+    def grid_upload(self, host: np.ndarray, which: int = 0):
+        host = np.ascontiguousarray(host.view(np.float64).reshape(-1))
+        assert host.size == self.grid_doubles()
+        check(self.lib.genpk_grid_upload(self.h, which, host.ctypes.data), "genpk_grid_upload")
+
+    def grid_ptr(self, which: int = 0) -> int:
+        p = self.lib.genpk_grid_device_ptr(self.h, which)
+        if not p:
+            raise _lib.GenPKError(_lib.last_error())
+        return p
+
+    # slab stages (device pointers)
+    def route_particles(self, pos_ptr, mass_ptr, n, boxsize, spos_ptr, smass_ptr, counts_ptr):
+        check(self.lib.genpk_route_particles(self.h, pos_ptr, mass_ptr or None, int(n), float(boxsize), spos_ptr,
+                                             smass_ptr or None, counts_ptr), "genpk_route_particles")
+
+    def ghost_ptr(self, which: int = 0):
+        nbytes = C.c_size_t(0)
+        p = self.lib.genpk_ghost_ptr(self.h, which, C.byref(nbytes))
+        if not p:
+            raise _lib.GenPKError(_lib.last_error())
+        return p, nbytes.value
+
+    def ghost_accumulate(self, recv_ptr: int, which: int = 0):
+        check(self.lib.genpk_ghost_accumulate(self.h, which, recv_ptr), "genpk_ghost_accumulate")
+
+    def slab_fft_yz(self, which: int = 0):
+        check(self.lib.genpk_slab_fft_yz(self.h, which), "genpk_slab_fft_yz")
+
+    def slab_pack(self, send_ptr: int, which: int = 0):
+        check(self.lib.genpk_slab_pack(self.h, which, send_ptr), "genpk_slab_pack")
+
+    def slab_fft_x(self, recv_ptr: int):
+        check(self.lib.genpk_slab_fft_x(self.h, recv_ptr), "genpk_slab_fft_x")
+
+    def slab_spectrum_bytes(self) -> int:
+        return self.lib.genpk_slab_spectrum_bytes(self.h)
+
+    def slab_power_partial(self, spec_a_ptr: int, spec_b_ptr: int, nrbins: int, sums_ptr: int):
+        check(self.lib.genpk_slab_power_partial(self.h, spec_a_ptr, spec_b_ptr or None, int(nrbins), sums_ptr),
+              "genpk_slab_power_partial")
+
+
+def power_finalize(sums: np.ndarray, nrbins: int, total_mass: float, total_mass2: float):
+    """powerspectrum.c:102-108 applied to all-reduced raw sums [3][nrbins]."""
+    sums = np.ascontiguousarray(sums, np.float64)
+    power = np.zeros(nrbins, np.float64)
+    count = np.zeros(nrbins, np.int32)
+    keffs = np.zeros(nrbins, np.float64)
+    check(_lib.load().genpk_power_finalize(sums.ctypes.data, int(nrbins), float(total_mass), float(total_mass2),
+                                           power.ctypes.data, count.ctypes.data, keffs.ctypes.data),
+          "genpk_power_finalize")
+    return power, count, keffs
+
+
+def bin_thresholds(dims: int, nrbins: int, flags: int = 0) -> np.ndarray:
+    """Plan-time bin edges in k^2 (host arithmetic; see genpk_bin_thresholds)."""
+    out = np.zeros(nrbins + 1, np.uint32)
+    check(_lib.load().genpk_bin_thresholds(int(dims), int(nrbins), int(flags), out.ctypes.data), "genpk_bin_thresholds")
+    return out
+
+
+def synth_particles_dev(kind: int, seed: int, n_side: int, first: int, count: int, boxsize: float, grid_dims: float,
+                        pos_ptr: int, stream: int = 0):
+    check(_lib.load().genpk_synth_particles(int(kind), int(seed), int(n_side), int(first), int(count), float(boxsize),
+                                            float(grid_dims), pos_ptr, stream or None), "genpk_synth_particles")

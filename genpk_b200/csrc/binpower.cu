@@ -1,0 +1,270 @@
+// Fused |delta_k|^2 binning -- replaces powerspectrum() (powerspectrum.c:35-110)
+// and the per-mode invwindow() calls inside it (fieldize.cpp:125-133).
+//
+// One streaming pass over the half-complex spectrum [outer][mid][kz] (16 B per
+// mode, read once): per mode
+//     k2   = ki^2 + kj^2 + kz^2                      (exact integer)
+//     bin  = max{b : thresh[b] <= k2}                (host-built table == floor(bpu*log|k|))
+//     P   += mult * (re1*re2 + im1*im2) * W^4,  W = (float)((iw[ki]*iw[kj])*iw[kz])
+//     K   += mult * sqrt(k2);   N += mult;   mult = 1 on the kz=0 and kz=dims/2 planes, else 2
+// The DC mode is skipped (powerspectrum.c:63).
+//
+// Mapping: persistent warps.  A "panel" unit is 32 consecutive kz (one lane
+// each, so every load is a coalesced 512 B) times JC consecutive mid rows that
+// the thread walks; along that walk |k| changes slowly, so the thread keeps a
+// run (bin, P, K, N) in registers and only touches the CTA's shared-memory
+// histogram when the bin changes.  The nc%32 leftover columns (the Nyquist
+// column for power-of-two grids) are "tail" units with lanes on rows.  Shared
+// histograms are flushed to global with one red.add per non-empty bin per CTA.
+#include "common.cuh"
+
+namespace genpk {
+
+struct PowerArgs {
+    const double2 *a;
+    const double2 *b;
+    int dims, nc;
+    int n_outer, outer0, n_mid, mid0;
+    int nrbins;
+    int jc;               // mid rows per unit
+    int n_mchunks;        // ceil(n_mid / jc)
+    int n_panels;         // nc / 32
+    int n_tail;           // nc % 32
+    long long n_units;
+    const float *iw1d;
+    const uint32_t *thresh;
+    float half_bpu;       // first guess of the bin only; the threshold walk makes it exact
+    double *sums;         // [3][nrbins]
+};
+
+__device__ __forceinline__ int kval(int i, int dims) { return i <= dims / 2 ? i : i - dims; }   // powerspectrum.c:33
+
+struct Run {
+    int bin;
+    unsigned lo, hi;      // thresh[bin], thresh[bin+1]
+    double p, k;
+    unsigned n;
+};
+
+__device__ __forceinline__ void run_flush(const Run &r, int mult, double *sP, double *sK, unsigned *sN)
+{
+    if (r.n) {
+        atomicAdd(&sP[r.bin], r.p * mult);
+        atomicAdd(&sK[r.bin], r.k * mult);
+        atomicAdd(&sN[r.bin], r.n * (unsigned)mult);
+    }
+}
+
+__device__ __forceinline__ void run_seek(Run &r, unsigned k2, const unsigned *sT, int nrbins, float half_bpu, bool guess)
+{
+    int b = r.bin;
+    if (guess) {
+        b = (int)(half_bpu * __logf((float)k2));
+        b = max(0, min(b, nrbins - 1));
+    }
+    while (k2 >= sT[b + 1]) b++;
+    while (k2 < sT[b]) b--;
+    r.bin = b;
+    r.lo = sT[b];
+    r.hi = sT[b + 1];
+    r.p = 0.0;
+    r.k = 0.0;
+    r.n = 0;
+}
+
+template <bool CROSS>
+__device__ __forceinline__ void run_add(Run &r, unsigned k2, double2 va, double2 vb, float fwin, int mult,
+                                        const unsigned *sT, int nrbins, float half_bpu, double *sP, double *sK,
+                                        unsigned *sN)
+{
+    if (k2 == 0)
+        return;                                             // DC mode, powerspectrum.c:63
+    if (k2 < r.lo || k2 >= r.hi) {
+        run_flush(r, mult, sP, sK, sN);
+        run_seek(r, k2, sT, nrbins, half_bpu, r.hi == 0);
+    }
+    const double mod2 = CROSS ? fma(va.x, vb.x, va.y * vb.y) : fma(va.x, va.x, va.y * va.y);
+    double w = (double)fwin;                                // float product promoted, fieldize.cpp:132
+    w = w * w;                                              // invwindow() = prod^2
+    w = w * w;                                              // pow(invwindow,2), powerspectrum.c:68
+    r.p = fma(mod2, w, r.p);
+    r.k += sqrt((double)k2);
+    r.n += 1;
+}
+
+constexpr int POWER_THREADS = 256;
+constexpr int POWER_UNROLL = 4;
+
+template <bool CROSS>
+__global__ void __launch_bounds__(POWER_THREADS) bin_power_kernel(PowerArgs A)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *sP = reinterpret_cast<double *>(smem_raw);
+    double *sK = sP + A.nrbins;
+    unsigned *sN = reinterpret_cast<unsigned *>(sK + A.nrbins);
+    unsigned *sT = sN + A.nrbins;                           // nrbins + 1
+    float *sW = reinterpret_cast<float *>(sT + A.nrbins + 1);   // dims/2 + 1
+    const int half = A.dims / 2;
+    for (int i = threadIdx.x; i < A.nrbins; i += POWER_THREADS) {
+        sP[i] = 0.0;
+        sK[i] = 0.0;
+        sN[i] = 0;
+    }
+    for (int i = threadIdx.x; i <= A.nrbins; i += POWER_THREADS)
+        sT[i] = A.thresh[i];
+    for (int i = threadIdx.x; i <= half; i += POWER_THREADS)
+        sW[i] = A.iw1d[i];
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const int warps_per_cta = POWER_THREADS / 32;
+    const long long warp_global = (long long)blockIdx.x * warps_per_cta + (threadIdx.x >> 5);
+    const long long warp_total = (long long)gridDim.x * warps_per_cta;
+    const int units_per_chunk = A.n_panels + (A.n_tail ? 1 : 0);
+
+    for (long long u = warp_global; u < A.n_units; u += warp_total) {
+        const int p = (int)(u % units_per_chunk);
+        const long long oc = u / units_per_chunk;
+        const int mc = (int)(oc % A.n_mchunks);
+        const int o = (int)(oc / A.n_mchunks);
+        const int ki = kval(A.outer0 + o, A.dims);
+        const float fi = sW[abs(ki)];
+        const int jbeg = mc * A.jc, jend = min(A.n_mid, jbeg + A.jc);
+        const size_t row0 = ((size_t)o * A.n_mid + jbeg) * A.nc;
+        Run r;
+        r.bin = 0; r.lo = 0; r.hi = 0; r.p = 0.0; r.k = 0.0; r.n = 0;
+
+        if (p < A.n_panels) {
+            // ---- panel unit: lane = kz, walk over mid rows ----
+            const int kz = p * 32 + lane;
+            const int mult = (kz == 0 || kz == half) ? 1 : 2;          // powerspectrum.c:59-89
+            const float fz = sW[kz];
+            const unsigned base2 = (unsigned)(ki * ki) + (unsigned)(kz * kz);
+            const double2 *pa = A.a + row0 + kz;
+            const double2 *pb = CROSS ? A.b + row0 + kz : nullptr;
+            for (int j0 = jbeg; j0 < jend; j0 += POWER_UNROLL) {
+                double2 va[POWER_UNROLL], vb[POWER_UNROLL];
+#pragma unroll
+                for (int t = 0; t < POWER_UNROLL; t++) {
+                    if (j0 + t < jend) {
+                        va[t] = __ldcs(pa + (size_t)(j0 - jbeg + t) * A.nc);
+                        if (CROSS) vb[t] = __ldcs(pb + (size_t)(j0 - jbeg + t) * A.nc);
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < POWER_UNROLL; t++) {
+                    if (j0 + t < jend) {
+                        const int kj = kval(A.mid0 + j0 + t, A.dims);
+                        const float fwin = __fmul_rn(__fmul_rn(fi, sW[abs(kj)]), fz);   // (iwx*iwy)*iwz in float
+                        run_add<CROSS>(r, base2 + (unsigned)(kj * kj), va[t], vb[t], fwin, mult, sT, A.nrbins,
+                                       A.half_bpu, sP, sK, sN);
+                    }
+                }
+            }
+            run_flush(r, mult, sP, sK, sN);
+        } else {
+            // ---- tail unit: lane = mid row, walk over the leftover kz columns ----
+            for (int jb = jbeg; jb < jend; jb += 32) {
+                const int j = jb + lane;
+                if (j < jend) {
+                    const int kj = kval(A.mid0 + j, A.dims);
+                    const float fij = __fmul_rn(fi, sW[abs(kj)]);
+                    const unsigned base2 = (unsigned)(ki * ki) + (unsigned)(kj * kj);
+                    const size_t row = ((size_t)o * A.n_mid + j) * A.nc;
+                    for (int kz = A.n_panels * 32; kz < A.nc; kz++) {
+                        const int mult = (kz == 0 || kz == half) ? 1 : 2;
+                        const double2 va = __ldcs(A.a + row + kz);
+                        const double2 vb = CROSS ? __ldcs(A.b + row + kz) : va;
+                        r.bin = 0; r.lo = 0; r.hi = 0; r.p = 0.0; r.k = 0.0; r.n = 0;
+                        run_add<CROSS>(r, base2 + (unsigned)(kz * kz), va, vb, __fmul_rn(fij, sW[kz]), mult, sT,
+                                       A.nrbins, A.half_bpu, sP, sK, sN);
+                        run_flush(r, mult, sP, sK, sN);
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < A.nrbins; i += POWER_THREADS) {
+        if (sN[i]) {
+            atomicAdd(&A.sums[i], sP[i]);
+            atomicAdd(&A.sums[A.nrbins + i], sK[i]);
+            atomicAdd(&A.sums[2 * A.nrbins + i], (double)sN[i]);     // exact: integers < 2^53
+        }
+    }
+}
+
+int ensure_tables(genpk_ctx *ctx, int nrbins)
+{
+    const unsigned rule = (ctx->flags & GENPK_FLAG_BINRULE_SOURCE) ? 1u : 0u;
+    if (ctx->tables.nrbins == nrbins && ctx->tables.dims == ctx->g.dims && ctx->d_thresh)
+        return 0;
+    if (int rc = build_bin_tables(ctx->g.dims, nrbins, rule, &ctx->tables))
+        return rc;
+    if (ctx->d_thresh) cudaFree(ctx->d_thresh);
+    if (ctx->d_iw1d) cudaFree(ctx->d_iw1d);
+    if (ctx->d_sums) cudaFree(ctx->d_sums);
+    if (ctx->h_sums) cudaFreeHost(ctx->h_sums);
+    ctx->d_thresh = nullptr; ctx->d_iw1d = nullptr; ctx->d_sums = nullptr; ctx->h_sums = nullptr;
+    GENPK_CUDA_OK(cudaMalloc(&ctx->d_thresh, ctx->tables.thresh.size() * sizeof(uint32_t)));
+    GENPK_CUDA_OK(cudaMalloc(&ctx->d_iw1d, ctx->tables.iw1d.size() * sizeof(float)));
+    GENPK_CUDA_OK(cudaMalloc(&ctx->d_sums, (size_t)3 * nrbins * sizeof(double)));
+    GENPK_CUDA_OK(cudaMallocHost(&ctx->h_sums, (size_t)3 * nrbins * sizeof(double)));
+    ctx->sums_cap = nrbins;
+    GENPK_CUDA_OK(cudaMemcpyAsync(ctx->d_thresh, ctx->tables.thresh.data(), ctx->tables.thresh.size() * sizeof(uint32_t),
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    GENPK_CUDA_OK(cudaMemcpyAsync(ctx->d_iw1d, ctx->tables.iw1d.data(), ctx->tables.iw1d.size() * sizeof(float),
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    GENPK_CUDA_OK(cudaStreamSynchronize(ctx->stream));     // the host vectors may be rebuilt later
+    return 0;
+}
+
+// Raw per-bin sums of a spectrum block [n_outer][n_mid][nc] whose first outer
+// (mid) index is global FFT index outer0 (mid0).  sums_dev: 3*nrbins doubles.
+int power_raw(genpk_ctx *ctx, const double *spec_a, const double *spec_b, int n_outer, int outer0, int n_mid,
+              int mid0, int nrbins, double *sums_dev)
+{
+    if (int rc = ensure_tables(ctx, nrbins))
+        return rc;
+    PowerArgs A;
+    A.a = reinterpret_cast<const double2 *>(spec_a);
+    A.b = reinterpret_cast<const double2 *>(spec_b);
+    A.dims = ctx->g.dims;
+    A.nc = ctx->g.nc;
+    A.n_outer = n_outer;
+    A.outer0 = outer0;
+    A.n_mid = n_mid;
+    A.mid0 = mid0;
+    A.nrbins = nrbins;
+    A.jc = 32;
+    A.n_mchunks = (n_mid + A.jc - 1) / A.jc;
+    A.n_panels = A.nc / 32;
+    A.n_tail = A.nc % 32;
+    A.n_units = (long long)n_outer * A.n_mchunks * (A.n_panels + (A.n_tail ? 1 : 0));
+    A.iw1d = ctx->d_iw1d;
+    A.thresh = ctx->d_thresh;
+    A.half_bpu = nrbins > 1 ? (float)(0.5 * (nrbins - 1) / log(sqrt(3.0) * A.dims / 2.0)) : 0.f;
+    A.sums = sums_dev;
+    GENPK_CUDA_OK(cudaMemsetAsync(sums_dev, 0, (size_t)3 * nrbins * sizeof(double), ctx->stream));
+
+    const size_t smem = (size_t)nrbins * (8 + 8 + 4) + (size_t)(nrbins + 1) * 4 + (size_t)(A.dims / 2 + 1) * 4 + 16;
+    const bool cross = spec_b != spec_a;
+    auto kern = cross ? bin_power_kernel<true> : bin_power_kernel<false>;
+    GENPK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    GENPK_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, POWER_THREADS, smem));
+    if (per_sm < 1) {
+        set_error("bin_power: %zu bytes of shared memory do not fit (nrbins=%d dims=%d)", smem, nrbins, A.dims);
+        return 1;
+    }
+    long long ctas = (long long)per_sm * ctx->sm_count;
+    const long long need = (A.n_units + POWER_THREADS / 32 - 1) / (POWER_THREADS / 32);
+    if (ctas > need) ctas = need;
+    if (ctas < 1) ctas = 1;
+    kern<<<(int)ctas, POWER_THREADS, smem, ctx->stream>>>(A);
+    ctx->launches++;
+    GENPK_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace genpk

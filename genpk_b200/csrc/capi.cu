@@ -1,0 +1,511 @@
+// C ABI of libgenpk_cuda.so (see include/genpk_cuda.h).
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "common.cuh"
+
+namespace genpk {
+
+static thread_local char g_error[1024] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+int fieldize_host_shim(double boxsize, int dims, double *out, int64_t n, const float *positions,
+                       const float *masses, double mass, int extra);
+
+static bool check_which(const genpk_ctx *ctx, int which, const char *fn)
+{
+    if (!ctx) {
+        set_error("%s: null context", fn);
+        return false;
+    }
+    if (which < 0 || which > 1 || !ctx->grid[which]) {
+        set_error("%s: grid %d not allocated (create the context with GENPK_FLAG_TWO_FIELDS for grid 1)", fn, which);
+        return false;
+    }
+    return true;
+}
+
+static genpk_ctx *create_common(int dims, int device, int nranks, int rank, unsigned flags)
+{
+    if (dims < 1 || nranks < 1 || rank < 0 || rank >= nranks || dims % nranks != 0) {
+        set_error("genpk_create: bad geometry dims=%d nranks=%d rank=%d (dims must be divisible by nranks)", dims,
+                  nranks, rank);
+        return nullptr;
+    }
+    if (device >= 0 && cudaSetDevice(device) != cudaSuccess) {
+        set_error("genpk_create: cudaSetDevice(%d) failed: %s", device, cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        set_error("genpk_create: no CUDA device: %s", cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    genpk_ctx *ctx = new (std::nothrow) genpk_ctx();
+    if (!ctx) {
+        set_error("genpk_create: out of host memory");
+        return nullptr;
+    }
+    ctx->device = dev;
+    ctx->flags = flags;
+    ctx->fixed = (flags & GENPK_FLAG_FIXED_POINT) != 0;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) {
+        ctx->sm_count = prop.multiProcessorCount;
+        ctx->l2_bytes = (size_t)prop.l2CacheSize;
+    }
+    SlabGeom &g = ctx->g;
+    g.dims = dims;
+    g.nranks = nranks;
+    g.rank = rank;
+    g.nx = dims / nranks;
+    g.x0 = rank * g.nx;
+    g.ghost = nranks > 1 ? 1 : 0;
+    g.nc = dims / 2 + 1;
+    g.fd = 2 * g.nc;
+    const int ngrids = (flags & GENPK_FLAG_TWO_FIELDS) ? 2 : 1;
+    bool ok = true;
+    for (int i = 0; i < ngrids && ok; i++)
+        ok = cudaMalloc(&ctx->grid[i], g.grid_doubles() * sizeof(double)) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->d_errors, sizeof(unsigned long long)) == cudaSuccess;
+    ok = ok && cudaMemset(ctx->d_errors, 0, sizeof(unsigned long long)) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < ST_COUNT && ok; i++)
+        for (int s = 0; s < genpk_ctx::EV_SLOTS && ok; s++)
+            ok = cudaEventCreate(&ctx->ev_begin[i][s]) == cudaSuccess && cudaEventCreate(&ctx->ev_end[i][s]) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; i++)
+        ok = cudaEventCreateWithFlags(&ctx->stage_free[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+        set_error("genpk_create: CUDA allocation failed for dims=%d (%zu bytes per grid): %s", dims,
+                  g.grid_doubles() * sizeof(double), cudaGetErrorString(cudaGetLastError()));
+        genpk_destroy(ctx);
+        return nullptr;
+    }
+    return ctx;
+}
+
+}  // namespace genpk
+
+using namespace genpk;
+
+extern "C" {
+
+const char *genpk_last_error(void) { return g_error; }
+int genpk_abi_version(void) { return GENPK_ABI_VERSION; }
+
+genpk_ctx *genpk_create(int dims, int device, unsigned flags) { return create_common(dims, device, 1, 0, flags); }
+
+genpk_ctx *genpk_create_slab(int dims, int device, int nranks, int rank, unsigned flags)
+{
+    return create_common(dims, device, nranks, rank, flags);
+}
+
+void genpk_destroy(genpk_ctx *ctx)
+{
+    if (!ctx)
+        return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    fft_release(ctx);
+    for (int i = 0; i < 2; i++) {
+        if (ctx->grid[i]) cudaFree(ctx->grid[i]);
+        if (ctx->d_stage_pos[i]) cudaFree(ctx->d_stage_pos[i]);
+        if (ctx->d_stage_mass[i]) cudaFree(ctx->d_stage_mass[i]);
+        if (ctx->stage_free[i]) cudaEventDestroy(ctx->stage_free[i]);
+    }
+    if (ctx->d_iw1d) cudaFree(ctx->d_iw1d);
+    if (ctx->d_thresh) cudaFree(ctx->d_thresh);
+    if (ctx->d_sums) cudaFree(ctx->d_sums);
+    if (ctx->h_sums) cudaFreeHost(ctx->h_sums);
+    if (ctx->d_sorted_pos) cudaFree(ctx->d_sorted_pos);
+    if (ctx->d_sorted_mass) cudaFree(ctx->d_sorted_mass);
+    if (ctx->d_brick_counts) cudaFree(ctx->d_brick_counts);
+    if (ctx->d_errors) cudaFree(ctx->d_errors);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    for (int i = 0; i < ST_COUNT; i++)
+        for (int s = 0; s < genpk_ctx::EV_SLOTS; s++) {
+            if (ctx->ev_begin[i][s]) cudaEventDestroy(ctx->ev_begin[i][s]);
+            if (ctx->ev_end[i][s]) cudaEventDestroy(ctx->ev_end[i][s]);
+        }
+    delete ctx;
+}
+
+int genpk_set_stream(genpk_ctx *ctx, void *cuda_stream)
+{
+    if (!ctx) { set_error("genpk_set_stream: null context"); return 1; }
+    ctx->stream = (cudaStream_t)cuda_stream;
+    return 0;
+}
+
+int genpk_set_option(genpk_ctx *ctx, int option, int64_t value)
+{
+    if (!ctx) { set_error("genpk_set_option: null context"); return 1; }
+    switch (option) {
+    case GENPK_OPT_DEPOSIT:
+        if (value < GENPK_DEPOSIT_AUTO || value > GENPK_DEPOSIT_TILED) break;
+        ctx->deposit_mode = (int)value;
+        return 0;
+    case GENPK_OPT_SCALE_BITS:
+        if (value < 0 || value > 62) break;
+        ctx->scale_bits = (int)value;
+        return 0;
+    }
+    set_error("genpk_set_option: bad option %d / value %lld", option, (long long)value);
+    return 1;
+}
+
+int genpk_synchronize(genpk_ctx *ctx)
+{
+    if (!ctx) { set_error("genpk_synchronize: null context"); return 1; }
+    GENPK_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    unsigned long long bad = 0;
+    GENPK_CUDA_OK(cudaMemcpy(&bad, ctx->d_errors, sizeof(bad), cudaMemcpyDeviceToHost));
+    if (bad) {
+        cudaMemset(ctx->d_errors, 0, sizeof(bad));
+        set_error("%llu particles rejected (non-finite position, or outside this rank's x-slab)", bad);
+        return 3;
+    }
+    return 0;
+}
+
+int genpk_grid_zero(genpk_ctx *ctx, int which)
+{
+    if (!check_which(ctx, which, "genpk_grid_zero")) return 1;
+    GENPK_CUDA_OK(cudaMemsetAsync(ctx->grid[which], 0, ctx->g.grid_doubles() * sizeof(double), ctx->stream));
+    ctx->grid_is_fixed[which] = false;
+    return 0;
+}
+
+static int ensure_stage(genpk_ctx *ctx, int64_t cap, bool with_mass)
+{
+    if (cap > ctx->stage_cap) {
+        for (int i = 0; i < 2; i++) {
+            if (ctx->d_stage_pos[i]) cudaFree(ctx->d_stage_pos[i]);
+            if (ctx->d_stage_mass[i]) cudaFree(ctx->d_stage_mass[i]);
+            ctx->d_stage_pos[i] = nullptr;
+            ctx->d_stage_mass[i] = nullptr;
+        }
+        ctx->stage_cap = 0;
+        for (int i = 0; i < 2; i++)
+            GENPK_CUDA_OK(cudaMalloc(&ctx->d_stage_pos[i], (size_t)cap * 3 * sizeof(float)));
+        ctx->stage_cap = cap;
+    }
+    if (with_mass && !ctx->d_stage_mass[0])
+        for (int i = 0; i < 2; i++)
+            GENPK_CUDA_OK(cudaMalloc(&ctx->d_stage_mass[i], (size_t)ctx->stage_cap * sizeof(float)));
+    return 0;
+}
+
+int genpk_deposit(genpk_ctx *ctx, int which, const float *positions, const float *masses, int64_t n, double mass,
+                  double boxsize, int on_device)
+{
+    if (!check_which(ctx, which, "genpk_deposit")) return 1;
+    if (n < 0 || (n > 0 && !positions)) { set_error("genpk_deposit: bad particle array"); return 1; }
+    if (n == 0) return 0;
+    stage_begin(ctx, ST_DEPOSIT);
+    int rc = 0;
+    if (on_device) {
+        rc = deposit_device(ctx, which, positions, masses, n, mass, boxsize);
+    } else {
+        // Host particles: chunks go up on the copy stream into two device staging
+        // buffers while the previous chunk is being deposited (chunk loop of
+        // read_fieldize.cpp:51-93, overlapped).
+        const int64_t chunk = n < ((int64_t)1 << 25) ? n : ((int64_t)1 << 25);
+        if ((rc = ensure_stage(ctx, chunk, masses != nullptr))) return rc;
+        int buf = 0;
+        for (int64_t off = 0; off < n && !rc; off += chunk, buf ^= 1) {
+            const int64_t m = (n - off) < chunk ? (n - off) : chunk;
+            GENPK_CUDA_OK(cudaStreamWaitEvent(ctx->copy_stream, ctx->stage_free[buf], 0));
+            GENPK_CUDA_OK(cudaMemcpyAsync(ctx->d_stage_pos[buf], positions + 3 * off, (size_t)m * 3 * sizeof(float),
+                                          cudaMemcpyHostToDevice, ctx->copy_stream));
+            if (masses)
+                GENPK_CUDA_OK(cudaMemcpyAsync(ctx->d_stage_mass[buf], masses + off, (size_t)m * sizeof(float),
+                                              cudaMemcpyHostToDevice, ctx->copy_stream));
+            cudaEvent_t up;   // chunk uploaded
+            GENPK_CUDA_OK(cudaEventCreateWithFlags(&up, cudaEventDisableTiming));
+            GENPK_CUDA_OK(cudaEventRecord(up, ctx->copy_stream));
+            GENPK_CUDA_OK(cudaStreamWaitEvent(ctx->stream, up, 0));
+            GENPK_CUDA_OK(cudaEventDestroy(up));
+            rc = deposit_device(ctx, which, ctx->d_stage_pos[buf], masses ? ctx->d_stage_mass[buf] : nullptr, m, mass,
+                                boxsize);
+            GENPK_CUDA_OK(cudaEventRecord(ctx->stage_free[buf], ctx->stream));
+        }
+    }
+    stage_end(ctx, ST_DEPOSIT);
+    return rc;
+}
+
+int genpk_fft(genpk_ctx *ctx, int which)
+{
+    if (!check_which(ctx, which, "genpk_fft")) return 1;
+    if (ctx->g.nranks != 1) {
+        set_error("genpk_fft: slab contexts use genpk_slab_fft_yz / genpk_slab_pack / genpk_slab_fft_x");
+        return 1;
+    }
+    stage_begin(ctx, ST_FFT);
+    if (int rc = fixed_to_double(ctx, which)) return rc;
+    if (int rc = fft_3d(ctx, which)) return rc;
+    stage_end(ctx, ST_FFT);
+    return 0;
+}
+
+int genpk_power_finalize(const double *sums, int nrbins, double total_mass, double total_mass2, double *power,
+                         int *count, double *keffs)
+{
+    if (!sums || !power || !count || !keffs || nrbins < 1) { set_error("genpk_power_finalize: bad arguments"); return 1; }
+    for (int b = 0; b < nrbins; b++) {
+        const long long c = (long long)sums[2 * (size_t)nrbins + b];
+        count[b] = (int)c;                                   // int count[], powerspectrum.c:35
+        power[b] = sums[b];
+        keffs[b] = sums[(size_t)nrbins + b];
+        if (count[b]) {                                      // powerspectrum.c:102-108
+            power[b] /= total_mass * total_mass2;
+            power[b] /= count[b];
+            keffs[b] /= count[b];
+        }
+    }
+    return 0;
+}
+
+int genpk_power(genpk_ctx *ctx, int a, int b, int nrbins, double *power, int *count, double *keffs, double total_mass,
+                double total_mass2)
+{
+    if (!check_which(ctx, a, "genpk_power") || !check_which(ctx, b, "genpk_power")) return 1;
+    if (nrbins < 1 || !power || !count || !keffs) { set_error("genpk_power: bad arguments"); return 1; }
+    if (ctx->g.nranks != 1) { set_error("genpk_power: slab contexts use genpk_slab_power_partial"); return 1; }
+    if (int rc = ensure_tables(ctx, nrbins)) return rc;
+    stage_begin(ctx, ST_POWER);
+    if (int rc = power_raw(ctx, ctx->grid[a], ctx->grid[b], ctx->g.dims, 0, ctx->g.dims, 0, nrbins, ctx->d_sums)) return rc;
+    stage_end(ctx, ST_POWER);
+    GENPK_CUDA_OK(cudaMemcpyAsync(ctx->h_sums, ctx->d_sums, (size_t)3 * nrbins * sizeof(double), cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+    GENPK_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    return genpk_power_finalize(ctx->h_sums, nrbins, total_mass, total_mass2, power, count, keffs);
+}
+
+int genpk_pk_from_particles(genpk_ctx *ctx, const float *positions, const float *masses, int64_t n, double mass,
+                            double boxsize, double total_mass, int nrbins, double *power, int *count, double *keffs)
+{
+    if (int rc = genpk_grid_zero(ctx, 0)) return rc;
+    if (int rc = genpk_deposit(ctx, 0, positions, masses, n, mass, boxsize, 0)) return rc;
+    if (int rc = genpk_fft(ctx, 0)) return rc;
+    if (int rc = genpk_power(ctx, 0, 0, nrbins, power, count, keffs, total_mass, total_mass)) return rc;
+    return genpk_synchronize(ctx);
+}
+
+size_t genpk_grid_doubles(const genpk_ctx *ctx) { return ctx ? ctx->g.grid_doubles() : 0; }
+
+void *genpk_grid_device_ptr(genpk_ctx *ctx, int which)
+{
+    return check_which(ctx, which, "genpk_grid_device_ptr") ? ctx->grid[which] : nullptr;
+}
+
+int genpk_grid_download(genpk_ctx *ctx, int which, double *host)
+{
+    if (!check_which(ctx, which, "genpk_grid_download")) return 1;
+    const size_t n = ctx->g.grid_doubles();
+    GENPK_CUDA_OK(cudaMemcpyAsync(host, ctx->grid[which], n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    GENPK_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->grid_is_fixed[which]) {                         // exact: (double)q * 2^-S
+        const double inv = ldexp(1.0, -ctx->scale_bits);
+        for (size_t i = 0; i < n; i++) {
+            long long q;
+            memcpy(&q, &host[i], sizeof(q));
+            host[i] = (double)q * inv;
+        }
+    }
+    return 0;
+}
+
+int genpk_grid_download_fixed(genpk_ctx *ctx, int which, int64_t *host)
+{
+    if (!check_which(ctx, which, "genpk_grid_download_fixed")) return 1;
+    if (!ctx->grid_is_fixed[which] && ctx->fixed) {
+        // an untouched (zeroed) grid is valid fixed-point data too
+    } else if (!ctx->grid_is_fixed[which]) {
+        set_error("genpk_grid_download_fixed: grid %d does not hold fixed-point sums", which);
+        return 1;
+    }
+    GENPK_CUDA_OK(cudaMemcpyAsync(host, ctx->grid[which], ctx->g.grid_doubles() * sizeof(double), cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+    GENPK_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int genpk_grid_upload(genpk_ctx *ctx, int which, const double *host)
+{
+    if (!check_which(ctx, which, "genpk_grid_upload")) return 1;
+    GENPK_CUDA_OK(cudaMemcpyAsync(ctx->grid[which], host, ctx->g.grid_doubles() * sizeof(double), cudaMemcpyHostToDevice,
+                                  ctx->stream));
+    GENPK_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    ctx->grid_is_fixed[which] = false;
+    return 0;
+}
+
+int genpk_stage_ms(genpk_ctx *ctx, int stage, float *ms)
+{
+    if (!ctx || stage < 0 || stage >= ST_COUNT || !ms) { set_error("genpk_stage_ms: bad arguments"); return 1; }
+    *ms = 0.f;
+    if (ctx->ev_count[stage] == 0) return 0;
+    const int s = (int)((ctx->ev_count[stage] - 1) % genpk_ctx::EV_SLOTS);
+    GENPK_CUDA_OK(cudaEventSynchronize(ctx->ev_end[stage][s]));
+    GENPK_CUDA_OK(cudaEventElapsedTime(ms, ctx->ev_begin[stage][s], ctx->ev_end[stage][s]));
+    return 0;
+}
+
+int genpk_stage_total_ms(genpk_ctx *ctx, int stage, float *total_ms, int64_t *records)
+{
+    if (!ctx || stage < 0 || stage >= ST_COUNT || !total_ms || !records) { set_error("genpk_stage_total_ms: bad arguments"); return 1; }
+    const int64_t n = ctx->ev_count[stage] < genpk_ctx::EV_SLOTS ? ctx->ev_count[stage] : genpk_ctx::EV_SLOTS;
+    double sum = 0;
+    for (int64_t i = 0; i < n; i++) {
+        const int s = (int)((ctx->ev_count[stage] - 1 - i) % genpk_ctx::EV_SLOTS);
+        float ms = 0.f;
+        GENPK_CUDA_OK(cudaEventSynchronize(ctx->ev_end[stage][s]));
+        GENPK_CUDA_OK(cudaEventElapsedTime(&ms, ctx->ev_begin[stage][s], ctx->ev_end[stage][s]));
+        sum += ms;
+    }
+    *total_ms = (float)sum;
+    *records = n;
+    return 0;
+}
+
+int genpk_stage_reset(genpk_ctx *ctx)
+{
+    if (!ctx) { set_error("genpk_stage_reset: null context"); return 1; }
+    for (int i = 0; i < ST_COUNT; i++) ctx->ev_count[i] = 0;
+    return 0;
+}
+
+int64_t genpk_launch_count(const genpk_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+/* ---------------- slab stages ---------------- */
+
+int genpk_route_particles(genpk_ctx *ctx, const float *pos_dev, const float *mass_dev, int64_t n, double boxsize,
+                          float *sorted_pos_dev, float *sorted_mass_dev, int64_t *counts_dev)
+{
+    if (!ctx || n < 0 || !counts_dev || (n > 0 && (!pos_dev || !sorted_pos_dev))) {
+        set_error("genpk_route_particles: bad arguments");
+        return 1;
+    }
+    return route_particles(ctx, pos_dev, mass_dev, n, boxsize, sorted_pos_dev, sorted_mass_dev, counts_dev);
+}
+
+void *genpk_ghost_ptr(genpk_ctx *ctx, int which, size_t *bytes)
+{
+    if (!check_which(ctx, which, "genpk_ghost_ptr")) return nullptr;
+    if (!ctx->g.ghost) { set_error("genpk_ghost_ptr: single-rank context has no ghost plane"); return nullptr; }
+    if (bytes) *bytes = ctx->g.plane() * sizeof(double);
+    return ctx->grid[which] + ctx->g.owned_doubles();
+}
+
+int genpk_ghost_accumulate(genpk_ctx *ctx, int which, const void *recv_plane_dev)
+{
+    if (!check_which(ctx, which, "genpk_ghost_accumulate")) return 1;
+    return ghost_accumulate(ctx, which, recv_plane_dev);
+}
+
+int genpk_slab_fft_yz(genpk_ctx *ctx, int which)
+{
+    if (!check_which(ctx, which, "genpk_slab_fft_yz")) return 1;
+    stage_begin(ctx, ST_FFT);
+    if (int rc = fixed_to_double(ctx, which)) return rc;
+    if (int rc = fft_yz(ctx, which)) return rc;
+    stage_end(ctx, ST_FFT);
+    return 0;
+}
+
+int genpk_slab_pack(genpk_ctx *ctx, int which, void *send_dev)
+{
+    if (!check_which(ctx, which, "genpk_slab_pack")) return 1;
+    return slab_pack(ctx, which, send_dev);
+}
+
+int genpk_slab_fft_x(genpk_ctx *ctx, void *recv_dev)
+{
+    if (!ctx || !recv_dev) { set_error("genpk_slab_fft_x: bad arguments"); return 1; }
+    return fft_x(ctx, recv_dev);
+}
+
+size_t genpk_slab_spectrum_bytes(const genpk_ctx *ctx)
+{
+    return ctx ? (size_t)ctx->g.dims * (ctx->g.dims / ctx->g.nranks) * ctx->g.nc * 2 * sizeof(double) : 0;
+}
+
+int genpk_slab_power_partial(genpk_ctx *ctx, const void *spec_a_dev, const void *spec_b_dev, int nrbins, double *sums_dev)
+{
+    if (!ctx || !spec_a_dev || !sums_dev || nrbins < 1) { set_error("genpk_slab_power_partial: bad arguments"); return 1; }
+    const int ny = ctx->g.dims / ctx->g.nranks;
+    stage_begin(ctx, ST_POWER);
+    if (int rc = power_raw(ctx, (const double *)spec_a_dev, (const double *)(spec_b_dev ? spec_b_dev : spec_a_dev),
+                           ctx->g.dims, 0, ny, ctx->g.rank * ny, nrbins, sums_dev))
+        return rc;
+    stage_end(ctx, ST_POWER);
+    return 0;
+}
+
+int genpk_bin_thresholds(int dims, int nrbins, unsigned flags, uint32_t *thresh_out)
+{
+    if (!thresh_out) { set_error("genpk_bin_thresholds: null output"); return 1; }
+    BinTables t;
+    if (int rc = build_bin_tables(dims, nrbins, (flags & GENPK_FLAG_BINRULE_SOURCE) ? 1u : 0u, &t)) return rc;
+    memcpy(thresh_out, t.thresh.data(), t.thresh.size() * sizeof(uint32_t));
+    return 0;
+}
+
+/* ---------------- reference-signature shims on host buffers ---------------- */
+
+int genpk_fieldize(double boxsize, int dims, double *out, int64_t segment_particles, const float *positions,
+                   const float *masses, double mass, int extra)
+{
+    if (!out || (segment_particles > 0 && !positions)) { set_error("genpk_fieldize: null buffer"); return 1; }
+    return fieldize_host_shim(boxsize, dims, out, segment_particles, positions, masses, mass, extra);
+}
+
+double genpk_invwindow(int64_t kx, int64_t ky, int64_t kz, int64_t n)
+{
+    if (n == 0)                                              // fieldize.cpp:127
+        return 0;
+    const float iwx = oned_invwindow_f32(kx, n), iwy = oned_invwindow_f32(ky, n), iwz = oned_invwindow_f32(kz, n);
+    const float prod = (iwx * iwy) * iwz;
+    return (double)prod * (double)prod;
+}
+
+int genpk_r2c_3d(int dims, double *field)
+{
+    if (!field) { set_error("genpk_r2c_3d: null buffer"); return 1; }
+    genpk_ctx *ctx = genpk_create(dims, -1, 0);
+    if (!ctx) return 1;
+    int rc = genpk_grid_upload(ctx, 0, field);
+    if (!rc) rc = genpk_fft(ctx, 0);
+    if (!rc) rc = genpk_grid_download(ctx, 0, field);
+    genpk_destroy(ctx);
+    return rc;
+}
+
+int genpk_powerspectrum(int64_t dims, const double *outfield, const double *outfield2, int nrbins, double *power,
+                        int *count, double *keffs, double total_mass, double total_mass2)
+{
+    if (!outfield || !outfield2) { set_error("genpk_powerspectrum: null field"); return 1; }
+    const bool cross = outfield2 != outfield;
+    genpk_ctx *ctx = genpk_create((int)dims, -1, cross ? GENPK_FLAG_TWO_FIELDS : 0);
+    if (!ctx) return 1;
+    int rc = genpk_grid_upload(ctx, 0, outfield);
+    if (!rc && cross) rc = genpk_grid_upload(ctx, 1, outfield2);
+    if (!rc) rc = genpk_power(ctx, 0, cross ? 1 : 0, nrbins, power, count, keffs, total_mass, total_mass2);
+    genpk_destroy(ctx);
+    return rc;
+}
+
+}  // extern "C"

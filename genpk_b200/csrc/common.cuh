@@ -1,0 +1,148 @@
+// Shared declarations of libgenpk_cuda.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cufft.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <string>
+#include <vector>
+
+#include "../../include/genpk_cuda.h"
+
+namespace genpk {
+
+void set_error(const char *fmt, ...);
+
+#define GENPK_CUDA_OK(expr)                                                                   \
+    do {                                                                                      \
+        cudaError_t e__ = (expr);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            genpk::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); \
+            return 1;                                                                         \
+        }                                                                                     \
+    } while (0)
+
+#define GENPK_CUFFT_OK(expr)                                                                  \
+    do {                                                                                      \
+        cufftResult r__ = (expr);                                                             \
+        if (r__ != CUFFT_SUCCESS) {                                                           \
+            genpk::set_error("%s:%d: %s -> cufft error %d", __FILE__, __LINE__, #expr, (int)r__); \
+            return 2;                                                                         \
+        }                                                                                     \
+    } while (0)
+
+// Host-built tables for the binning kernel (tables.cpp).
+struct BinTables {
+    int dims = 0, nrbins = 0;
+    unsigned rule = 0;
+    std::vector<float> iw1d;          // iw1d[k] = (float) onedinvwindow(k, dims), k = 0..dims/2
+    std::vector<uint32_t> thresh;     // thresh[b] = smallest k2 >= 1 whose bin is >= b; thresh[nrbins] = k2max+1
+    bool monotone = true;
+};
+// rule 0: bin = floor((0.5*bpu)*log((double)k2))  (what gcc -O2 -ffast-math makes of powerspectrum.c:66)
+// rule 1: bin = floor(bpu*log(sqrt((double)k2)))  (powerspectrum.c:66 as written)
+int reference_bin_of_k2(int dims, int nrbins, int64_t k2, unsigned rule);
+int build_bin_tables(int dims, int nrbins, unsigned rule, BinTables *out);
+float oned_invwindow_f32(int64_t k, int64_t n);
+
+// Geometry of the part of the grid / spectrum one context owns.
+struct SlabGeom {
+    int dims = 0;      // global grid side
+    int nranks = 1, rank = 0;
+    int nx = 0;        // local x planes (dims / nranks)
+    int x0 = 0;        // first global x plane
+    int ghost = 0;     // 1 when a high-x ghost plane is stored (nranks > 1)
+    int fd = 0;        // padded z stride in doubles, 2*(dims/2+1)
+    int nc = 0;        // complex z extent, dims/2+1
+    size_t plane() const { return (size_t)dims * fd; }                    // doubles per x plane
+    size_t grid_doubles() const { return plane() * (size_t)(nx + ghost); }
+    size_t owned_doubles() const { return plane() * (size_t)nx; }
+};
+
+enum Stage { ST_DEPOSIT = 0, ST_FFT = 1, ST_POWER = 2, ST_SORT = 3, ST_COUNT = 4 };
+
+}  // namespace genpk
+
+struct genpk_ctx {
+    genpk::SlabGeom g;
+    unsigned flags = 0;
+    int device = 0;
+    int sm_count = 148;
+    size_t l2_bytes = 0;
+    cudaStream_t stream = nullptr;
+    bool fixed = false;
+    int scale_bits = 40;
+    int deposit_mode = GENPK_DEPOSIT_AUTO;
+
+    double *grid[2] = {nullptr, nullptr};
+    bool grid_is_fixed[2] = {false, false};   // grid currently holds int64 fixed-point sums
+
+    // cuFFT
+    cufftHandle plan3d = 0, plan_yz = 0, plan_x = 0;
+    bool have_plan3d = false, have_plan_yz = false, have_plan_x = false;
+    void *fft_work = nullptr;
+    size_t fft_work_bytes = 0;
+
+    // binning
+    genpk::BinTables tables;
+    float *d_iw1d = nullptr;
+    uint32_t *d_thresh = nullptr;
+    double *d_sums = nullptr;         // 3*nrbins raw sums
+    double *h_sums = nullptr;         // pinned
+    int sums_cap = 0;
+
+    // deposit scratch
+    float *d_stage_pos[2] = {nullptr, nullptr};
+    float *d_stage_mass[2] = {nullptr, nullptr};
+    float *h_stage_pos[2] = {nullptr, nullptr};
+    float *h_stage_mass[2] = {nullptr, nullptr};
+    cudaEvent_t stage_free[2] = {nullptr, nullptr};
+    cudaStream_t copy_stream = nullptr;
+    int64_t stage_cap = 0;            // particles per staging buffer
+    float *d_sorted_pos = nullptr;
+    float *d_sorted_mass = nullptr;
+    int64_t sorted_cap = 0;
+    uint32_t *d_brick_counts = nullptr;   // histogram / cursors
+    int64_t brick_cap = 0;
+    unsigned long long *d_errors = nullptr;   // device-side counter of rejected particles
+
+    // timing: a ring of event pairs per stage, summed on request (no host sync while recording)
+    static constexpr int EV_SLOTS = 128;
+    cudaEvent_t ev_begin[genpk::ST_COUNT][EV_SLOTS] = {}, ev_end[genpk::ST_COUNT][EV_SLOTS] = {};
+    int64_t ev_count[genpk::ST_COUNT] = {};   // records since the last reset
+    int64_t launches = 0;     // our own kernels
+    int64_t lib_calls = 0;    // cuFFT executions
+};
+
+namespace genpk {
+
+// deposit.cu
+int deposit_device(genpk_ctx *ctx, int which, const float *pos, const float *masses, int64_t n,
+                   double mass, double boxsize);
+int fixed_to_double(genpk_ctx *ctx, int which);
+// binpower.cu
+int ensure_tables(genpk_ctx *ctx, int nrbins);
+int power_raw(genpk_ctx *ctx, const double *spec_a, const double *spec_b, int n_outer, int outer0,
+              int n_mid, int mid0, int nrbins, double *sums_dev);
+// fft.cu
+int fft_3d(genpk_ctx *ctx, int which);
+int fft_yz(genpk_ctx *ctx, int which);
+int fft_x(genpk_ctx *ctx, void *recv);
+void fft_release(genpk_ctx *ctx);
+// slab.cu
+int route_particles(genpk_ctx *ctx, const float *pos, const float *mass, int64_t n, double boxsize,
+                    float *spos, float *smass, int64_t *counts);
+int ghost_accumulate(genpk_ctx *ctx, int which, const void *recv);
+int slab_pack(genpk_ctx *ctx, int which, void *send);
+
+inline void stage_begin(genpk_ctx *ctx, int st)
+{
+    cudaEventRecord(ctx->ev_begin[st][ctx->ev_count[st] % genpk_ctx::EV_SLOTS], ctx->stream);
+}
+inline void stage_end(genpk_ctx *ctx, int st)
+{
+    cudaEventRecord(ctx->ev_end[st][ctx->ev_count[st] % genpk_ctx::EV_SLOTS], ctx->stream);
+    ctx->ev_count[st]++;
+}
+
+}  // namespace genpk

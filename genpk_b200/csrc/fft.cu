@@ -1,0 +1,106 @@
+// 3-D real-to-complex transform -- replaces fftw_plan_dft_r2c_3d(...) + fftw_execute()
+// (gen-pk.cpp:193,233): unnormalised, forward (exp(-2 pi i ...)), in place on the
+// FFTW padded layout, which is also cuFFT's in-place D2Z layout.
+//
+// Single GPU: one cufftPlan3d D2Z.  Slab mode: batched 2-D D2Z over the local x
+// planes, then (after the caller's transpose) strided 1-D Z2Z along x.
+// All plans share one work area owned by the context.
+#include "common.cuh"
+
+namespace genpk {
+
+static int grow_work(genpk_ctx *ctx, size_t bytes)
+{
+    if (bytes <= ctx->fft_work_bytes)
+        return 0;
+    if (ctx->fft_work) cudaFree(ctx->fft_work);
+    ctx->fft_work = nullptr;
+    ctx->fft_work_bytes = 0;
+    GENPK_CUDA_OK(cudaMalloc(&ctx->fft_work, bytes));
+    ctx->fft_work_bytes = bytes;
+    return 0;
+}
+
+static int attach_work(genpk_ctx *ctx)
+{
+    if (ctx->have_plan3d) GENPK_CUFFT_OK(cufftSetWorkArea(ctx->plan3d, ctx->fft_work));
+    if (ctx->have_plan_yz) GENPK_CUFFT_OK(cufftSetWorkArea(ctx->plan_yz, ctx->fft_work));
+    if (ctx->have_plan_x) GENPK_CUFFT_OK(cufftSetWorkArea(ctx->plan_x, ctx->fft_work));
+    return 0;
+}
+
+int fft_3d(genpk_ctx *ctx, int which)
+{
+    const int d = ctx->g.dims;
+    if (!ctx->have_plan3d) {
+        size_t ws = 0;
+        GENPK_CUFFT_OK(cufftCreate(&ctx->plan3d));
+        GENPK_CUFFT_OK(cufftSetAutoAllocation(ctx->plan3d, 0));
+        GENPK_CUFFT_OK(cufftMakePlan3d(ctx->plan3d, d, d, d, CUFFT_D2Z, &ws));
+        ctx->have_plan3d = true;
+        if (int rc = grow_work(ctx, ws)) return rc;
+        if (int rc = attach_work(ctx)) return rc;
+    }
+    GENPK_CUFFT_OK(cufftSetStream(ctx->plan3d, ctx->stream));
+    GENPK_CUFFT_OK(cufftExecD2Z(ctx->plan3d, ctx->grid[which], reinterpret_cast<cufftDoubleComplex *>(ctx->grid[which])));
+    ctx->lib_calls++;
+    return 0;
+}
+
+int fft_yz(genpk_ctx *ctx, int which)
+{
+    const SlabGeom &g = ctx->g;
+    if (!ctx->have_plan_yz) {
+        size_t ws = 0;
+        long long n[2] = {g.dims, g.dims};
+        long long inembed[2] = {g.dims, g.fd};
+        long long onembed[2] = {g.dims, g.nc};
+        GENPK_CUFFT_OK(cufftCreate(&ctx->plan_yz));
+        GENPK_CUFFT_OK(cufftSetAutoAllocation(ctx->plan_yz, 0));
+        GENPK_CUFFT_OK(cufftMakePlanMany64(ctx->plan_yz, 2, n, inembed, 1, (long long)g.dims * g.fd, onembed, 1,
+                                           (long long)g.dims * g.nc, CUFFT_D2Z, g.nx, &ws));
+        ctx->have_plan_yz = true;
+        if (int rc = grow_work(ctx, ws)) return rc;
+        if (int rc = attach_work(ctx)) return rc;
+    }
+    GENPK_CUFFT_OK(cufftSetStream(ctx->plan_yz, ctx->stream));
+    GENPK_CUFFT_OK(cufftExecD2Z(ctx->plan_yz, ctx->grid[which], reinterpret_cast<cufftDoubleComplex *>(ctx->grid[which])));
+    ctx->lib_calls++;
+    return 0;
+}
+
+int fft_x(genpk_ctx *ctx, void *recv)
+{
+    const SlabGeom &g = ctx->g;
+    const long long ny = g.dims / g.nranks;
+    const long long inner = ny * g.nc;                 // stride between consecutive x
+    if (!ctx->have_plan_x) {
+        size_t ws = 0;
+        long long n[1] = {g.dims};
+        long long embed[1] = {g.dims};
+        GENPK_CUFFT_OK(cufftCreate(&ctx->plan_x));
+        GENPK_CUFFT_OK(cufftSetAutoAllocation(ctx->plan_x, 0));
+        GENPK_CUFFT_OK(cufftMakePlanMany64(ctx->plan_x, 1, n, embed, inner, 1, embed, inner, 1, CUFFT_Z2Z, inner, &ws));
+        ctx->have_plan_x = true;
+        if (int rc = grow_work(ctx, ws)) return rc;
+        if (int rc = attach_work(ctx)) return rc;
+    }
+    GENPK_CUFFT_OK(cufftSetStream(ctx->plan_x, ctx->stream));
+    cufftDoubleComplex *p = reinterpret_cast<cufftDoubleComplex *>(recv);
+    GENPK_CUFFT_OK(cufftExecZ2Z(ctx->plan_x, p, p, CUFFT_FORWARD));
+    ctx->lib_calls++;
+    return 0;
+}
+
+void fft_release(genpk_ctx *ctx)
+{
+    if (ctx->have_plan3d) cufftDestroy(ctx->plan3d);
+    if (ctx->have_plan_yz) cufftDestroy(ctx->plan_yz);
+    if (ctx->have_plan_x) cufftDestroy(ctx->plan_x);
+    ctx->have_plan3d = ctx->have_plan_yz = ctx->have_plan_x = false;
+    if (ctx->fft_work) cudaFree(ctx->fft_work);
+    ctx->fft_work = nullptr;
+    ctx->fft_work_bytes = 0;
+}
+
+}  // namespace genpk

@@ -1,0 +1,214 @@
+/* genpk_cuda.h -- C ABI of libgenpk_cuda.so, the B200 (sm_100a) implementation
+ * of GenPK's matter-power-spectrum hot path:
+ *
+ *     cloud-in-cell deposit  ->  3-D r2c FFT  ->  |delta_k|^2 binning
+ *
+ * It replaces, behind the reference's own link-time function boundary
+ * (gen-pk.h:93-119), what happens between the memset at gen-pk.cpp:208 and the
+ * return of powerspectrum() at gen-pk.cpp:234.  All entry points are
+ * extern "C", take plain pointers and sizes, and return 0 on success and a
+ * nonzero code on failure (genpk_last_error() has the message); nothing here
+ * aborts the process and nothing falls back to the CPU.
+ *
+ * Three layers:
+ *   1. reference-signature shims on HOST buffers (drop-in for the callers in
+ *      read_fieldize*.cpp, gen-pk.cpp and test.cpp);
+ *   2. a handle API that keeps the grid resident in HBM across
+ *      zero -> deposit* -> fft -> power (the fast path the host CLI uses);
+ *   3. slab-stage entry points on DEVICE buffers for the multi-GPU pipeline,
+ *      where the caller owns the inter-GPU exchange steps.
+ *
+ * Layout conventions (same as the reference / FFTW in-place r2c):
+ *   real grid   double [dims][dims][fd],  fd = 2*(dims/2+1), x slowest, z fastest
+ *   spectrum    complex double [dims][dims][dims/2+1] in the same bytes
+ *   particles   float32 AoS [n][3]; optional float32 masses [n]
+ */
+#ifndef GENPK_CUDA_H
+#define GENPK_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GENPK_ABI_VERSION 1
+
+/* ---- flags for genpk_create / genpk_create_slab ---------------------------------- */
+#define GENPK_FLAG_FIXED_POINT   0x1u  /* deterministic int64 fixed-point accumulation */
+#define GENPK_FLAG_TWO_FIELDS    0x2u  /* allocate a second grid (cross spectra, gen-pk.cpp:263,314)   */
+#define GENPK_FLAG_BINRULE_SOURCE 0x4u /* bin = floor(b*log(sqrt(k2))) evaluated as written in
+                                          powerspectrum.c:66 instead of the 0.5*b*log(k2) form that
+                                          gcc -ffast-math (the reference's Makefile:30) compiles it to */
+
+/* ---- deposit algorithm selection (genpk_set_option(ctx, GENPK_OPT_DEPOSIT, v)) ---- */
+#define GENPK_OPT_DEPOSIT        1
+#define GENPK_DEPOSIT_AUTO       0     /* pick from particle density and spatial coherence */
+#define GENPK_DEPOSIT_DIRECT     1     /* one thread per particle, 8 global red.add          */
+#define GENPK_DEPOSIT_SORTED     2     /* counting sort into L2-sized bricks, then deposit   */
+#define GENPK_DEPOSIT_TILED      3     /* sort into bricks, shared-memory tile accumulation  */
+#define GENPK_OPT_SCALE_BITS     2     /* fixed-point mode: q = llrint(w * 2^bits), default 40 */
+
+typedef struct genpk_ctx genpk_ctx;
+
+/* ================= 1. reference-signature shims (host buffers) ====================== */
+
+/* Replaces fieldize() (fieldize.cpp:46, gen-pk.h:93).  Same arguments, same
+ * meaning: `out` is a caller-owned, caller-zeroed host grid that is ACCUMULATED
+ * into; extra=1 selects the FFTW padded z stride 2*(dims/2+1), extra=0 the
+ * unpadded stride 2*(dims/2).  Copies `out` up, deposits on the GPU, copies it
+ * back.  Returns 0 (the reference always returns 0) or nonzero on a CUDA error. */
+int genpk_fieldize(double boxsize, int dims, double *out, int64_t segment_particles,
+                   const float *positions, const float *masses, double mass, int extra);
+
+/* Replaces invwindow() (fieldize.cpp:125, gen-pk.h:104): ((float)wx*(float)wy*(float)wz)^2,
+ * 0 when n==0.  Host arithmetic, identical roundings to the table the binning
+ * kernel consumes; kept so test.cpp:52-57 can be run against this library. */
+double genpk_invwindow(int64_t kx, int64_t ky, int64_t kz, int64_t n);
+
+/* Replaces fftw_plan_dft_r2c_3d(d,d,d,field,(fftw_complex*)field,FFTW_ESTIMATE) +
+ * fftw_execute() (gen-pk.cpp:193,233): unnormalised forward in-place r2c on a
+ * host buffer of 2*d*d*(d/2+1) doubles, computed with cuFFT on the GPU. */
+int genpk_r2c_3d(int dims, double *field);
+
+/* Replaces powerspectrum() (powerspectrum.c:35, gen-pk.h:119).  outfield and
+ * outfield2 are host arrays of dims*dims*(dims/2+1) interleaved complex doubles
+ * and may alias.  power/count/keffs (nrbins each) are overwritten. */
+int genpk_powerspectrum(int64_t dims, const double *outfield, const double *outfield2, int nrbins,
+                        double *power, int *count, double *keffs, double total_mass, double total_mass2);
+
+/* ================= 2. handle API (grid resident in HBM) ============================= */
+
+/* One context = one GPU, one cubic grid of side `dims` (or one x-slab of it),
+ * its cuFFT plans and its scratch.  device<0 keeps the current device. */
+genpk_ctx *genpk_create(int dims, int device, unsigned flags);
+void genpk_destroy(genpk_ctx *ctx);
+const char *genpk_last_error(void);
+int genpk_abi_version(void);
+
+/* All work of the context is issued on `cuda_stream` (a cudaStream_t; NULL =
+ * the legacy default stream).  Lets a host that owns streams (e.g. torch) order
+ * our kernels against its own copies and collectives. */
+int genpk_set_stream(genpk_ctx *ctx, void *cuda_stream);
+int genpk_set_option(genpk_ctx *ctx, int option, int64_t value);
+int genpk_synchronize(genpk_ctx *ctx);
+
+/* memset(field,0,...) of gen-pk.cpp:208 for grid `which` (0 or 1). */
+int genpk_grid_zero(genpk_ctx *ctx, int which);
+
+/* fieldize() into the resident grid `which`; additive across calls until the
+ * next genpk_grid_zero (chunk loop read_fieldize.cpp:51-93; stars into baryons
+ * gen-pk.cpp:228-230).  positions/masses are host pointers when on_device==0
+ * (copied through an internal pinned double buffer) or device pointers when
+ * on_device!=0.  masses may be NULL (constant `mass`). */
+int genpk_deposit(genpk_ctx *ctx, int which, const float *positions, const float *masses,
+                  int64_t n, double mass, double boxsize, int on_device);
+
+/* fftw_execute() of gen-pk.cpp:233 on grid `which`, in place (cuFFT D2Z).  In
+ * fixed-point mode the int64 grid is converted to double first. */
+int genpk_fft(genpk_ctx *ctx, int which);
+
+/* powerspectrum(dims, grid a, grid b, ...) (gen-pk.cpp:234,297,348) on the
+ * resident spectra; results to host arrays of nrbins entries. */
+int genpk_power(genpk_ctx *ctx, int a, int b, int nrbins, double *power, int *count, double *keffs,
+                double total_mass, double total_mass2);
+
+/* Whole per-type step of gen-pk.cpp:208-234 in one call on host particle
+ * arrays: zero, deposit, FFT, binning, results on the host. */
+int genpk_pk_from_particles(genpk_ctx *ctx, const float *positions, const float *masses, int64_t n,
+                            double mass, double boxsize, double total_mass, int nrbins,
+                            double *power, int *count, double *keffs);
+
+/* Parity / debugging: copy grid `which` to/from a host buffer of
+ * genpk_grid_doubles(ctx) doubles (real padded grid before genpk_fft, the
+ * interleaved spectrum after it).  In fixed-point mode before genpk_fft the
+ * download converts to double; genpk_grid_download_fixed returns the raw int64. */
+size_t genpk_grid_doubles(const genpk_ctx *ctx);
+int genpk_grid_download(genpk_ctx *ctx, int which, double *host);
+int genpk_grid_upload(genpk_ctx *ctx, int which, const double *host);
+int genpk_grid_download_fixed(genpk_ctx *ctx, int which, int64_t *host);
+void *genpk_grid_device_ptr(genpk_ctx *ctx, int which);
+
+/* Elapsed GPU milliseconds of the most recent deposit / fft / power stage of
+ * this context (CUDA events on the context's stream), and kernels launched
+ * since creation. */
+#define GENPK_STAGE_DEPOSIT 0
+#define GENPK_STAGE_FFT     1
+#define GENPK_STAGE_POWER   2
+#define GENPK_STAGE_SORT    3
+int genpk_stage_ms(genpk_ctx *ctx, int stage, float *ms);
+/* Sum over the (up to 128 most recent) recorded instances of a stage since
+ * genpk_stage_reset, and how many were summed.  Recording never synchronises
+ * the host; this call does. */
+int genpk_stage_total_ms(genpk_ctx *ctx, int stage, float *total_ms, int64_t *records);
+int genpk_stage_reset(genpk_ctx *ctx);
+int64_t genpk_launch_count(const genpk_ctx *ctx);
+
+/* ================= 3. slab stages for the multi-GPU pipeline ======================== */
+/* Rank `rank` of `nranks` owns x-planes [rank*dims/nranks, (rank+1)*dims/nranks)
+ * of the real grid plus one ghost plane on the high-x side, and after the
+ * transpose the ky rows [rank*dims/nranks, ...) of the spectrum.  dims must be
+ * divisible by nranks.  The caller (one process per GPU) performs the three
+ * exchange steps between the stages with its own collectives:
+ *
+ *   genpk_route_particles   -> all-to-all-v of particle runs      (caller)
+ *   genpk_deposit(on_device)
+ *   genpk_ghost_ptr         -> ring shift of the ghost plane      (caller)
+ *   genpk_ghost_accumulate
+ *   genpk_slab_fft_yz, genpk_slab_pack
+ *                           -> all-to-all of the packed blocks    (caller)
+ *   genpk_slab_fft_x
+ *   genpk_slab_power_partial-> all-reduce of 3*nrbins doubles     (caller)
+ *   genpk_power_finalize
+ */
+genpk_ctx *genpk_create_slab(int dims, int device, int nranks, int rank, unsigned flags);
+
+/* Destination rank of every particle: floor(x*dims/box) wrapped, / (dims/nranks).
+ * Writes counts[nranks] (device int64) and the particles grouped by destination
+ * into sorted_pos (device, n*3 floats) / sorted_mass (or NULL). */
+int genpk_route_particles(genpk_ctx *ctx, const float *pos_dev, const float *mass_dev, int64_t n,
+                          double boxsize, float *sorted_pos_dev, float *sorted_mass_dev,
+                          int64_t *counts_dev);
+
+/* Device pointer and byte size of the ghost plane (send buffer of the ring
+ * shift), and accumulation of a received plane into local plane 0. */
+void *genpk_ghost_ptr(genpk_ctx *ctx, int which, size_t *bytes);
+int genpk_ghost_accumulate(genpk_ctx *ctx, int which, const void *recv_plane_dev);
+
+/* Batched 2-D D2Z over the local x-planes (in place). */
+int genpk_slab_fft_yz(genpk_ctx *ctx, int which);
+/* Reorder [x_local][y][kz] into nranks contiguous blocks [dest][x_local][y_local][kz]. */
+int genpk_slab_pack(genpk_ctx *ctx, int which, void *send_dev);
+/* 1-D Z2Z along x on the received [x][y_local][kz] array (in place in recv_dev). */
+int genpk_slab_fft_x(genpk_ctx *ctx, void *recv_dev);
+size_t genpk_slab_spectrum_bytes(const genpk_ctx *ctx);
+
+/* Raw per-bin sums of this rank's part of the spectrum: sums_dev holds
+ * 3*nrbins doubles = [sum w*P*W^2][sum w*|k|][sum w] (counts are exact integers
+ * below 2^53).  spec_a/spec_b are [dims][ny_local][dims/2+1] device arrays. */
+int genpk_slab_power_partial(genpk_ctx *ctx, const void *spec_a_dev, const void *spec_b_dev, int nrbins,
+                             double *sums_dev);
+
+/* Normalisation of powerspectrum.c:102-108 applied to reduced raw sums (host). */
+int genpk_power_finalize(const double *sums_host, int nrbins, double total_mass, double total_mass2,
+                         double *power, int *count, double *keffs);
+
+/* Host-built bin edges the binning kernel consumes (plan-time table, no GPU
+ * needed): thresh_out[b], b = 0..nrbins, is the smallest k2 = ki^2+kj^2+kz^2 >= 1
+ * whose bin floor(binsperunit*log|k|) (powerspectrum.c:38,66) is >= b, and
+ * thresh_out[nrbins] = 3*(dims/2)^2 + 1.  flags: GENPK_FLAG_BINRULE_SOURCE or 0. */
+int genpk_bin_thresholds(int dims, int nrbins, unsigned flags, uint32_t *thresh_out);
+
+/* ================= synthetic particle sets (BASELINE.json configs) ================== */
+#define GENPK_SYNTH_UNIFORM_RANDOM 0   /* x = box * hash24(seed, 3p+a) / 2^24, random order       */
+#define GENPK_SYNTH_LATTICE        1   /* q = (i+1/2) box/n, z fastest                              */
+#define GENPK_SYNTH_CLUSTERED      2   /* lattice + sum of 32 plane-wave displacements, rms ~2 cells*/
+/* Fills pos_dev[count][3] with particles first..first+count-1 of an n_side^3 set. */
+int genpk_synth_particles(int kind, uint64_t seed, int64_t n_side, int64_t first, int64_t count,
+                          double boxsize, double grid_dims, float *pos_dev, void *cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GENPK_CUDA_H */

@@ -1,0 +1,88 @@
+"""Oracle-backed stand-in for genpk_b200.distributed.CudaStages on CPU tensors.
+
+TEST INFRASTRUCTURE: lets the exchange choreography of SlabPipeline (all-to-all-v
+routing, ghost ring shift, transpose, all-reduce) run over gloo without GPUs.
+Every stage is computed with numpy / the CPU oracle."""
+import numpy as np
+import torch
+
+from oracle.oracle import Oracle, padded_shape
+
+
+class NumpyStages:
+    def __init__(self, dims, nranks, rank):
+        self.dims, self.nranks, self.rank = dims, nranks, rank
+        self.nc, self.fd = dims // 2 + 1, 2 * (dims // 2 + 1)
+        self.nx = dims // nranks
+        self.x0 = rank * self.nx
+        self.orc = Oracle("port")
+        self.grid = None
+        self.spec2d = None
+
+    def _cell_x(self, pos, boxsize):
+        x = pos.reshape(-1, 3)[:, 0].astype(np.float64) * (self.dims / boxsize)
+        return np.mod(np.floor(x).astype(np.int64), self.dims)
+
+    def route(self, pos, mass, boxsize):
+        p = pos.numpy().reshape(-1, 3)
+        dest = self._cell_x(p, boxsize) // self.nx
+        order = np.argsort(dest, kind="stable")
+        counts = np.bincount(dest, minlength=self.nranks).astype(np.int64)
+        spos = torch.from_numpy(np.ascontiguousarray(p[order]).reshape(-1))
+        smass = torch.from_numpy(np.ascontiguousarray(mass.numpy()[order])) if mass is not None else None
+        return spos, smass, torch.from_numpy(counts)
+
+    def zero(self, which=0):
+        self.grid = np.zeros((self.nx + 1, self.dims, self.fd))
+
+    def deposit(self, pos, mass, cmass, boxsize, which=0):
+        p = pos.numpy().reshape(-1, 3)
+        if len(p) == 0:
+            return
+        ix = self._cell_x(p, boxsize)
+        assert np.all((ix >= self.x0) & (ix < self.x0 + self.nx)), "particle routed to the wrong slab"
+        full = np.zeros(padded_shape(self.dims))
+        self.orc.fieldize(boxsize, self.dims, full, p, None if mass is None else mass.numpy(), cmass, 1)
+        self.grid[: self.nx] += full[self.x0: self.x0 + self.nx]
+        if self.nranks > 1:             # with one rank the periodic wrap already landed in plane 0
+            self.grid[self.nx] += full[(self.x0 + self.nx) % self.dims]
+
+    def ghost_plane(self, which=0):
+        return torch.from_numpy(self.grid[self.nx].reshape(-1))
+
+    def ghost_accumulate(self, recv, which=0):
+        self.grid[0] += recv.numpy().reshape(self.dims, self.fd)
+
+    def fft_yz(self, which=0):
+        self.spec2d = np.fft.rfft2(self.grid[: self.nx, :, : self.dims], axes=(1, 2))
+
+    def pack(self, which=0):
+        ny = self.dims // self.nranks
+        blocks = self.spec2d.reshape(self.nx, self.nranks, ny, self.nc).transpose(1, 0, 2, 3)
+        return torch.from_numpy(np.ascontiguousarray(blocks).view(np.float64).reshape(-1))
+
+    def spectrum_buffer(self, which=0):
+        ny = self.dims // self.nranks
+        return torch.empty(self.dims * ny * self.nc * 2, dtype=torch.float64)
+
+    def fft_x(self, spec):
+        ny = self.dims // self.nranks
+        a = spec.numpy().view(np.complex128).reshape(self.dims, ny, self.nc)
+        a[...] = np.fft.fft(a, axis=0)
+
+    def power_partial(self, spec_a, spec_b, nrbins):
+        """Raw sums of this rank's ky rows: the oracle bins a full-size spectrum that is
+        zero outside them; the geometry-only sums (|k|, counts) are contributed by rank 0."""
+        ny = self.dims // self.nranks
+        full = np.zeros((self.dims, self.dims, self.nc), np.complex128)
+        full[:, self.rank * ny: (self.rank + 1) * ny] = spec_a.numpy().view(np.complex128).reshape(self.dims, ny, self.nc)
+        _, p, c, k = self.orc.powerspectrum(self.dims, full, None, nrbins, 1.0, 1.0)
+        sums = np.zeros(3 * nrbins)
+        sums[:nrbins] = p * c
+        if self.rank == 0:
+            sums[nrbins: 2 * nrbins] = k * c
+            sums[2 * nrbins:] = c
+        return torch.from_numpy(sums)
+
+    def check(self):
+        pass

@@ -1,0 +1,75 @@
+"""world_size-2 (and 4) runs of the slab pipeline's exchange choreography over
+gloo on CPU tensors, with oracle-backed stages, against the single-process
+oracle.  The CUDA stages themselves are covered by the -m gpu tests."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _particles(n, box, seed, var_mass):
+    rng = np.random.default_rng(seed)
+    pos = ((rng.random((n, 3)) * 1.1 - 0.05) * box).astype(np.float32)       # some outside the box
+    masses = (10.0 ** rng.uniform(-1, 1, n)).astype(np.float32) if var_mass else None
+    return pos, masses
+
+
+def _worker(rank, world, port, dims, n, box, var_mass, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from genpk_b200.distributed import SlabPipeline
+        from tests.slab_numpy_stages import NumpyStages
+        pos, masses = _particles(n, box, 123, var_mass)
+        lo, hi = rank * n // world, (rank + 1) * n // world                 # rank-sharded, arbitrary order
+        tm = float(masses.astype(np.float64).sum()) if var_mass else 0.5 * n
+        pipe = SlabPipeline(dims, NumpyStages(dims, world, rank))
+        p, c, k = pipe.pk(torch.from_numpy(pos[lo:hi].reshape(-1).copy()),
+                          torch.from_numpy(masses[lo:hi].copy()) if var_mass else None, 0.5, box, tm, dims)
+        if rank == 0:
+            np.savez(os.path.join(out_dir, "out.npz"), p=p, c=c, k=k)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,dims,var_mass", [(2, 16, False), (2, 32, True), (4, 16, True)])
+def test_slab_pipeline_over_gloo(tmp_path, port, world, dims, var_mass):
+    n, box = 6000, 100.0
+    mp.spawn(_worker, args=(world, _free_port(), dims, n, box, var_mass, str(tmp_path)), nprocs=world, join=True)
+    got = np.load(tmp_path / "out.npz")
+    pos, masses = _particles(n, box, 123, var_mass)
+    tm = float(masses.astype(np.float64).sum()) if var_mass else 0.5 * n
+    _, pr, cr, kr = port.pk(box, dims, pos, masses, 0.5, tm, dims)
+    assert np.array_equal(got["c"], cr)
+    nz = cr > 0
+    np.testing.assert_allclose(got["p"][nz], pr[nz], rtol=1e-9)
+    np.testing.assert_allclose(got["k"][nz], kr[nz], rtol=1e-12)
+
+
+def test_single_rank_pipeline_without_process_group(port):
+    sys.path.insert(0, ROOT)
+    from genpk_b200.distributed import SlabPipeline
+    from tests.slab_numpy_stages import NumpyStages
+    dims, n, box = 16, 3000, 10.0
+    pos, _ = _particles(n, box, 5, False)
+    pipe = SlabPipeline(dims, NumpyStages(dims, 1, 0))
+    p, c, k = pipe.pk(torch.from_numpy(pos.reshape(-1).copy()), None, 1.0, box, float(n), dims)
+    _, pr, cr, kr = port.pk(box, dims, pos, None, 1.0, float(n), dims)
+    assert np.array_equal(c, cr)
+    nz = cr > 0
+    np.testing.assert_allclose(p[nz], pr[nz], rtol=1e-9)
