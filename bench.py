@@ -1,0 +1,432 @@
+#!/usr/bin/env python
+"""bench.py -- GenPK P(k) hot path on B200: deposit -> r2c FFT -> |delta_k|^2 binning.
+
+    python bench.py --gpus N --steps K --warmup W            our CUDA path
+    python bench.py --impl reference --gpus N ...            the reference's CPU code (oracle/_ref)
+
+One "step" = one pass of the hot path over one synthetic particle set
+(gen-pk.cpp:208-234: zero the grid, deposit, FFT, bin, results on the host).
+Prints ONE JSON line on rank 0 (see DESIGN.md "Measurement" for every key).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "end-to-end P(k) throughput, CIC deposit -> r2c FFT -> |delta_k|^2 binning"
+UNIT = "Mparticles/s"
+
+# BASELINE.json configs.  `cpu` is the bounded replica the CPU arms time.
+WORKLOADS = {
+    # configs[1]: synthetic 256^3 DM particles uniform, 512^3 grid, single B200
+    "c2": dict(n_side=256, dims=512, kind="uniform", label="synthetic 256^3 uniform-random particles -> 512^3 grid",
+               cpu=dict(n_side=256, dims=512)),
+    # configs[2]: synthetic 1024^3 clustered (Zel'dovich-displaced) particles, 1024^3 grid, 1/2/4/8 B200
+    "c3": dict(n_side=1024, dims=1024, kind="clustered",
+               label="synthetic 1024^3 clustered (Zel'dovich-displaced) particles -> 1024^3 grid",
+               cpu=dict(n_side=256, dims=256)),
+    # configs[4]: synthetic 2048^3 particles on a 2048^3 grid, slab-decomposed across 8 GPUs
+    "c5": dict(n_side=2048, dims=2048, kind="clustered", label="synthetic 2048^3 clustered particles -> 2048^3 grid",
+               cpu=dict(n_side=256, dims=256)),
+    "tiny": dict(n_side=64, dims=128, kind="clustered", label="synthetic 64^3 clustered particles -> 128^3 grid",
+                 cpu=dict(n_side=64, dims=128)),
+}
+BOX = 1000.0
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("GENPK_WORKLOAD", "c3"), choices=sorted(WORKLOADS))
+    ap.add_argument("--fixed-point", action="store_true", help="deterministic int64 accumulation mode")
+    ap.add_argument("--deposit", default="auto", choices=["auto", "direct", "sorted", "tiled"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------
+# helpers
+# ----------------------------------------------------------------------------------------
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, STREAM-style copy)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+def algorithmic_bytes(n_particles, dims, nranks=1):
+    """particles read once (12 B), padded real grid written once (8 B/cell);
+    spectrum read once (16 B/mode).  Per GPU."""
+    fd = 2 * (dims // 2 + 1)
+    deposit = 12 * n_particles / nranks + 8 * dims * dims * fd / nranks
+    binning = 16 * dims * dims * (dims // 2 + 1) / nranks
+    return deposit, binning
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.proc, self.lines, self.gpu = None, [], gpu_index
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(gpu_index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0=None, t1=None):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        for ts, line in self.lines:
+            if t0 is not None and not (t0 - 0.05 <= ts <= t1 + 0.15):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
+                "power_w_max": float(max(power)), "samples": len(sm)}
+
+
+def host_particles(kind, n_side, dims, seed=42):
+    """Host-side synthetic particles of the same distributions as genpk_synth_particles
+    (statistically, not bit for bit) for the CPU arms."""
+    n = n_side ** 3
+    if kind == "uniform":
+        rng = np.random.default_rng(seed)
+        return (rng.random((n, 3), dtype=np.float32) * np.float32(BOX))
+    q1 = ((np.arange(n_side) + 0.5) / n_side)
+    q = np.stack(np.meshgrid(q1, q1, q1, indexing="ij"), axis=-1).reshape(-1, 3)
+    rng = np.random.default_rng(seed)
+    modes = []
+    while len(modes) < 32:
+        v = rng.integers(-8, 9, 3)
+        ln = np.sqrt((v ** 2).sum())
+        if 0.5 < ln <= 8.0:
+            modes.append(v)
+    modes = np.array(modes, np.float64)
+    ln = np.sqrt((modes ** 2).sum(1))
+    amp = ln ** -1.5
+    amp *= (2.0 / dims) / np.sqrt((amp ** 2).sum() / 6.0)           # per-component rms of ~2 cells
+    phase = rng.random(32)
+    disp = np.zeros_like(q)
+    for m in range(32):
+        s = np.sin(2 * np.pi * (q @ modes[m] + phase[m]))
+        disp += (amp[m] * modes[m] / ln[m])[None, :] * s[:, None]
+    x = (q + disp) % 1.0
+    return (x * BOX).astype(np.float32)
+
+
+_HOST_CACHE = {}
+
+
+def time_cpu_path(kind, wl, reps=1, want="reference"):
+    """Times the reference's CPU implementation (oracle/_ref when built, else the oracle
+    port) on wl['cpu'] = a bounded replica of the workload with the same particles per
+    cell and distribution.  Returns per-stage seconds (best of reps)."""
+    from oracle.oracle import Oracle, have_reference, padded_shape, rfftn_padded
+    backend = "reference" if (want == "reference" and have_reference()) else "port"
+    orc = Oracle(backend)
+    n_side, dims = wl["cpu"]["n_side"], wl["cpu"]["dims"]
+    key = (kind, n_side, dims)
+    if key not in _HOST_CACHE:                       # generated once, outside every timed region
+        _HOST_CACHE.clear()
+        _HOST_CACHE[key] = host_particles(kind, n_side, dims)
+    pos = _HOST_CACHE[key]
+    n = n_side ** 3
+    best = None
+    for _ in range(reps):
+        field = np.zeros(padded_shape(dims))
+        t0 = time.perf_counter()
+        orc.fieldize(BOX, dims, field, pos, None, 1.0, 1)
+        t1 = time.perf_counter()
+        spec = rfftn_padded(field, dims)
+        t2 = time.perf_counter()
+        orc.powerspectrum(dims, spec, None, dims, float(n), float(n))
+        t3 = time.perf_counter()
+        cur = dict(deposit=t1 - t0, fft=t2 - t1, binning=t3 - t2, total=t3 - t0)
+        if best is None or cur["total"] < best["total"]:
+            best = cur
+    threads = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
+    return dict(kind=backend, n=n, n_side=n_side, dims=dims, cores=threads, **best)
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+# ----------------------------------------------------------------------------------------
+# the reference arm: the reference's own CPU code on the box's host cores
+# ----------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = WORKLOADS[args.workload]
+    times = []
+    for i in range(args.warmup + args.steps):
+        t = time_cpu_path(wl["kind"], wl, reps=1)
+        if i >= args.warmup:
+            times.append(t)
+    tot = float(np.mean([t["total"] for t in times]))
+    n = times[0]["n"]
+    value = n / tot / 1e6
+    sample = (f"{wl['cpu']['n_side']}^3 {wl['kind']} particles -> {wl['cpu']['dims']}^3 grid per step "
+              f"(same particles per cell and distribution as the workload); "
+              f"FFT stage = pocketfft stand-in, FFTW3 is absent from the image")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": tot * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["label"], "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": times[0]["cores"], "kind": times[0]["kind"],
+                         "sample": sample, "cpu_model": cpu_model(),
+                         "stage_s": {k: float(np.mean([t[k] for t in times])) for k in ("deposit", "fft", "binning")}},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import genpk_b200 as gp
+    from genpk_b200 import api
+    from genpk_b200.distributed import CudaStages, SlabPipeline
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    wl = WORKLOADS[args.workload]
+    n_side, dims = wl["n_side"], wl["dims"]
+    n_total = n_side ** 3
+    nrbins = dims                                                   # gen-pk.cpp:173
+    kind = {"uniform": api.SYNTH_UNIFORM_RANDOM, "clustered": api.SYNTH_CLUSTERED}[wl["kind"]]
+    flags = api.FLAG_FIXED_POINT if args.fixed_point else 0
+    mode = {"auto": api.DEPOSIT_AUTO, "direct": api.DEPOSIT_DIRECT, "sorted": api.DEPOSIT_SORTED,
+            "tiled": api.DEPOSIT_TILED}[args.deposit]
+
+    # this rank's shard: a contiguous index range of the set (an x-slab of the lattice for the
+    # lattice-ordered kinds, an arbitrary subset for the random kind)
+    first = rank * n_total // world
+    count = (rank + 1) * n_total // world - first
+    dpos = torch.empty(3 * count, dtype=torch.float32, device=dev)
+    api.synth_particles_dev(kind, 42, n_side, first, count, BOX, dims, dpos.data_ptr(),
+                            torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    total_mass = float(n_total)
+
+    if world == 1:
+        ctx = gp.Context(dims, local, flags)
+        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        ctx.set_deposit_mode(mode)
+        pipe = None
+
+        def step_device():
+            ctx.grid_zero()
+            ctx.deposit_dev(dpos.data_ptr(), count, 0, 1.0, BOX)
+            ctx.fft()
+            return ctx.power(nrbins, total_mass, total_mass)          # raw sums D2H + normalisation inside
+
+        def step_host(hpos):
+            return ctx.pk_from_particles_ptr(hpos.data_ptr(), count, 1.0, BOX, total_mass, nrbins)
+    else:
+        stages = CudaStages(dims, world, rank, dev, flags)
+        stages.ctx.set_deposit_mode(mode)
+        ctx = stages.ctx
+        pipe = SlabPipeline(dims, stages)
+
+        def step_device():
+            return pipe.pk(dpos, None, 1.0, BOX, total_mass, nrbins)
+
+        def step_host(hpos):
+            d = hpos.to(dev, non_blocking=True)
+            return pipe.pk(d, None, 1.0, BOX, total_mass, nrbins)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident timing ------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        out = step_device()
+    barrier()
+    ctx.stage_reset()
+    launches0 = ctx.launch_count()
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        out = step_device()
+    e1.record()
+    barrier()
+    t_wall1 = time.time()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    launches = ctx.launch_count() - launches0
+    ms_step = ms_total / args.steps
+    value = n_total / (ms_step * 1e-3) / 1e6
+    stage_ms = {}
+    for name, st in (("deposit", api.STAGE_DEPOSIT), ("sort", api.STAGE_SORT), ("fft", api.STAGE_FFT),
+                     ("binning", api.STAGE_POWER)):
+        tot, nrec = ctx.stage_total_ms(st)
+        stage_ms[name] = tot / args.steps if nrec else 0.0
+    ctx.synchronize()
+    power, cnt, keffs = out
+    assert int(cnt.astype(np.int64).sum()) == dims ** 3 - 1, "mode counts do not sum to dims^3-1"
+
+    # ---- end to end from pinned host memory ---------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        k_e2e = args.e2e_steps or min(args.steps, 5)
+        hpos = torch.empty(3 * count, dtype=torch.float32, pin_memory=True)
+        hpos.copy_(dpos)
+        torch.cuda.synchronize()
+        step_host(hpos)
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(k_e2e):
+            out2 = step_host(hpos)
+        a1.record()
+        barrier()
+        ms_e2e = max_over_ranks(a0.elapsed_time(a1)) / k_e2e
+        assert np.array_equal(out2[1], cnt)
+        e2e = {"value": n_total / (ms_e2e * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms_e2e, "steps": k_e2e,
+               "h2d_bytes_per_step": 12 * n_total, "d2h_bytes_per_step": 3 * nrbins * 8 * world,
+               "api": "genpk_pk_from_particles (host float32 positions in, power/count/keffs out)" if world == 1
+               else "SlabPipeline.pk on pinned host shards"}
+        del hpos
+
+    # ---- roofline of the dominant kernel of ours ----------------------------------------------
+    peak, peak_src = measured_peaks()
+    dep_bytes, bin_bytes = algorithmic_bytes(n_total, dims, world)
+    roof = {}
+    for name, nbytes in (("deposit", dep_bytes), ("binning", bin_bytes)):
+        ms = stage_ms[name]
+        ach = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        roof[name] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                      "traffic": None, "ms": ms, "algorithmic_bytes": nbytes}
+    dom = "deposit" if stage_ms["deposit"] >= stage_ms["binning"] else "binning"
+    roofline = dict(roof[dom])
+    roofline["kernel"] = {"deposit": "deposit stage (brick sort + deposit_direct_kernel)",
+                          "binning": "bin_power_kernel"}[dom]
+    roofline["peak_source"] = peak_src
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["label"], "particles": n_total, "grid": dims, "nrbins": nrbins, "box": BOX,
+                   "accumulation": "int64 fixed-point" if args.fixed_point else "fp64 red.add",
+                   "deposit_mode": args.deposit, "parallelism": f"x-slab x{world}" if world > 1 else "single GPU",
+                   "l2": "inputs larger than L2 (no flush needed)"},
+        "pk_time_ms": ms_step,
+        "stage_ms": stage_ms,
+        "deposit_mparticles_per_s": (n_total / (stage_ms["deposit"] * 1e-3) / 1e6) if stage_ms["deposit"] else None,
+        "binning_gcells_per_s": (dims ** 2 * (dims // 2 + 1) / (stage_ms["binning"] * 1e-3) / 1e9)
+        if stage_ms["binning"] else None,
+        "roofline": roofline, "roofline_all": roof,
+        "gpu_launches": int(launches), "cufft_execs_per_step": 1 if world == 1 else 2,
+        "e2e": e2e, "clocks": clocks,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        t = time_cpu_path(wl["kind"], wl, reps=2)
+        line["cpu_baseline"] = {
+            "value": t["n"] / t["total"] / 1e6, "unit": UNIT, "cores": t["cores"], "kind": t["kind"],
+            "sample": f"{t['n_side']}^3 {wl['kind']} particles -> {t['dims']}^3 grid (bounded replica, same particles "
+                      f"per cell); FFT = pocketfft stand-in (FFTW3 absent)",
+            "cpu_model": cpu_model(), "stage_s": {k: t[k] for k in ("deposit", "fft", "binning")}}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        stages.close()
+        dist.destroy_process_group()
+    else:
+        ctx.close()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -235,6 +235,18 @@ class Context:
                                                keffs.ctypes.data), "genpk_pk_from_particles")
         return power, count, keffs
 
+    def pk_from_particles_ptr(self, pos_host_ptr: int, n: int, mass=1.0, boxsize=1.0, total_mass=1.0, nrbins=None,
+                              mass_host_ptr: int = 0):
+        """genpk_pk_from_particles on raw HOST pointers (e.g. a pinned torch tensor)."""
+        nrbins = self.dims if nrbins is None else int(nrbins)
+        power = np.zeros(nrbins, np.float64)
+        count = np.zeros(nrbins, np.int32)
+        keffs = np.zeros(nrbins, np.float64)
+        check(self.lib.genpk_pk_from_particles(self.h, pos_host_ptr, mass_host_ptr or None, int(n), float(mass),
+                                               float(boxsize), float(total_mass), nrbins, power.ctypes.data,
+                                               count.ctypes.data, keffs.ctypes.data), "genpk_pk_from_particles")
+        return power, count, keffs
+
     # parity helpers
     def grid_doubles(self) -> int:
         return self.lib.genpk_grid_doubles(self.h)
