@@ -54,6 +54,8 @@ def parse_args():
     ap.add_argument("--workload", default=os.environ.get("GENPK_WORKLOAD", "c3"), choices=sorted(WORKLOADS))
     ap.add_argument("--fixed-point", action="store_true", help="deterministic int64 accumulation mode")
     ap.add_argument("--deposit", default="auto", choices=["auto", "direct", "sorted", "tiled"])
+    ap.add_argument("--power", default="cached", choices=["cached", "fused"],
+                    help="binning pass: geometry sums cached in the context, or recomputed every call")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
@@ -283,6 +285,7 @@ def run_ours(args):
         ctx = gp.Context(dims, local, flags)
         ctx.set_stream(torch.cuda.current_stream().cuda_stream)
         ctx.set_deposit_mode(mode)
+        ctx.set_power_mode(api.POWER_FUSED if args.power == "fused" else api.POWER_CACHED)
         pipe = None
 
         def step_device():
@@ -296,6 +299,7 @@ def run_ours(args):
     else:
         stages = CudaStages(dims, world, rank, dev, flags)
         stages.ctx.set_deposit_mode(mode)
+        stages.ctx.set_power_mode(api.POWER_FUSED if args.power == "fused" else api.POWER_CACHED)
         ctx = stages.ctx
         pipe = SlabPipeline(dims, stages)
 
@@ -392,7 +396,7 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl["label"], "particles": n_total, "grid": dims, "nrbins": nrbins, "box": BOX,
                    "accumulation": "int64 fixed-point" if args.fixed_point else "fp64 red.add",
-                   "deposit_mode": args.deposit, "parallelism": f"x-slab x{world}" if world > 1 else "single GPU",
+                   "deposit_mode": args.deposit, "binning_mode": args.power, "parallelism": f"x-slab x{world}" if world > 1 else "single GPU",
                    "l2": "inputs larger than L2 (no flush needed)"},
         "pk_time_ms": ms_step,
         "stage_ms": stage_ms,

@@ -16,7 +16,8 @@ from ._lib import check
 FLAG_FIXED_POINT = 0x1
 FLAG_TWO_FIELDS = 0x2
 FLAG_BINRULE_SOURCE = 0x4
-OPT_DEPOSIT, OPT_SCALE_BITS = 1, 2
+OPT_DEPOSIT, OPT_SCALE_BITS, OPT_POWER = 1, 2, 3
+POWER_CACHED, POWER_FUSED = 0, 1
 DEPOSIT_AUTO, DEPOSIT_DIRECT, DEPOSIT_SORTED, DEPOSIT_TILED = 0, 1, 2, 3
 STAGE_DEPOSIT, STAGE_FFT, STAGE_POWER, STAGE_SORT = 0, 1, 2, 3
 SYNTH_UNIFORM_RANDOM, SYNTH_LATTICE, SYNTH_CLUSTERED = 0, 1, 2
@@ -157,6 +158,9 @@ class Context:
 
     def set_deposit_mode(self, mode: int):
         self.set_option(OPT_DEPOSIT, mode)
+
+    def set_power_mode(self, mode: int):
+        self.set_option(OPT_POWER, mode)
 
     def set_scale_bits(self, bits: int):
         self.set_option(OPT_SCALE_BITS, bits)

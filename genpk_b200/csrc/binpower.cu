@@ -16,6 +16,12 @@
 // histogram when the bin changes.  The nc%32 leftover columns (the Nyquist
 // column for power-of-two grids) are "tail" units with lanes on rows.  Shared
 // histograms are flushed to global with one red.add per non-empty bin per CTA.
+//
+// K and N depend on the grid geometry only, not on the data.  In the default
+// mode they are produced once per (dims, nrbins, block) by the same kernel
+// instantiated without loads (GEOM), cached in the context like an FFT plan's
+// twiddles, and the per-spectrum pass (DATA) carries P alone; the FUSED
+// instantiation does all three in one pass.
 #include "common.cuh"
 
 namespace genpk {
@@ -34,8 +40,10 @@ struct PowerArgs {
     const float *iw1d;
     const uint32_t *thresh;
     float half_bpu;       // first guess of the bin only; the threshold walk makes it exact
-    double *sums;         // [3][nrbins]
+    double *sums;         // [3][nrbins]: P, K, N
 };
+
+enum PowerKind { PK_FUSED = 0, PK_DATA = 1, PK_GEOM = 2 };
 
 __device__ __forceinline__ int kval(int i, int dims) { return i <= dims / 2 ? i : i - dims; }   // powerspectrum.c:33
 
@@ -46,12 +54,16 @@ struct Run {
     unsigned n;
 };
 
+template <int KIND>
 __device__ __forceinline__ void run_flush(const Run &r, int mult, double *sP, double *sK, unsigned *sN)
 {
     if (r.n) {
-        atomicAdd(&sP[r.bin], r.p * mult);
-        atomicAdd(&sK[r.bin], r.k * mult);
-        atomicAdd(&sN[r.bin], r.n * (unsigned)mult);
+        if (KIND != PK_GEOM)
+            atomicAdd(&sP[r.bin], r.p * mult);
+        if (KIND != PK_DATA) {
+            atomicAdd(&sK[r.bin], r.k * mult);
+            atomicAdd(&sN[r.bin], r.n * (unsigned)mult);
+        }
     }
 }
 
@@ -72,7 +84,7 @@ __device__ __forceinline__ void run_seek(Run &r, unsigned k2, const unsigned *sT
     r.n = 0;
 }
 
-template <bool CROSS>
+template <int KIND, bool CROSS>
 __device__ __forceinline__ void run_add(Run &r, unsigned k2, double2 va, double2 vb, float fwin, int mult,
                                         const unsigned *sT, int nrbins, float half_bpu, double *sP, double *sK,
                                         unsigned *sN)
@@ -80,22 +92,25 @@ __device__ __forceinline__ void run_add(Run &r, unsigned k2, double2 va, double2
     if (k2 == 0)
         return;                                             // DC mode, powerspectrum.c:63
     if (k2 < r.lo || k2 >= r.hi) {
-        run_flush(r, mult, sP, sK, sN);
+        run_flush<KIND>(r, mult, sP, sK, sN);
         run_seek(r, k2, sT, nrbins, half_bpu, r.hi == 0);
     }
-    const double mod2 = CROSS ? fma(va.x, vb.x, va.y * vb.y) : fma(va.x, va.x, va.y * va.y);
-    double w = (double)fwin;                                // float product promoted, fieldize.cpp:132
-    w = w * w;                                              // invwindow() = prod^2
-    w = w * w;                                              // pow(invwindow,2), powerspectrum.c:68
-    r.p = fma(mod2, w, r.p);
-    r.k += sqrt((double)k2);
+    if (KIND != PK_GEOM) {
+        const double mod2 = CROSS ? fma(va.x, vb.x, va.y * vb.y) : fma(va.x, va.x, va.y * va.y);
+        double w = (double)fwin;                            // float product promoted, fieldize.cpp:132
+        w = w * w;                                          // invwindow() = prod^2
+        w = w * w;                                          // pow(invwindow,2), powerspectrum.c:68
+        r.p = fma(mod2, w, r.p);
+    }
+    if (KIND != PK_DATA)
+        r.k += sqrt((double)k2);
     r.n += 1;
 }
 
 constexpr int POWER_THREADS = 256;
-constexpr int POWER_UNROLL = 4;
+constexpr int POWER_UNROLL = 8;
 
-template <bool CROSS>
+template <int KIND, bool CROSS>
 __global__ void __launch_bounds__(POWER_THREADS) bin_power_kernel(PowerArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -144,11 +159,13 @@ __global__ void __launch_bounds__(POWER_THREADS) bin_power_kernel(PowerArgs A)
             const double2 *pb = CROSS ? A.b + row0 + kz : nullptr;
             for (int j0 = jbeg; j0 < jend; j0 += POWER_UNROLL) {
                 double2 va[POWER_UNROLL], vb[POWER_UNROLL];
+                if (KIND != PK_GEOM) {
 #pragma unroll
-                for (int t = 0; t < POWER_UNROLL; t++) {
-                    if (j0 + t < jend) {
-                        va[t] = __ldcs(pa + (size_t)(j0 - jbeg + t) * A.nc);
-                        if (CROSS) vb[t] = __ldcs(pb + (size_t)(j0 - jbeg + t) * A.nc);
+                    for (int t = 0; t < POWER_UNROLL; t++) {
+                        if (j0 + t < jend) {
+                            va[t] = __ldcs(pa + (size_t)(j0 - jbeg + t) * A.nc);
+                            if (CROSS) vb[t] = __ldcs(pb + (size_t)(j0 - jbeg + t) * A.nc);
+                        }
                     }
                 }
 #pragma unroll
@@ -156,12 +173,12 @@ __global__ void __launch_bounds__(POWER_THREADS) bin_power_kernel(PowerArgs A)
                     if (j0 + t < jend) {
                         const int kj = kval(A.mid0 + j0 + t, A.dims);
                         const float fwin = __fmul_rn(__fmul_rn(fi, sW[abs(kj)]), fz);   // (iwx*iwy)*iwz in float
-                        run_add<CROSS>(r, base2 + (unsigned)(kj * kj), va[t], vb[t], fwin, mult, sT, A.nrbins,
-                                       A.half_bpu, sP, sK, sN);
+                        run_add<KIND, CROSS>(r, base2 + (unsigned)(kj * kj), va[t], vb[t], fwin, mult, sT, A.nrbins,
+                                             A.half_bpu, sP, sK, sN);
                     }
                 }
             }
-            run_flush(r, mult, sP, sK, sN);
+            run_flush<KIND>(r, mult, sP, sK, sN);
         } else {
             // ---- tail unit: lane = mid row, walk over the leftover kz columns ----
             for (int jb = jbeg; jb < jend; jb += 32) {
@@ -173,12 +190,15 @@ __global__ void __launch_bounds__(POWER_THREADS) bin_power_kernel(PowerArgs A)
                     const size_t row = ((size_t)o * A.n_mid + j) * A.nc;
                     for (int kz = A.n_panels * 32; kz < A.nc; kz++) {
                         const int mult = (kz == 0 || kz == half) ? 1 : 2;
-                        const double2 va = __ldcs(A.a + row + kz);
-                        const double2 vb = CROSS ? __ldcs(A.b + row + kz) : va;
+                        double2 va = make_double2(0.0, 0.0), vb = va;
+                        if (KIND != PK_GEOM) {
+                            va = __ldcs(A.a + row + kz);
+                            vb = CROSS ? __ldcs(A.b + row + kz) : va;
+                        }
                         r.bin = 0; r.lo = 0; r.hi = 0; r.p = 0.0; r.k = 0.0; r.n = 0;
-                        run_add<CROSS>(r, base2 + (unsigned)(kz * kz), va, vb, __fmul_rn(fij, sW[kz]), mult, sT,
-                                       A.nrbins, A.half_bpu, sP, sK, sN);
-                        run_flush(r, mult, sP, sK, sN);
+                        run_add<KIND, CROSS>(r, base2 + (unsigned)(kz * kz), va, vb, __fmul_rn(fij, sW[kz]), mult, sT,
+                                             A.nrbins, A.half_bpu, sP, sK, sN);
+                        run_flush<KIND>(r, mult, sP, sK, sN);
                     }
                 }
             }
@@ -186,8 +206,9 @@ __global__ void __launch_bounds__(POWER_THREADS) bin_power_kernel(PowerArgs A)
     }
     __syncthreads();
     for (int i = threadIdx.x; i < A.nrbins; i += POWER_THREADS) {
-        if (sN[i]) {
+        if (KIND != PK_GEOM && sP[i] != 0.0)
             atomicAdd(&A.sums[i], sP[i]);
+        if (KIND != PK_DATA && sN[i]) {
             atomicAdd(&A.sums[A.nrbins + i], sK[i]);
             atomicAdd(&A.sums[2 * A.nrbins + i], (double)sN[i]);     // exact: integers < 2^53
         }
@@ -204,11 +225,14 @@ int ensure_tables(genpk_ctx *ctx, int nrbins)
     if (ctx->d_thresh) cudaFree(ctx->d_thresh);
     if (ctx->d_iw1d) cudaFree(ctx->d_iw1d);
     if (ctx->d_sums) cudaFree(ctx->d_sums);
+    if (ctx->d_geom) cudaFree(ctx->d_geom);
     if (ctx->h_sums) cudaFreeHost(ctx->h_sums);
-    ctx->d_thresh = nullptr; ctx->d_iw1d = nullptr; ctx->d_sums = nullptr; ctx->h_sums = nullptr;
+    ctx->d_thresh = nullptr; ctx->d_iw1d = nullptr; ctx->d_sums = nullptr; ctx->h_sums = nullptr; ctx->d_geom = nullptr;
+    ctx->geom_valid = false;
     GENPK_CUDA_OK(cudaMalloc(&ctx->d_thresh, ctx->tables.thresh.size() * sizeof(uint32_t)));
     GENPK_CUDA_OK(cudaMalloc(&ctx->d_iw1d, ctx->tables.iw1d.size() * sizeof(float)));
     GENPK_CUDA_OK(cudaMalloc(&ctx->d_sums, (size_t)3 * nrbins * sizeof(double)));
+    GENPK_CUDA_OK(cudaMalloc(&ctx->d_geom, (size_t)3 * nrbins * sizeof(double)));
     GENPK_CUDA_OK(cudaMallocHost(&ctx->h_sums, (size_t)3 * nrbins * sizeof(double)));
     ctx->sums_cap = nrbins;
     GENPK_CUDA_OK(cudaMemcpyAsync(ctx->d_thresh, ctx->tables.thresh.data(), ctx->tables.thresh.size() * sizeof(uint32_t),
@@ -216,6 +240,27 @@ int ensure_tables(genpk_ctx *ctx, int nrbins)
     GENPK_CUDA_OK(cudaMemcpyAsync(ctx->d_iw1d, ctx->tables.iw1d.data(), ctx->tables.iw1d.size() * sizeof(float),
                                   cudaMemcpyHostToDevice, ctx->stream));
     GENPK_CUDA_OK(cudaStreamSynchronize(ctx->stream));     // the host vectors may be rebuilt later
+    return 0;
+}
+
+template <int KIND, bool CROSS>
+static int launch_power(genpk_ctx *ctx, const PowerArgs &A, size_t smem)
+{
+    auto kern = bin_power_kernel<KIND, CROSS>;
+    GENPK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    GENPK_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, POWER_THREADS, smem));
+    if (per_sm < 1) {
+        set_error("bin_power: %zu bytes of shared memory do not fit (nrbins=%d dims=%d)", smem, A.nrbins, A.dims);
+        return 1;
+    }
+    long long ctas = (long long)per_sm * ctx->sm_count;
+    const long long need = (A.n_units + POWER_THREADS / 32 - 1) / (POWER_THREADS / 32);
+    if (ctas > need) ctas = need;
+    if (ctas < 1) ctas = 1;
+    kern<<<(int)ctas, POWER_THREADS, smem, ctx->stream>>>(A);
+    ctx->launches++;
+    GENPK_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
@@ -245,26 +290,34 @@ int power_raw(genpk_ctx *ctx, const double *spec_a, const double *spec_b, int n_
     A.thresh = ctx->d_thresh;
     A.half_bpu = nrbins > 1 ? (float)(0.5 * (nrbins - 1) / log(sqrt(3.0) * A.dims / 2.0)) : 0.f;
     A.sums = sums_dev;
-    GENPK_CUDA_OK(cudaMemsetAsync(sums_dev, 0, (size_t)3 * nrbins * sizeof(double), ctx->stream));
-
     const size_t smem = (size_t)nrbins * (8 + 8 + 4) + (size_t)(nrbins + 1) * 4 + (size_t)(A.dims / 2 + 1) * 4 + 16;
     const bool cross = spec_b != spec_a;
-    auto kern = cross ? bin_power_kernel<true> : bin_power_kernel<false>;
-    GENPK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    GENPK_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, POWER_THREADS, smem));
-    if (per_sm < 1) {
-        set_error("bin_power: %zu bytes of shared memory do not fit (nrbins=%d dims=%d)", smem, nrbins, A.dims);
-        return 1;
+    const size_t sums_bytes = (size_t)3 * nrbins * sizeof(double);
+
+    if (ctx->power_mode == GENPK_POWER_FUSED) {
+        GENPK_CUDA_OK(cudaMemsetAsync(sums_dev, 0, sums_bytes, ctx->stream));
+        return cross ? launch_power<PK_FUSED, true>(ctx, A, smem) : launch_power<PK_FUSED, false>(ctx, A, smem);
     }
-    long long ctas = (long long)per_sm * ctx->sm_count;
-    const long long need = (A.n_units + POWER_THREADS / 32 - 1) / (POWER_THREADS / 32);
-    if (ctas > need) ctas = need;
-    if (ctas < 1) ctas = 1;
-    kern<<<(int)ctas, POWER_THREADS, smem, ctx->stream>>>(A);
-    ctx->launches++;
-    GENPK_CUDA_OK(cudaGetLastError());
-    return 0;
+    // geometry sums cached per block of the spectrum
+    const long long key[5] = {nrbins, n_outer, outer0, n_mid, mid0};
+    bool hit = ctx->geom_valid;
+    for (int i = 0; i < 5 && hit; i++)
+        hit = ctx->geom_key[i] == key[i];
+    if (!hit) {
+        GENPK_CUDA_OK(cudaMemsetAsync(ctx->d_geom, 0, sums_bytes, ctx->stream));
+        PowerArgs G = A;
+        G.sums = ctx->d_geom;
+        if (int rc = launch_power<PK_GEOM, false>(ctx, G, smem))
+            return rc;
+        for (int i = 0; i < 5; i++)
+            ctx->geom_key[i] = key[i];
+        ctx->geom_valid = true;
+    }
+    // P from the data pass; K and N copied from the cache
+    GENPK_CUDA_OK(cudaMemsetAsync(sums_dev, 0, (size_t)nrbins * sizeof(double), ctx->stream));
+    GENPK_CUDA_OK(cudaMemcpyAsync(sums_dev + nrbins, ctx->d_geom + nrbins, (size_t)2 * nrbins * sizeof(double),
+                                  cudaMemcpyDeviceToDevice, ctx->stream));
+    return cross ? launch_power<PK_DATA, true>(ctx, A, smem) : launch_power<PK_DATA, false>(ctx, A, smem);
 }
 
 }  // namespace genpk

@@ -127,11 +127,13 @@ void genpk_destroy(genpk_ctx *ctx)
     if (ctx->d_iw1d) cudaFree(ctx->d_iw1d);
     if (ctx->d_thresh) cudaFree(ctx->d_thresh);
     if (ctx->d_sums) cudaFree(ctx->d_sums);
+    if (ctx->d_geom) cudaFree(ctx->d_geom);
     if (ctx->h_sums) cudaFreeHost(ctx->h_sums);
     if (ctx->d_sorted_pos) cudaFree(ctx->d_sorted_pos);
     if (ctx->d_sorted_mass) cudaFree(ctx->d_sorted_mass);
     if (ctx->d_brick_counts) cudaFree(ctx->d_brick_counts);
     if (ctx->d_errors) cudaFree(ctx->d_errors);
+    if (ctx->d_use_sorted) cudaFree(ctx->d_use_sorted);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (int i = 0; i < ST_COUNT; i++)
         for (int s = 0; s < genpk_ctx::EV_SLOTS; s++) {
@@ -159,6 +161,10 @@ int genpk_set_option(genpk_ctx *ctx, int option, int64_t value)
     case GENPK_OPT_SCALE_BITS:
         if (value < 0 || value > 62) break;
         ctx->scale_bits = (int)value;
+        return 0;
+    case GENPK_OPT_POWER:
+        if (value != GENPK_POWER_CACHED && value != GENPK_POWER_FUSED) break;
+        ctx->power_mode = (int)value;
         return 0;
     }
     set_error("genpk_set_option: bad option %d / value %lld", option, (long long)value);
@@ -221,7 +227,7 @@ int genpk_deposit(genpk_ctx *ctx, int which, const float *positions, const float
         // Host particles: chunks go up on the copy stream into two device staging
         // buffers while the previous chunk is being deposited (chunk loop of
         // read_fieldize.cpp:51-93, overlapped).
-        const int64_t chunk = n < ((int64_t)1 << 25) ? n : ((int64_t)1 << 25);
+        const int64_t chunk = n < ((int64_t)1 << 23) ? n : ((int64_t)1 << 23);
         if ((rc = ensure_stage(ctx, chunk, masses != nullptr))) return rc;
         int buf = 0;
         for (int64_t off = 0; off < n && !rc; off += chunk, buf ^= 1) {

@@ -90,6 +90,10 @@ struct genpk_ctx {
     double *d_sums = nullptr;         // 3*nrbins raw sums
     double *h_sums = nullptr;         // pinned
     int sums_cap = 0;
+    int power_mode = GENPK_POWER_CACHED;
+    double *d_geom = nullptr;         // cached geometry sums (K, N) of the last spectrum block
+    bool geom_valid = false;
+    long long geom_key[5] = {0, 0, 0, 0, 0};
 
     // deposit scratch
     float *d_stage_pos[2] = {nullptr, nullptr};
@@ -105,6 +109,7 @@ struct genpk_ctx {
     uint32_t *d_brick_counts = nullptr;   // histogram / cursors
     int64_t brick_cap = 0;
     unsigned long long *d_errors = nullptr;   // device-side counter of rejected particles
+    int *d_use_sorted = nullptr;              // device flag written by the coherence probe
 
     // timing: a ring of event pairs per stage, summed on request (no host sync while recording)
     static constexpr int EV_SLOTS = 128;

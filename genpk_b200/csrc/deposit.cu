@@ -24,6 +24,9 @@ struct DepositArgs {
     size_t plane;          // doubles per x plane = dims*fd
     void *grid;
     unsigned long long *errors;
+    const int *use_sorted; // optional device flag: 1 = read sorted_pos/sorted_mass instead of pos/mass
+    const float *sorted_pos;
+    const float *sorted_mass;
 };
 
 struct AxisCell {
@@ -51,55 +54,151 @@ __device__ __forceinline__ AxisCell axis_cell(float p, double units, int dims)
     return c;
 }
 
-template <bool FIXED>
-__device__ __forceinline__ void add_cell(void *grid, size_t idx, double w, double scale)
-{
-    if (FIXED) {
-        const long long q = __double2ll_rn(__dmul_rn(w, scale));
-        atomicAdd(reinterpret_cast<unsigned long long *>(grid) + idx, (unsigned long long)q);
-    } else {
-        atomicAdd(reinterpret_cast<double *>(grid) + idx, w);     // REDG.E.ADD.F64
+// A contribution is a double (fp64 mode) or llrint(w*2^S) as int64 (fixed-point mode);
+// the quantisation happens per contribution, before any merging, so merged
+// integer sums are bit-identical to eight separate adds.
+template <bool FIXED> struct Acc;
+template <> struct Acc<false> {
+    typedef double type;
+    static __device__ __forceinline__ double make(double w, double) { return w; }
+    static __device__ __forceinline__ void red(void *grid, size_t idx, double v)
+    {
+        atomicAdd(reinterpret_cast<double *>(grid) + idx, v);               // REDG.E.ADD.F64
     }
-}
+};
+template <> struct Acc<true> {
+    typedef long long type;
+    static __device__ __forceinline__ long long make(double w, double scale) { return __double2ll_rn(__dmul_rn(w, scale)); }
+    static __device__ __forceinline__ void red(void *grid, size_t idx, long long v)
+    {
+        atomicAdd(reinterpret_cast<unsigned long long *>(grid) + idx, (unsigned long long)v);   // REDG.E.ADD.64
+    }
+};
 
-// One particle per thread, eight reductions into global memory.
+// One particle per thread, CTA b owns particles [256 b, 256 b + 256): consecutive
+// particles stay consecutive in time, which keeps brick-sorted and snapshot-ordered
+// input L2-local.  Eight reductions per particle, minus the ones merged below.
+//
+// Neighbour merge: in lattice / snapshot order the next particle usually sits one
+// cell further along z, so its four low-z corners are this particle's four high-z
+// corners.  Those four contributions are handed to the next lane by shuffle and
+// leave with its reductions: ~4 instead of 8 red.add per particle on coherent input,
+// unchanged results (the sum per cell is the same set of terms).
 template <bool FIXED>
 __global__ void __launch_bounds__(256) deposit_direct_kernel(DepositArgs a)
 {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < a.n; p += stride) {
-        const float px = a.pos[3 * p], py = a.pos[3 * p + 1], pz = a.pos[3 * p + 2];
-        const double m = a.mass ? (double)a.mass[p] : a.cmass;    // fieldize.cpp:63
-        const AxisCell cx = axis_cell(px, a.units, a.dims);
-        const AxisCell cy = axis_cell(py, a.units, a.dims);
-        const AxisCell cz = axis_cell(pz, a.units, a.dims);
-        int xl = cx.lo - a.x0, xh;
-        bool ok = cx.ok && cy.ok && cz.ok;
-        if (a.ghost) {                       // slab: the +1 neighbour may be the ghost plane
-            ok = ok && xl >= 0 && xl < a.nx;
-            xh = xl + 1;
-        } else {
-            xh = cx.hi;
-        }
-        if (!ok) {
-            atomicAdd(a.errors, 1ull);
-            continue;
-        }
-        const size_t bx0 = a.plane * (size_t)xl, bx1 = a.plane * (size_t)xh;
-        const size_t by0 = (size_t)a.fd * cy.lo, by1 = (size_t)a.fd * cy.hi;
-        const double mx0 = __dmul_rn(m, cx.wl), mx1 = __dmul_rn(m, cx.wh);
-        const double w00 = __dmul_rn(mx0, cy.wl), w10 = __dmul_rn(mx1, cy.wl);
-        const double w01 = __dmul_rn(mx0, cy.wh), w11 = __dmul_rn(mx1, cy.wh);
-        // order of fieldize.cpp:77-92
-        add_cell<FIXED>(a.grid, bx0 + by0 + cz.lo, __dmul_rn(w00, cz.wl), a.scale);
-        add_cell<FIXED>(a.grid, bx1 + by0 + cz.lo, __dmul_rn(w10, cz.wl), a.scale);
-        add_cell<FIXED>(a.grid, bx0 + by1 + cz.lo, __dmul_rn(w01, cz.wl), a.scale);
-        add_cell<FIXED>(a.grid, bx1 + by1 + cz.lo, __dmul_rn(w11, cz.wl), a.scale);
-        add_cell<FIXED>(a.grid, bx0 + by0 + cz.hi, __dmul_rn(w00, cz.wh), a.scale);
-        add_cell<FIXED>(a.grid, bx1 + by0 + cz.hi, __dmul_rn(w10, cz.wh), a.scale);
-        add_cell<FIXED>(a.grid, bx0 + by1 + cz.hi, __dmul_rn(w01, cz.wh), a.scale);
-        add_cell<FIXED>(a.grid, bx1 + by1 + cz.hi, __dmul_rn(w11, cz.wh), a.scale);
+    typedef typename Acc<FIXED>::type acc_t;
+    const int lane = threadIdx.x & 31;
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = p < a.n;
+    const float *pos = a.pos;
+    const float *mass = a.mass;
+    if (a.use_sorted && *a.use_sorted) {       // device-side choice made by the coherence probe
+        pos = a.sorted_pos;
+        mass = a.mass ? a.sorted_mass : nullptr;
     }
+    float px = 0.f, py = 0.f, pz = 0.f;
+    double m = a.cmass;
+    if (live) {
+        px = pos[3 * p];
+        py = pos[3 * p + 1];
+        pz = pos[3 * p + 2];
+        if (mass)
+            m = (double)mass[p];                                          // fieldize.cpp:63
+    }
+    const AxisCell cx = axis_cell(px, a.units, a.dims);
+    const AxisCell cy = axis_cell(py, a.units, a.dims);
+    const AxisCell cz = axis_cell(pz, a.units, a.dims);
+    int xl = cx.lo - a.x0, xh;
+    bool ok = live && cx.ok && cy.ok && cz.ok;
+    if (a.ghost) {                           // slab: the +1 neighbour may be the ghost plane
+        ok = ok && xl >= 0 && xl < a.nx;
+        xh = xl + 1;
+    } else {
+        xh = cx.hi;
+    }
+    if (live && !ok)
+        atomicAdd(a.errors, 1ull);
+    const double mx0 = __dmul_rn(m, cx.wl), mx1 = __dmul_rn(m, cx.wh);
+    const double w00 = __dmul_rn(mx0, cy.wl), w10 = __dmul_rn(mx1, cy.wl);
+    const double w01 = __dmul_rn(mx0, cy.wh), w11 = __dmul_rn(mx1, cy.wh);
+    // weights in the order of fieldize.cpp:77-84
+    acc_t lo[4], hi[4];
+    lo[0] = Acc<FIXED>::make(__dmul_rn(w00, cz.wl), a.scale);
+    lo[1] = Acc<FIXED>::make(__dmul_rn(w10, cz.wl), a.scale);
+    lo[2] = Acc<FIXED>::make(__dmul_rn(w01, cz.wl), a.scale);
+    lo[3] = Acc<FIXED>::make(__dmul_rn(w11, cz.wl), a.scale);
+    hi[0] = Acc<FIXED>::make(__dmul_rn(w00, cz.wh), a.scale);
+    hi[1] = Acc<FIXED>::make(__dmul_rn(w10, cz.wh), a.scale);
+    hi[2] = Acc<FIXED>::make(__dmul_rn(w01, cz.wh), a.scale);
+    hi[3] = Acc<FIXED>::make(__dmul_rn(w11, cz.wh), a.scale);
+
+    // (x,y) column id and z cells; -1/-2 never match
+    const long long col = ((long long)cx.lo * a.dims + cy.lo) * a.dims;
+    const long long key_lo = ok ? col + cz.lo : -1;
+    const long long key_hi = ok ? col + cz.hi : -2;
+    const long long next_lo = __shfl_down_sync(0xffffffffu, key_lo, 1);
+    const bool give = lane < 31 && next_lo == key_hi;      // my high-z corners are the next lane's low-z corners
+    const bool take = __shfl_up_sync(0xffffffffu, (int)give, 1) && lane > 0;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const acc_t from_prev = __shfl_up_sync(0xffffffffu, hi[c], 1);
+        if (take)
+            lo[c] += from_prev;
+    }
+    if (!ok)
+        return;
+    const size_t bx0 = a.plane * (size_t)xl, bx1 = a.plane * (size_t)xh;
+    const size_t by0 = (size_t)a.fd * cy.lo, by1 = (size_t)a.fd * cy.hi;
+    // cell order of fieldize.cpp:85-92
+    Acc<FIXED>::red(a.grid, bx0 + by0 + cz.lo, lo[0]);
+    Acc<FIXED>::red(a.grid, bx1 + by0 + cz.lo, lo[1]);
+    Acc<FIXED>::red(a.grid, bx0 + by1 + cz.lo, lo[2]);
+    Acc<FIXED>::red(a.grid, bx1 + by1 + cz.lo, lo[3]);
+    if (!give) {
+        Acc<FIXED>::red(a.grid, bx0 + by0 + cz.hi, hi[0]);
+        Acc<FIXED>::red(a.grid, bx1 + by0 + cz.hi, hi[1]);
+        Acc<FIXED>::red(a.grid, bx0 + by1 + cz.hi, hi[2]);
+        Acc<FIXED>::red(a.grid, bx1 + by1 + cz.hi, hi[3]);
+    }
+}
+
+// Spatial coherence probe: are consecutive particles near each other on the grid?
+// Samples pairs (i, i+1) across the run; writes *use_sorted = 0 when at least 60 % of
+// them are within 4 cells in every axis (lattice, snapshot or already-sorted order:
+// sorting would only cost bandwidth), else 1.  The decision stays on the device: the
+// sort kernels return at once when it is 0 and the deposit reads the original array.
+__global__ void __launch_bounds__(1024) coherence_probe_kernel(const float *pos, int64_t n, double units, int dims,
+                                                               int *use_sorted)
+{
+    __shared__ int s_near;
+    if (threadIdx.x == 0)
+        s_near = 0;
+    __syncthreads();
+    const int samples = 8 * 1024;
+    int near = 0, tried = 0;
+    for (int s = threadIdx.x; s < samples; s += blockDim.x) {
+        const int64_t i = (int64_t)((double)s / samples * (double)(n - 1));
+        if (i + 1 >= n)
+            continue;
+        tried++;
+        bool all = true;
+        for (int ax = 0; ax < 3; ax++) {
+            const AxisCell c0 = axis_cell(pos[3 * i + ax], units, dims);
+            const AxisCell c1 = axis_cell(pos[3 * (i + 1) + ax], units, dims);
+            int d = abs(c0.lo - c1.lo);
+            d = min(d, dims - d);
+            all = all && d <= 4;
+        }
+        near += all ? 1 : 0;
+    }
+    atomicAdd(&s_near, near);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int total = (int)min((int64_t)samples, n > 1 ? n - 1 : 0);
+        *use_sorted = (total > 0 && s_near * 10 >= total * 6) ? 0 : 1;
+    }
+    (void)tried;
 }
 
 // ---------------------------------------------------------------------------------
@@ -127,9 +226,11 @@ constexpr int SORT_ITEMS = 8;
 constexpr int SORT_MAX_KEYS = 4096;   // 12 B of shared memory per key in the scatter
 
 __global__ void __launch_bounds__(SORT_THREADS) brick_histogram_kernel(const float *pos, int64_t n, BrickMap bm,
-                                                                      unsigned long long *counts)
+                                                                      unsigned long long *counts, const int *enabled)
 {
     extern __shared__ unsigned s_hist[];
+    if (enabled && !*enabled)           // the coherence probe said sorting is not needed
+        return;
     for (int k = threadIdx.x; k < bm.nbricks; k += SORT_THREADS)
         s_hist[k] = 0;
     __syncthreads();
@@ -173,9 +274,11 @@ __global__ void __launch_bounds__(1024) exclusive_scan_kernel(unsigned long long
 
 __global__ void __launch_bounds__(SORT_THREADS) brick_scatter_kernel(const float *pos, const float *mass, int64_t n,
                                                                     BrickMap bm, unsigned long long *cursors,
-                                                                    float *out_pos, float *out_mass)
+                                                                    float *out_pos, float *out_mass, const int *enabled)
 {
     extern __shared__ unsigned long long s_mem[];
+    if (enabled && !*enabled)
+        return;
     unsigned long long *s_base = s_mem;                                  // [nbricks]
     unsigned *s_cnt = reinterpret_cast<unsigned *>(s_mem + bm.nbricks);  // [nbricks]
     for (int k = threadIdx.x; k < bm.nbricks; k += SORT_THREADS)
@@ -230,7 +333,11 @@ static int launch_direct(genpk_ctx *ctx, const DepositArgs &a)
         return 0;
     const int threads = 256;
     const int64_t want = (a.n + threads - 1) / threads;
-    const int blocks = (int)(want < (int64_t)ctx->sm_count * 32 ? want : (int64_t)ctx->sm_count * 32);
+    if (want > 0x7fffffffLL) {
+        set_error("deposit: %lld particles in one call exceed the launch grid; split the call", (long long)a.n);
+        return 1;
+    }
+    const int blocks = (int)want;
     if (ctx->fixed)
         deposit_direct_kernel<true><<<blocks, threads, 0, ctx->stream>>>(a);
     else
@@ -280,7 +387,7 @@ __global__ void copy_counts_kernel(const unsigned long long *in, int64_t *out, i
 }
 
 static int sort_by_brick(genpk_ctx *ctx, const float *pos, const float *mass, int64_t n, const BrickMap &bm,
-                         float *out_pos, float *out_mass, int64_t *counts_out)
+                         float *out_pos, float *out_mass, int64_t *counts_out, const int *enabled)
 {
     if (bm.nbricks > ctx->brick_cap) {
         if (ctx->d_brick_counts) cudaFree(ctx->d_brick_counts);
@@ -294,7 +401,7 @@ static int sort_by_brick(genpk_ctx *ctx, const float *pos, const float *mass, in
     const int64_t per_block = (int64_t)SORT_THREADS * SORT_ITEMS;
     const int blocks = (int)((n + per_block - 1) / per_block);
     if (blocks > 0) {
-        brick_histogram_kernel<<<blocks, SORT_THREADS, bm.nbricks * sizeof(unsigned), ctx->stream>>>(pos, n, bm, counts);
+        brick_histogram_kernel<<<blocks, SORT_THREADS, bm.nbricks * sizeof(unsigned), ctx->stream>>>(pos, n, bm, counts, enabled);
         ctx->launches++;
     }
     if (counts_out) {
@@ -306,14 +413,14 @@ static int sort_by_brick(genpk_ctx *ctx, const float *pos, const float *mass, in
     if (blocks > 0) {
         const size_t smem = (size_t)bm.nbricks * (sizeof(unsigned long long) + sizeof(unsigned));
         brick_scatter_kernel<<<blocks, SORT_THREADS, smem, ctx->stream>>>(pos, mass, n, bm, counts, out_pos,
-                                                                          mass ? out_mass : nullptr);
+                                                                          mass ? out_mass : nullptr, enabled);
         ctx->launches++;
     }
     GENPK_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
-static int ensure_sorted_scratch(genpk_ctx *ctx, int64_t n)
+static int ensure_sorted_scratch(genpk_ctx *ctx, int64_t n, bool with_mass)
 {
     if (n > ctx->sorted_cap) {
         if (ctx->d_sorted_pos) cudaFree(ctx->d_sorted_pos);
@@ -322,9 +429,12 @@ static int ensure_sorted_scratch(genpk_ctx *ctx, int64_t n)
         ctx->d_sorted_mass = nullptr;
         ctx->sorted_cap = 0;
         GENPK_CUDA_OK(cudaMalloc(&ctx->d_sorted_pos, (size_t)n * 3 * sizeof(float)));
-        GENPK_CUDA_OK(cudaMalloc(&ctx->d_sorted_mass, (size_t)n * sizeof(float)));
         ctx->sorted_cap = n;
     }
+    if (with_mass && !ctx->d_sorted_mass)
+        GENPK_CUDA_OK(cudaMalloc(&ctx->d_sorted_mass, (size_t)ctx->sorted_cap * sizeof(float)));
+    if (!ctx->d_use_sorted)
+        GENPK_CUDA_OK(cudaMalloc(&ctx->d_use_sorted, sizeof(int)));
     return 0;
 }
 
@@ -340,7 +450,7 @@ int route_particles(genpk_ctx *ctx, const float *pos, const float *mass, int64_t
     bm.by = g.dims;
     bm.nby = 1;
     bm.nbricks = g.nranks;
-    return sort_by_brick(ctx, pos, mass, n, bm, spos, smass, counts);
+    return sort_by_brick(ctx, pos, mass, n, bm, spos, smass, counts, nullptr);
 }
 
 int deposit_device(genpk_ctx *ctx, int which, const float *pos, const float *masses, int64_t n,
@@ -368,26 +478,45 @@ int deposit_device(genpk_ctx *ctx, int which, const float *pos, const float *mas
     a.plane = g.plane();
     a.grid = ctx->grid[which];
     a.errors = ctx->d_errors;
+    a.use_sorted = nullptr;
+    a.sorted_pos = nullptr;
+    a.sorted_mass = nullptr;
     if (ctx->fixed)
         ctx->grid_is_fixed[which] = true;
 
+    // DIRECT: reductions straight from the caller's order.  SORTED: always brick-sort
+    // first.  AUTO: nothing to gain from sorting when the owned grid fits in L2;
+    // otherwise a device-side probe of spatial coherence decides, without a host sync.
     int mode = ctx->deposit_mode;
-    if (mode == GENPK_DEPOSIT_AUTO || mode == GENPK_DEPOSIT_TILED) {
-        // Bricks pay off when the owned grid does not fit in L2.
-        const size_t grid_bytes = g.grid_doubles() * sizeof(double);
-        mode = (ctx->l2_bytes && grid_bytes <= ctx->l2_bytes / 2) ? GENPK_DEPOSIT_DIRECT : GENPK_DEPOSIT_SORTED;
-    }
-    if (mode == GENPK_DEPOSIT_SORTED) {
+    const size_t grid_bytes = g.grid_doubles() * sizeof(double);
+    const bool fits_l2 = ctx->l2_bytes && grid_bytes <= ctx->l2_bytes / 2;
+    if (mode == GENPK_DEPOSIT_TILED)
+        mode = GENPK_DEPOSIT_AUTO;
+    if (mode == GENPK_DEPOSIT_AUTO && fits_l2)
+        mode = GENPK_DEPOSIT_DIRECT;
+    if (mode != GENPK_DEPOSIT_DIRECT) {
         const BrickMap bm = choose_bricks(ctx, a.units);
         if (bm.nbricks > 1 && bm.nbricks <= SORT_MAX_KEYS) {
             stage_begin(ctx, ST_SORT);
-            if (int rc = ensure_sorted_scratch(ctx, n))
+            if (int rc = ensure_sorted_scratch(ctx, n, masses != nullptr))
                 return rc;
-            if (int rc = sort_by_brick(ctx, pos, masses, n, bm, ctx->d_sorted_pos, ctx->d_sorted_mass, nullptr))
+            const int *enabled = nullptr;
+            if (mode == GENPK_DEPOSIT_AUTO) {
+                coherence_probe_kernel<<<1, 1024, 0, ctx->stream>>>(pos, n, a.units, g.dims, ctx->d_use_sorted);
+                ctx->launches++;
+                enabled = ctx->d_use_sorted;
+            }
+            if (int rc = sort_by_brick(ctx, pos, masses, n, bm, ctx->d_sorted_pos, ctx->d_sorted_mass, nullptr, enabled))
                 return rc;
             stage_end(ctx, ST_SORT);
-            a.pos = ctx->d_sorted_pos;
-            a.mass = masses ? ctx->d_sorted_mass : nullptr;
+            if (enabled) {
+                a.use_sorted = enabled;
+                a.sorted_pos = ctx->d_sorted_pos;
+                a.sorted_mass = ctx->d_sorted_mass;
+            } else {
+                a.pos = ctx->d_sorted_pos;
+                a.mass = masses ? ctx->d_sorted_mass : nullptr;
+            }
         }
     }
     return launch_direct(ctx, a);
@@ -446,9 +575,12 @@ int fieldize_host_shim(double boxsize, int dims, double *out, int64_t n, const f
         a.plane = (size_t)dims * fd;
         a.grid = d_grid;
         a.errors = d_err;
+        a.use_sorted = nullptr;
+        a.sorted_pos = nullptr;
+        a.sorted_mass = nullptr;
         const int threads = 256;
-        int64_t blocks = (n + threads - 1) / threads;
-        if (blocks > 148 * 32) blocks = 148 * 32;
+        const int64_t blocks = (n + threads - 1) / threads;
+        if (blocks > 0x7fffffffLL) break;
         deposit_direct_kernel<false><<<(int)blocks, threads>>>(a);
         if (cudaGetLastError() != cudaSuccess) break;
         if (cudaMemcpy(out, d_grid, cells * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) break;

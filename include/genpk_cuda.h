@@ -49,6 +49,12 @@ extern "C" {
 #define GENPK_DEPOSIT_SORTED     2     /* counting sort into L2-sized bricks, then deposit   */
 #define GENPK_DEPOSIT_TILED      3     /* sort into bricks, shared-memory tile accumulation  */
 #define GENPK_OPT_SCALE_BITS     2     /* fixed-point mode: q = llrint(w * 2^bits), default 40 */
+/* ---- binning pass selection (genpk_set_option(ctx, GENPK_OPT_POWER, v)) ------------ */
+#define GENPK_OPT_POWER          3
+#define GENPK_POWER_CACHED       0     /* sum|k| and mode counts per bin depend on the grid only: computed
+                                          on the GPU once per (dims, nrbins) and cached in the context;
+                                          the per-spectrum pass accumulates P alone (default)          */
+#define GENPK_POWER_FUSED        1     /* P, sum|k| and counts in one pass every call                  */
 
 typedef struct genpk_ctx genpk_ctx;
 

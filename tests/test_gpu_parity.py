@@ -248,7 +248,9 @@ def test_powerspectrum_vs_oracle(orc, dims, nrbins):
         _, pr, cr, kr = orc.powerspectrum(dims, a, other, nrbins, 3.5, tm2)
         p, c, k = np.empty(nrbins), np.empty(nrbins, np.int32), np.empty(nrbins)
         gp.powerspectrum(dims, a, a if other is None else other, nrbins, p, c, k, 3.5, tm2)
-        assert np.array_equal(c, cr) and c.sum() == dims ** 3 - 1
+        assert np.array_equal(c, cr)
+        if dims % 2 == 0:
+            assert c.sum() == dims ** 3 - 1
         scale = np.abs(pr).max()
         np.testing.assert_allclose(p, pr, rtol=PK_RTOL if other is None else 1e-4, atol=1e-10 * scale)
         np.testing.assert_allclose(k, kr, rtol=1e-12)

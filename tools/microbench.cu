@@ -103,6 +103,44 @@ __global__ void match_kernel(int *out, int nops)
         out[0] = acc;
 }
 
+// TMA bulk reduction: cp.reduce.async.bulk.global.shared::cta.add.f64 of `bytes` per op
+// from a CTA-private shared buffer into a window of the grid.  One elected thread per
+// warp issues; span_cells bounds the window (L2-resident or not).
+__global__ void __launch_bounds__(256) bulk_red_kernel(double *grid, size_t span_cells, int bytes, int nops, int coherent)
+{
+    extern __shared__ __align__(128) double s_buf[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cells = bytes / 8;
+    double *mine = s_buf + warp * cells;
+    for (int i = lane; i < cells; i += 32)
+        mine[i] = 1.0;
+    __syncwarp();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (lane == 0) {
+        const unsigned saddr = (unsigned)__cvta_generic_to_shared(mine);
+        uint64_t h = mix64(blockIdx.x * 64ull + warp);
+        size_t base = (size_t)(blockIdx.x * 8 + warp) * (size_t)cells * nops;
+        for (int k = 0; k < nops; k++) {
+            size_t cell;
+            if (coherent) {
+                cell = (base + (size_t)k * cells) % (span_cells - cells);
+            } else {
+                h = mix64(h + k);
+                cell = (h % (span_cells - cells));
+            }
+            cell &= ~(size_t)1;                                   // 16-byte alignment
+            double *dst = grid + cell;
+            asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" ::"l"(dst), "r"(saddr),
+                         "r"(bytes)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            if ((k & 7) == 7)
+                asm volatile("cp.async.bulk.wait_group.read 4;" ::: "memory");
+        }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+}
+
 template <typename F>
 static float time_ms(F f, int reps = 3)
 {
@@ -160,6 +198,18 @@ int main()
             printf("red.f64 random over %6zu MB: %8.3f ms  %7.1f Gred/s\n", span * 8 >> 20, ms, nops / ms / 1e6);
             ms = time_ms([&] { red_kernel<unsigned long long><<<sms * 16, 256>>>((unsigned long long *)g, span, nops, 0, 0); });
             printf("red.u64 random over %6zu MB: %8.3f ms  %7.1f Gred/s\n", span * 8 >> 20, ms, nops / ms / 1e6);
+        }
+        for (size_t span : {(size_t)1 << 22, (size_t)1 << 28}) {
+            for (int bytes : {32, 64, 128, 256, 512, 2048}) {
+                for (int coherent : {0, 1}) {
+                    const int nops = 2048, ctas = sms * 4;
+                    float ms = time_ms([&] { bulk_red_kernel<<<ctas, 256, 8 * bytes>>>(g, span, bytes, nops, coherent); });
+                    double ops = (double)ctas * 8 * nops;
+                    printf("TMA bulk red.f64 %4d B/op %s over %5zu MB: %8.3f ms  %7.2f Gop/s  %8.1f Gcell/s  %7.0f GB/s\n", bytes,
+                           coherent ? "coherent" : "random  ", span * 8 >> 20, ms, ops / ms / 1e6, ops * (bytes / 8) / ms / 1e6,
+                           ops * bytes / ms / 1e6);
+                }
+            }
         }
         for (int dims : {256, 512}) {
             size_t np = (size_t)dims * dims * dims;
