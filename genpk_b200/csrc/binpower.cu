@@ -10,12 +10,21 @@
 // The DC mode is skipped (powerspectrum.c:63).
 //
 // Mapping: persistent warps.  A "panel" unit is 32 consecutive kz (one lane
-// each, so every load is a coalesced 512 B) times JC consecutive mid rows that
+// each, so every load is a coalesced 512 B) times JC consecutive mid steps that
 // the thread walks; along that walk |k| changes slowly, so the thread keeps a
 // run (bin, P, K, N) in registers and only touches the CTA's shared-memory
-// histogram when the bin changes.  The nc%32 leftover columns (the Nyquist
-// column for power-of-two grids) are "tail" units with lanes on rows.  Shared
-// histograms are flushed to global with one red.add per non-empty bin per CTA.
+// histogram when the bin changes.
+//
+// Mirror rows: bin, window and multiplicity depend on |ki|, |kj| only, so the up
+// to four rows (+-ki, +-kj) of one kz share everything but the data.  A step
+// loads all of them (four independent coalesced streams), adds their |delta|^2
+// and does the bin / window / run bookkeeping once.  The outer mirror needs the
+// whole outer axis in the block (always true: x is complete on every rank after
+// the transpose), the mid mirror the whole mid axis (single-rank contexts).
+//
+// The nc%32 leftover columns (the Nyquist column for power-of-two grids) are
+// "tail" units with lanes on rows.  Shared histograms are flushed to global
+// with one red.add per non-empty bin per CTA.
 //
 // K and N depend on the grid geometry only, not on the data.  In the default
 // mode they are produced once per (dims, nrbins, block) by the same kernel
@@ -31,9 +40,11 @@ struct PowerArgs {
     const double2 *b;
     int dims, nc;
     int n_outer, outer0, n_mid, mid0;
+    int mirror_outer, mirror_mid;   // block holds the whole axis: fold +-k rows into one step
+    int n_oc, n_mc;       // outer / mid classes (dims/2+1 when mirrored, else the extent)
     int nrbins;
-    int jc;               // mid rows per unit
-    int n_mchunks;        // ceil(n_mid / jc)
+    int jc;               // mid steps per unit
+    int n_mchunks;        // ceil(n_mc / jc)
     int n_panels;         // nc / 32
     int n_tail;           // nc % 32
     long long n_units;
@@ -84,8 +95,9 @@ __device__ __forceinline__ void run_seek(Run &r, unsigned k2, const unsigned *sT
     r.n = 0;
 }
 
-template <int KIND, bool CROSS>
-__device__ __forceinline__ void run_add(Run &r, unsigned k2, double2 va, double2 vb, float fwin, int mult,
+// mod2sum = sum over the mirror rows of re1*re2+im1*im2; rows = how many there were.
+template <int KIND>
+__device__ __forceinline__ void run_add(Run &r, unsigned k2, double mod2sum, int rows, float fwin, int mult,
                                         const unsigned *sT, int nrbins, float half_bpu, double *sP, double *sK,
                                         unsigned *sN)
 {
@@ -96,19 +108,24 @@ __device__ __forceinline__ void run_add(Run &r, unsigned k2, double2 va, double2
         run_seek(r, k2, sT, nrbins, half_bpu, r.hi == 0);
     }
     if (KIND != PK_GEOM) {
-        const double mod2 = CROSS ? fma(va.x, vb.x, va.y * vb.y) : fma(va.x, va.x, va.y * va.y);
         double w = (double)fwin;                            // float product promoted, fieldize.cpp:132
         w = w * w;                                          // invwindow() = prod^2
         w = w * w;                                          // pow(invwindow,2), powerspectrum.c:68
-        r.p = fma(mod2, w, r.p);
+        r.p = fma(mod2sum, w, r.p);
     }
     if (KIND != PK_DATA)
-        r.k += sqrt((double)k2);
-    r.n += 1;
+        r.k = fma((double)rows, sqrt((double)k2), r.k);
+    r.n += (unsigned)rows;
+}
+
+template <bool CROSS>
+__device__ __forceinline__ double mod2(double2 va, double2 vb)
+{
+    return CROSS ? fma(va.x, vb.x, va.y * vb.y) : fma(va.x, va.x, va.y * va.y);
 }
 
 constexpr int POWER_THREADS = 256;
-constexpr int POWER_UNROLL = 8;
+constexpr int POWER_UNROLL = 2;       // steps in flight per thread: up to 4 rows x 2 steps x 16 B
 
 template <int KIND, bool CROSS>
 __global__ void __launch_bounds__(POWER_THREADS) bin_power_kernel(PowerArgs A)
@@ -136,68 +153,113 @@ __global__ void __launch_bounds__(POWER_THREADS) bin_power_kernel(PowerArgs A)
     const long long warp_global = (long long)blockIdx.x * warps_per_cta + (threadIdx.x >> 5);
     const long long warp_total = (long long)gridDim.x * warps_per_cta;
     const int units_per_chunk = A.n_panels + (A.n_tail ? 1 : 0);
+    const long long row_stride = A.nc;                       // modes per (outer, mid) row
+    const long long outer_stride = (long long)A.n_mid * A.nc;
 
     for (long long u = warp_global; u < A.n_units; u += warp_total) {
         const int p = (int)(u % units_per_chunk);
         const long long oc = u / units_per_chunk;
         const int mc = (int)(oc % A.n_mchunks);
-        const int o = (int)(oc / A.n_mchunks);
+        const int o = (int)(oc / A.n_mchunks);              // outer class
+        // outer rows of this class: o and, when mirrored and distinct, dims-o
+        const int o_b = A.mirror_outer ? (A.dims - o) % A.dims : o;
+        const bool has_ob = o_b != o;
         const int ki = kval(A.outer0 + o, A.dims);
         const float fi = sW[abs(ki)];
-        const int jbeg = mc * A.jc, jend = min(A.n_mid, jbeg + A.jc);
-        const size_t row0 = ((size_t)o * A.n_mid + jbeg) * A.nc;
+        const int mbeg = mc * A.jc, mend = min(A.n_mc, mbeg + A.jc);
         Run r;
         r.bin = 0; r.lo = 0; r.hi = 0; r.p = 0.0; r.k = 0.0; r.n = 0;
 
         if (p < A.n_panels) {
-            // ---- panel unit: lane = kz, walk over mid rows ----
+            // ---- panel unit: lane = kz, walk over mid classes ----
             const int kz = p * 32 + lane;
             const int mult = (kz == 0 || kz == half) ? 1 : 2;          // powerspectrum.c:59-89
             const float fz = sW[kz];
             const unsigned base2 = (unsigned)(ki * ki) + (unsigned)(kz * kz);
-            const double2 *pa = A.a + row0 + kz;
-            const double2 *pb = CROSS ? A.b + row0 + kz : nullptr;
-            for (int j0 = jbeg; j0 < jend; j0 += POWER_UNROLL) {
-                double2 va[POWER_UNROLL], vb[POWER_UNROLL];
+            const size_t oa_off = (size_t)o * outer_stride + kz, ob_off = (size_t)o_b * outer_stride + kz;
+            for (int m0 = mbeg; m0 < mend; m0 += POWER_UNROLL) {
+                double2 va[POWER_UNROLL][4], vb[POWER_UNROLL][4];
+                int rows[POWER_UNROLL];
                 if (KIND != PK_GEOM) {
 #pragma unroll
                     for (int t = 0; t < POWER_UNROLL; t++) {
-                        if (j0 + t < jend) {
-                            va[t] = __ldcs(pa + (size_t)(j0 - jbeg + t) * A.nc);
-                            if (CROSS) vb[t] = __ldcs(pb + (size_t)(j0 - jbeg + t) * A.nc);
+                        const int m = m0 + t;
+                        if (m < mend) {
+                            const int j_b = A.mirror_mid ? (A.dims - m) % A.dims : m;
+                            const bool has_jb = j_b != m;
+                            const size_t ja = (size_t)m * row_stride, jb = (size_t)j_b * row_stride;
+                            va[t][0] = __ldcs(A.a + oa_off + ja);
+                            if (CROSS) vb[t][0] = __ldcs(A.b + oa_off + ja);
+                            if (has_ob) {
+                                va[t][1] = __ldcs(A.a + ob_off + ja);
+                                if (CROSS) vb[t][1] = __ldcs(A.b + ob_off + ja);
+                            }
+                            if (has_jb) {
+                                va[t][2] = __ldcs(A.a + oa_off + jb);
+                                if (CROSS) vb[t][2] = __ldcs(A.b + oa_off + jb);
+                                if (has_ob) {
+                                    va[t][3] = __ldcs(A.a + ob_off + jb);
+                                    if (CROSS) vb[t][3] = __ldcs(A.b + ob_off + jb);
+                                }
+                            }
                         }
                     }
                 }
 #pragma unroll
                 for (int t = 0; t < POWER_UNROLL; t++) {
-                    if (j0 + t < jend) {
-                        const int kj = kval(A.mid0 + j0 + t, A.dims);
+                    const int m = m0 + t;
+                    if (m < mend) {
+                        const int j_b = A.mirror_mid ? (A.dims - m) % A.dims : m;
+                        const bool has_jb = j_b != m;
+                        const int kj = kval(A.mid0 + m, A.dims);
                         const float fwin = __fmul_rn(__fmul_rn(fi, sW[abs(kj)]), fz);   // (iwx*iwy)*iwz in float
-                        run_add<KIND, CROSS>(r, base2 + (unsigned)(kj * kj), va[t], vb[t], fwin, mult, sT, A.nrbins,
-                                             A.half_bpu, sP, sK, sN);
+                        rows[t] = (has_ob ? 2 : 1) * (has_jb ? 2 : 1);
+                        double s = 0.0;
+                        if (KIND != PK_GEOM) {
+                            s = mod2<CROSS>(va[t][0], vb[t][0]);
+                            if (has_ob) s += mod2<CROSS>(va[t][1], vb[t][1]);
+                            if (has_jb) {
+                                s += mod2<CROSS>(va[t][2], vb[t][2]);
+                                if (has_ob) s += mod2<CROSS>(va[t][3], vb[t][3]);
+                            }
+                        }
+                        run_add<KIND>(r, base2 + (unsigned)(kj * kj), s, rows[t], fwin, mult, sT, A.nrbins, A.half_bpu,
+                                      sP, sK, sN);
                     }
                 }
             }
             run_flush<KIND>(r, mult, sP, sK, sN);
         } else {
-            // ---- tail unit: lane = mid row, walk over the leftover kz columns ----
-            for (int jb = jbeg; jb < jend; jb += 32) {
-                const int j = jb + lane;
-                if (j < jend) {
-                    const int kj = kval(A.mid0 + j, A.dims);
+            // ---- tail unit: lane = mid class, walk over the leftover kz columns ----
+            for (int mb = mbeg; mb < mend; mb += 32) {
+                const int m = mb + lane;
+                if (m < mend) {
+                    const int j_b = A.mirror_mid ? (A.dims - m) % A.dims : m;
+                    const bool has_jb = j_b != m;
+                    const int kj = kval(A.mid0 + m, A.dims);
                     const float fij = __fmul_rn(fi, sW[abs(kj)]);
                     const unsigned base2 = (unsigned)(ki * ki) + (unsigned)(kj * kj);
-                    const size_t row = ((size_t)o * A.n_mid + j) * A.nc;
+                    const int rows = (has_ob ? 2 : 1) * (has_jb ? 2 : 1);
+                    const size_t raa = (size_t)o * outer_stride + (size_t)m * row_stride;
+                    const size_t rba = (size_t)o_b * outer_stride + (size_t)m * row_stride;
+                    const size_t rab = (size_t)o * outer_stride + (size_t)j_b * row_stride;
+                    const size_t rbb = (size_t)o_b * outer_stride + (size_t)j_b * row_stride;
                     for (int kz = A.n_panels * 32; kz < A.nc; kz++) {
                         const int mult = (kz == 0 || kz == half) ? 1 : 2;
-                        double2 va = make_double2(0.0, 0.0), vb = va;
+                        double s = 0.0;
                         if (KIND != PK_GEOM) {
-                            va = __ldcs(A.a + row + kz);
-                            vb = CROSS ? __ldcs(A.b + row + kz) : va;
+                            s = mod2<CROSS>(__ldcs(A.a + raa + kz), CROSS ? __ldcs(A.b + raa + kz) : make_double2(0, 0));
+                            if (has_ob)
+                                s += mod2<CROSS>(__ldcs(A.a + rba + kz), CROSS ? __ldcs(A.b + rba + kz) : make_double2(0, 0));
+                            if (has_jb) {
+                                s += mod2<CROSS>(__ldcs(A.a + rab + kz), CROSS ? __ldcs(A.b + rab + kz) : make_double2(0, 0));
+                                if (has_ob)
+                                    s += mod2<CROSS>(__ldcs(A.a + rbb + kz), CROSS ? __ldcs(A.b + rbb + kz) : make_double2(0, 0));
+                            }
                         }
                         r.bin = 0; r.lo = 0; r.hi = 0; r.p = 0.0; r.k = 0.0; r.n = 0;
-                        run_add<KIND, CROSS>(r, base2 + (unsigned)(kz * kz), va, vb, __fmul_rn(fij, sW[kz]), mult, sT,
-                                             A.nrbins, A.half_bpu, sP, sK, sN);
+                        run_add<KIND>(r, base2 + (unsigned)(kz * kz), s, rows, __fmul_rn(fij, sW[kz]), mult, sT, A.nrbins,
+                                      A.half_bpu, sP, sK, sN);
                         run_flush<KIND>(r, mult, sP, sK, sN);
                     }
                 }
@@ -281,11 +343,15 @@ int power_raw(genpk_ctx *ctx, const double *spec_a, const double *spec_b, int n_
     A.n_mid = n_mid;
     A.mid0 = mid0;
     A.nrbins = nrbins;
+    A.mirror_outer = (outer0 == 0 && n_outer == A.dims) ? 1 : 0;
+    A.mirror_mid = (mid0 == 0 && n_mid == A.dims) ? 1 : 0;
+    A.n_oc = A.mirror_outer ? A.dims / 2 + 1 : n_outer;
+    A.n_mc = A.mirror_mid ? A.dims / 2 + 1 : n_mid;
     A.jc = 32;
-    A.n_mchunks = (n_mid + A.jc - 1) / A.jc;
+    A.n_mchunks = (A.n_mc + A.jc - 1) / A.jc;
     A.n_panels = A.nc / 32;
     A.n_tail = A.nc % 32;
-    A.n_units = (long long)n_outer * A.n_mchunks * (A.n_panels + (A.n_tail ? 1 : 0));
+    A.n_units = (long long)A.n_oc * A.n_mchunks * (A.n_panels + (A.n_tail ? 1 : 0));
     A.iw1d = ctx->d_iw1d;
     A.thresh = ctx->d_thresh;
     A.half_bpu = nrbins > 1 ? (float)(0.5 * (nrbins - 1) / log(sqrt(3.0) * A.dims / 2.0)) : 0.f;
