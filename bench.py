@@ -53,9 +53,12 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("GENPK_WORKLOAD", "c3"), choices=sorted(WORKLOADS))
     ap.add_argument("--fixed-point", action="store_true", help="deterministic int64 accumulation mode")
-    ap.add_argument("--deposit", default="auto", choices=["auto", "direct", "sorted", "tiled"])
+    ap.add_argument("--deposit", default="auto", choices=["auto", "direct", "sorted", "march"])
     ap.add_argument("--power", default="cached", choices=["cached", "fused"],
                     help="binning pass: geometry sums cached in the context, or recomputed every call")
+    ap.add_argument("--lattice-hint", action="store_true", help="pass the lattice extents instead of probing them")
+    ap.add_argument("--march-ry", type=int, default=0)
+    ap.add_argument("--march-rx", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
@@ -269,7 +272,7 @@ def run_ours(args):
     kind = {"uniform": api.SYNTH_UNIFORM_RANDOM, "clustered": api.SYNTH_CLUSTERED}[wl["kind"]]
     flags = api.FLAG_FIXED_POINT if args.fixed_point else 0
     mode = {"auto": api.DEPOSIT_AUTO, "direct": api.DEPOSIT_DIRECT, "sorted": api.DEPOSIT_SORTED,
-            "tiled": api.DEPOSIT_TILED}[args.deposit]
+            "march": api.DEPOSIT_MARCH}[args.deposit]
 
     # this rank's shard: a contiguous index range of the set (an x-slab of the lattice for the
     # lattice-ordered kinds, an arbitrary subset for the random kind)
@@ -310,6 +313,13 @@ def run_ours(args):
             d = hpos.to(dev, non_blocking=True)
             return pipe.pk(d, None, 1.0, BOX, total_mass, nrbins)
 
+    if args.lattice_hint and wl["kind"] != "uniform":
+        ctx.set_lattice_hint(n_side, n_side)
+    if args.march_ry:
+        ctx.set_option(api.OPT_MARCH_RY, args.march_ry)
+    if args.march_rx:
+        ctx.set_option(api.OPT_MARCH_RX, args.march_rx)
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -344,8 +354,8 @@ def run_ours(args):
     ms_step = ms_total / args.steps
     value = n_total / (ms_step * 1e-3) / 1e6
     stage_ms = {}
-    for name, st in (("deposit", api.STAGE_DEPOSIT), ("sort", api.STAGE_SORT), ("fft", api.STAGE_FFT),
-                     ("binning", api.STAGE_POWER)):
+    for name, st in (("zero", api.STAGE_ZERO), ("deposit", api.STAGE_DEPOSIT), ("sort", api.STAGE_SORT),
+                     ("fft", api.STAGE_FFT), ("binning", api.STAGE_POWER)):
         tot, nrec = ctx.stage_total_ms(st)
         stage_ms[name] = tot / args.steps if nrec else 0.0
     ctx.synchronize()
@@ -379,14 +389,17 @@ def run_ours(args):
     peak, peak_src = measured_peaks()
     dep_bytes, bin_bytes = algorithmic_bytes(n_total, dims, world)
     roof = {}
+    # the deposit's algorithmic bytes include writing the grid once, so its time includes zeroing it
+    stage_ms["deposit_with_zero"] = stage_ms["deposit"] + stage_ms["zero"]
     for name, nbytes in (("deposit", dep_bytes), ("binning", bin_bytes)):
-        ms = stage_ms[name]
+        ms = stage_ms["deposit_with_zero"] if name == "deposit" else stage_ms[name]
         ach = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
         roof[name] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                       "traffic": None, "ms": ms, "algorithmic_bytes": nbytes}
-    dom = "deposit" if stage_ms["deposit"] >= stage_ms["binning"] else "binning"
+    dom = "deposit" if stage_ms["deposit_with_zero"] >= stage_ms["binning"] else "binning"
     roofline = dict(roof[dom])
-    roofline["kernel"] = {"deposit": "deposit stage (brick sort + deposit_direct_kernel)",
+    roofline["kernel"] = {"deposit": "deposit stage (grid zero + order probe + deposit_march_kernel | brick sort + "
+                                     "deposit_direct_kernel)",
                           "binning": "bin_power_kernel"}[dom]
     roofline["peak_source"] = peak_src
 
@@ -396,11 +409,11 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl["label"], "particles": n_total, "grid": dims, "nrbins": nrbins, "box": BOX,
                    "accumulation": "int64 fixed-point" if args.fixed_point else "fp64 red.add",
-                   "deposit_mode": args.deposit, "binning_mode": args.power, "parallelism": f"x-slab x{world}" if world > 1 else "single GPU",
+                   "deposit_mode": args.deposit, "order_probe": ctx.last_order(), "binning_mode": args.power, "parallelism": f"x-slab x{world}" if world > 1 else "single GPU",
                    "l2": "inputs larger than L2 (no flush needed)"},
         "pk_time_ms": ms_step,
         "stage_ms": stage_ms,
-        "deposit_mparticles_per_s": (n_total / (stage_ms["deposit"] * 1e-3) / 1e6) if stage_ms["deposit"] else None,
+        "deposit_mparticles_per_s": (n_total / (stage_ms["deposit_with_zero"] * 1e-3) / 1e6) if stage_ms["deposit"] else None,
         "binning_gcells_per_s": (dims ** 2 * (dims // 2 + 1) / (stage_ms["binning"] * 1e-3) / 1e9)
         if stage_ms["binning"] else None,
         "roofline": roofline, "roofline_all": roof,

@@ -6,7 +6,7 @@ C ABI of libgenpk_cuda.so.  Device work only happens inside that library.
 from ._lib import GenPKError, build, load, LIB_PATH
 from .api import (Context, fieldize, invwindow, powerspectrum, r2c_3d, nexttwo, grid_dims_for, type_str, print_pk,
                   FLAG_FIXED_POINT, FLAG_TWO_FIELDS, FLAG_BINRULE_SOURCE, DEPOSIT_AUTO, DEPOSIT_DIRECT, DEPOSIT_SORTED,
-                  DEPOSIT_TILED, SYNTH_UNIFORM_RANDOM, SYNTH_LATTICE, SYNTH_CLUSTERED)
+                  DEPOSIT_TILED, DEPOSIT_MARCH, SYNTH_UNIFORM_RANDOM, SYNTH_LATTICE, SYNTH_CLUSTERED)
 
 __all__ = ["GenPKError", "build", "load", "LIB_PATH", "Context", "fieldize", "invwindow", "powerspectrum", "r2c_3d",
            "nexttwo", "grid_dims_for", "type_str", "print_pk"]

@@ -49,6 +49,7 @@ SIGNATURES = {
     "genpk_stage_total_ms": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int64)]),
     "genpk_stage_reset": (C.c_int, [C.c_void_p]),
     "genpk_launch_count": (C.c_int64, [C.c_void_p]),
+    "genpk_last_order": (C.c_int, [C.c_void_p, c_i64p]),
     # 3. slab stages
     "genpk_create_slab": (C.c_void_p, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint]),
     "genpk_route_particles": (C.c_int, [C.c_void_p, c_f32p, c_f32p, C.c_int64, C.c_double, c_f32p, c_f32p, c_i64p]),

@@ -17,9 +17,10 @@ FLAG_FIXED_POINT = 0x1
 FLAG_TWO_FIELDS = 0x2
 FLAG_BINRULE_SOURCE = 0x4
 OPT_DEPOSIT, OPT_SCALE_BITS, OPT_POWER = 1, 2, 3
+OPT_LATTICE_N0, OPT_LATTICE_N1, OPT_MARCH_RY, OPT_MARCH_RX = 4, 5, 6, 7
 POWER_CACHED, POWER_FUSED = 0, 1
-DEPOSIT_AUTO, DEPOSIT_DIRECT, DEPOSIT_SORTED, DEPOSIT_TILED = 0, 1, 2, 3
-STAGE_DEPOSIT, STAGE_FFT, STAGE_POWER, STAGE_SORT = 0, 1, 2, 3
+DEPOSIT_AUTO, DEPOSIT_DIRECT, DEPOSIT_SORTED, DEPOSIT_TILED, DEPOSIT_MARCH = 0, 1, 2, 3, 4
+STAGE_DEPOSIT, STAGE_FFT, STAGE_POWER, STAGE_SORT, STAGE_ZERO = 0, 1, 2, 3, 4
 SYNTH_UNIFORM_RANDOM, SYNTH_LATTICE, SYNTH_CLUSTERED = 0, 1, 2
 FIELD_DIMS = 3072          # gen-pk.cpp:63
 
@@ -158,6 +159,18 @@ class Context:
 
     def set_deposit_mode(self, mode: int):
         self.set_option(OPT_DEPOSIT, mode)
+
+    def set_lattice_hint(self, n0: int, n1: int = 0):
+        """Particle p sits near lattice site (ix,iy,iz), p = (ix*n1 + iy)*n0 + iz (0 = probe)."""
+        self.set_option(OPT_LATTICE_N0, n0)
+        self.set_option(OPT_LATTICE_N1, n1)
+
+    def last_order(self) -> dict:
+        """Verdict of the last order probe (diagnostics)."""
+        out = np.zeros(7, np.int64)
+        check(self.lib.genpk_last_order(self.h, out.ctypes.data), "genpk_last_order")
+        keys = ("coherent", "lattice", "n0", "n1", "score_z", "score_y", "score_x")
+        return {k: int(v) for k, v in zip(keys, out)}
 
     def set_power_mode(self, mode: int):
         self.set_option(OPT_POWER, mode)

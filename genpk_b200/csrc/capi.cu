@@ -133,7 +133,7 @@ void genpk_destroy(genpk_ctx *ctx)
     if (ctx->d_sorted_mass) cudaFree(ctx->d_sorted_mass);
     if (ctx->d_brick_counts) cudaFree(ctx->d_brick_counts);
     if (ctx->d_errors) cudaFree(ctx->d_errors);
-    if (ctx->d_use_sorted) cudaFree(ctx->d_use_sorted);
+    if (ctx->d_order) cudaFree(ctx->d_order);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (int i = 0; i < ST_COUNT; i++)
         for (int s = 0; s < genpk_ctx::EV_SLOTS; s++) {
@@ -155,12 +155,28 @@ int genpk_set_option(genpk_ctx *ctx, int option, int64_t value)
     if (!ctx) { set_error("genpk_set_option: null context"); return 1; }
     switch (option) {
     case GENPK_OPT_DEPOSIT:
-        if (value < GENPK_DEPOSIT_AUTO || value > GENPK_DEPOSIT_TILED) break;
+        if (value < GENPK_DEPOSIT_AUTO || value > GENPK_DEPOSIT_MARCH) break;
         ctx->deposit_mode = (int)value;
         return 0;
     case GENPK_OPT_SCALE_BITS:
         if (value < 0 || value > 62) break;
         ctx->scale_bits = (int)value;
+        return 0;
+    case GENPK_OPT_LATTICE_N0:
+        if (value < 0) break;
+        ctx->lattice_n0 = value;
+        return 0;
+    case GENPK_OPT_LATTICE_N1:
+        if (value < 0) break;
+        ctx->lattice_n1 = value;
+        return 0;
+    case GENPK_OPT_MARCH_RY:
+        if (value < 1 || value > 32) break;
+        ctx->march_ry = (int)value;
+        return 0;
+    case GENPK_OPT_MARCH_RX:
+        if (value < 1 || value > 4096) break;
+        ctx->march_rx = (int)value;
         return 0;
     case GENPK_OPT_POWER:
         if (value != GENPK_POWER_CACHED && value != GENPK_POWER_FUSED) break;
@@ -188,7 +204,9 @@ int genpk_synchronize(genpk_ctx *ctx)
 int genpk_grid_zero(genpk_ctx *ctx, int which)
 {
     if (!check_which(ctx, which, "genpk_grid_zero")) return 1;
+    stage_begin(ctx, ST_ZERO);
     GENPK_CUDA_OK(cudaMemsetAsync(ctx->grid[which], 0, ctx->g.grid_doubles() * sizeof(double), ctx->stream));
+    stage_end(ctx, ST_ZERO);
     ctx->grid_is_fixed[which] = false;
     return 0;
 }
@@ -395,6 +413,13 @@ int genpk_stage_reset(genpk_ctx *ctx)
 }
 
 int64_t genpk_launch_count(const genpk_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int genpk_last_order(const genpk_ctx *ctx, int64_t out[7])
+{
+    if (!ctx || !out) { set_error("genpk_last_order: bad arguments"); return 1; }
+    for (int i = 0; i < 7; i++) out[i] = ctx->last_order[i];
+    return 0;
+}
 
 /* ---------------- slab stages ---------------- */
 

@@ -59,7 +59,7 @@ struct SlabGeom {
     size_t owned_doubles() const { return plane() * (size_t)nx; }
 };
 
-enum Stage { ST_DEPOSIT = 0, ST_FFT = 1, ST_POWER = 2, ST_SORT = 3, ST_COUNT = 4 };
+enum Stage { ST_DEPOSIT = 0, ST_FFT = 1, ST_POWER = 2, ST_SORT = 3, ST_ZERO = 4, ST_COUNT = 5 };
 
 }  // namespace genpk
 
@@ -109,7 +109,10 @@ struct genpk_ctx {
     uint32_t *d_brick_counts = nullptr;   // histogram / cursors
     int64_t brick_cap = 0;
     unsigned long long *d_errors = nullptr;   // device-side counter of rejected particles
-    int *d_use_sorted = nullptr;              // device flag written by the coherence probe
+    void *d_order = nullptr;                  // OrderInfo written by the order probe
+    long long lattice_n0 = 0, lattice_n1 = 0; // caller's hint: particles per lattice row, rows per plane
+    int march_ry = 8, march_rx = 8;           // rows / planes one warp marches over
+    long long last_order[7] = {0, 0, 0, 0, 0, 0, 0};   // last probe verdict (diagnostics)
 
     // timing: a ring of event pairs per stage, summed on request (no host sync while recording)
     static constexpr int EV_SLOTS = 128;

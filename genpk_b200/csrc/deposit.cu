@@ -8,72 +8,9 @@
 //
 // Accumulation is order independent in fixed-point mode (int64 adds of
 // llrint(w*2^S)) and ordinary fp64 red.add otherwise.
-#include "common.cuh"
+#include "deposit.cuh"
 
 namespace genpk {
-
-struct DepositArgs {
-    const float *pos;
-    const float *mass;     // may be null
-    int64_t n;
-    double cmass;
-    double units;          // dims / boxsize
-    double scale;          // 2^scale_bits (fixed-point mode)
-    int dims, fd;
-    int x0, nx, ghost;     // slab: owned planes [x0, x0+nx), ghost plane stored at local index nx
-    size_t plane;          // doubles per x plane = dims*fd
-    void *grid;
-    unsigned long long *errors;
-    const int *use_sorted; // optional device flag: 1 = read sorted_pos/sorted_mass instead of pos/mass
-    const float *sorted_pos;
-    const float *sorted_mass;
-};
-
-struct AxisCell {
-    int lo, hi;
-    double wl, wh;
-    bool ok;
-};
-
-__device__ __forceinline__ AxisCell axis_cell(float p, double units, int dims)
-{
-    AxisCell c;
-    const double x = __dmul_rn((double)p, units);           // fieldize.cpp:66
-    const double fl = floor(x);                             // :67
-    c.wh = __dsub_rn(x, fl);                                // :68  dx
-    c.wl = __dsub_rn(1.0, c.wh);                            // :69  tx
-    c.ok = fabs(x) < 2.0e9;                                 // false for NaN/inf/out of int range
-    int f = c.ok ? (int)fl : 0;
-    if ((unsigned)f >= (unsigned)dims) {                    // :70-75 periodic wrap, negative fix-up
-        f %= dims;
-        if (f < 0)
-            f += dims;
-    }
-    c.lo = f;
-    c.hi = (f + 1 == dims) ? 0 : f + 1;
-    return c;
-}
-
-// A contribution is a double (fp64 mode) or llrint(w*2^S) as int64 (fixed-point mode);
-// the quantisation happens per contribution, before any merging, so merged
-// integer sums are bit-identical to eight separate adds.
-template <bool FIXED> struct Acc;
-template <> struct Acc<false> {
-    typedef double type;
-    static __device__ __forceinline__ double make(double w, double) { return w; }
-    static __device__ __forceinline__ void red(void *grid, size_t idx, double v)
-    {
-        atomicAdd(reinterpret_cast<double *>(grid) + idx, v);               // REDG.E.ADD.F64
-    }
-};
-template <> struct Acc<true> {
-    typedef long long type;
-    static __device__ __forceinline__ long long make(double w, double scale) { return __double2ll_rn(__dmul_rn(w, scale)); }
-    static __device__ __forceinline__ void red(void *grid, size_t idx, long long v)
-    {
-        atomicAdd(reinterpret_cast<unsigned long long *>(grid) + idx, (unsigned long long)v);   // REDG.E.ADD.64
-    }
-};
 
 // One particle per thread, CTA b owns particles [256 b, 256 b + 256): consecutive
 // particles stay consecutive in time, which keeps brick-sorted and snapshot-ordered
@@ -93,10 +30,6 @@ __global__ void __launch_bounds__(256) deposit_direct_kernel(DepositArgs a)
     const bool live = p < a.n;
     const float *pos = a.pos;
     const float *mass = a.mass;
-    if (a.use_sorted && *a.use_sorted) {       // device-side choice made by the coherence probe
-        pos = a.sorted_pos;
-        mass = a.mass ? a.sorted_mass : nullptr;
-    }
     float px = 0.f, py = 0.f, pz = 0.f;
     double m = a.cmass;
     if (live) {
@@ -163,44 +96,6 @@ __global__ void __launch_bounds__(256) deposit_direct_kernel(DepositArgs a)
     }
 }
 
-// Spatial coherence probe: are consecutive particles near each other on the grid?
-// Samples pairs (i, i+1) across the run; writes *use_sorted = 0 when at least 60 % of
-// them are within 4 cells in every axis (lattice, snapshot or already-sorted order:
-// sorting would only cost bandwidth), else 1.  The decision stays on the device: the
-// sort kernels return at once when it is 0 and the deposit reads the original array.
-__global__ void __launch_bounds__(1024) coherence_probe_kernel(const float *pos, int64_t n, double units, int dims,
-                                                               int *use_sorted)
-{
-    __shared__ int s_near;
-    if (threadIdx.x == 0)
-        s_near = 0;
-    __syncthreads();
-    const int samples = 8 * 1024;
-    int near = 0, tried = 0;
-    for (int s = threadIdx.x; s < samples; s += blockDim.x) {
-        const int64_t i = (int64_t)((double)s / samples * (double)(n - 1));
-        if (i + 1 >= n)
-            continue;
-        tried++;
-        bool all = true;
-        for (int ax = 0; ax < 3; ax++) {
-            const AxisCell c0 = axis_cell(pos[3 * i + ax], units, dims);
-            const AxisCell c1 = axis_cell(pos[3 * (i + 1) + ax], units, dims);
-            int d = abs(c0.lo - c1.lo);
-            d = min(d, dims - d);
-            all = all && d <= 4;
-        }
-        near += all ? 1 : 0;
-    }
-    atomicAdd(&s_near, near);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const int total = (int)min((int64_t)samples, n > 1 ? n - 1 : 0);
-        *use_sorted = (total > 0 && s_near * 10 >= total * 6) ? 0 : 1;
-    }
-    (void)tried;
-}
-
 // ---------------------------------------------------------------------------------
 // Counting sort of particles into bricks whose grid footprint fits in L2, so that
 // the reductions of the deposit kernel hit L2-resident lines instead of issuing a
@@ -226,11 +121,9 @@ constexpr int SORT_ITEMS = 8;
 constexpr int SORT_MAX_KEYS = 4096;   // 12 B of shared memory per key in the scatter
 
 __global__ void __launch_bounds__(SORT_THREADS) brick_histogram_kernel(const float *pos, int64_t n, BrickMap bm,
-                                                                      unsigned long long *counts, const int *enabled)
+                                                                      unsigned long long *counts)
 {
     extern __shared__ unsigned s_hist[];
-    if (enabled && !*enabled)           // the coherence probe said sorting is not needed
-        return;
     for (int k = threadIdx.x; k < bm.nbricks; k += SORT_THREADS)
         s_hist[k] = 0;
     __syncthreads();
@@ -274,11 +167,9 @@ __global__ void __launch_bounds__(1024) exclusive_scan_kernel(unsigned long long
 
 __global__ void __launch_bounds__(SORT_THREADS) brick_scatter_kernel(const float *pos, const float *mass, int64_t n,
                                                                     BrickMap bm, unsigned long long *cursors,
-                                                                    float *out_pos, float *out_mass, const int *enabled)
+                                                                    float *out_pos, float *out_mass)
 {
     extern __shared__ unsigned long long s_mem[];
-    if (enabled && !*enabled)
-        return;
     unsigned long long *s_base = s_mem;                                  // [nbricks]
     unsigned *s_cnt = reinterpret_cast<unsigned *>(s_mem + bm.nbricks);  // [nbricks]
     for (int k = threadIdx.x; k < bm.nbricks; k += SORT_THREADS)
@@ -387,7 +278,7 @@ __global__ void copy_counts_kernel(const unsigned long long *in, int64_t *out, i
 }
 
 static int sort_by_brick(genpk_ctx *ctx, const float *pos, const float *mass, int64_t n, const BrickMap &bm,
-                         float *out_pos, float *out_mass, int64_t *counts_out, const int *enabled)
+                         float *out_pos, float *out_mass, int64_t *counts_out)
 {
     if (bm.nbricks > ctx->brick_cap) {
         if (ctx->d_brick_counts) cudaFree(ctx->d_brick_counts);
@@ -401,7 +292,7 @@ static int sort_by_brick(genpk_ctx *ctx, const float *pos, const float *mass, in
     const int64_t per_block = (int64_t)SORT_THREADS * SORT_ITEMS;
     const int blocks = (int)((n + per_block - 1) / per_block);
     if (blocks > 0) {
-        brick_histogram_kernel<<<blocks, SORT_THREADS, bm.nbricks * sizeof(unsigned), ctx->stream>>>(pos, n, bm, counts, enabled);
+        brick_histogram_kernel<<<blocks, SORT_THREADS, bm.nbricks * sizeof(unsigned), ctx->stream>>>(pos, n, bm, counts);
         ctx->launches++;
     }
     if (counts_out) {
@@ -413,7 +304,7 @@ static int sort_by_brick(genpk_ctx *ctx, const float *pos, const float *mass, in
     if (blocks > 0) {
         const size_t smem = (size_t)bm.nbricks * (sizeof(unsigned long long) + sizeof(unsigned));
         brick_scatter_kernel<<<blocks, SORT_THREADS, smem, ctx->stream>>>(pos, mass, n, bm, counts, out_pos,
-                                                                          mass ? out_mass : nullptr, enabled);
+                                                                          mass ? out_mass : nullptr);
         ctx->launches++;
     }
     GENPK_CUDA_OK(cudaGetLastError());
@@ -433,8 +324,6 @@ static int ensure_sorted_scratch(genpk_ctx *ctx, int64_t n, bool with_mass)
     }
     if (with_mass && !ctx->d_sorted_mass)
         GENPK_CUDA_OK(cudaMalloc(&ctx->d_sorted_mass, (size_t)ctx->sorted_cap * sizeof(float)));
-    if (!ctx->d_use_sorted)
-        GENPK_CUDA_OK(cudaMalloc(&ctx->d_use_sorted, sizeof(int)));
     return 0;
 }
 
@@ -450,7 +339,7 @@ int route_particles(genpk_ctx *ctx, const float *pos, const float *mass, int64_t
     bm.by = g.dims;
     bm.nby = 1;
     bm.nbricks = g.nranks;
-    return sort_by_brick(ctx, pos, mass, n, bm, spos, smass, counts, nullptr);
+    return sort_by_brick(ctx, pos, mass, n, bm, spos, smass, counts);
 }
 
 int deposit_device(genpk_ctx *ctx, int which, const float *pos, const float *masses, int64_t n,
@@ -478,45 +367,51 @@ int deposit_device(genpk_ctx *ctx, int which, const float *pos, const float *mas
     a.plane = g.plane();
     a.grid = ctx->grid[which];
     a.errors = ctx->d_errors;
-    a.use_sorted = nullptr;
-    a.sorted_pos = nullptr;
-    a.sorted_mass = nullptr;
     if (ctx->fixed)
         ctx->grid_is_fixed[which] = true;
 
-    // DIRECT: reductions straight from the caller's order.  SORTED: always brick-sort
-    // first.  AUTO: nothing to gain from sorting when the owned grid fits in L2;
-    // otherwise a device-side probe of spatial coherence decides, without a host sync.
+    // DIRECT: reductions straight from the caller's order.  SORTED: brick-sort first.
+    // MARCH: lattice-march kernel (deposit_march.cu).  AUTO: a probe of the head of
+    // the stream decides -- lattice order => MARCH, merely coherent (or a grid that
+    // fits in L2) => DIRECT, incoherent => SORTED.  The verdict is one small D2H.
     int mode = ctx->deposit_mode;
-    const size_t grid_bytes = g.grid_doubles() * sizeof(double);
-    const bool fits_l2 = ctx->l2_bytes && grid_bytes <= ctx->l2_bytes / 2;
     if (mode == GENPK_DEPOSIT_TILED)
         mode = GENPK_DEPOSIT_AUTO;
-    if (mode == GENPK_DEPOSIT_AUTO && fits_l2)
+    const size_t grid_bytes = g.grid_doubles() * sizeof(double);
+    const bool fits_l2 = ctx->l2_bytes && grid_bytes <= ctx->l2_bytes / 2;
+    long long n0 = ctx->lattice_n0, n1 = ctx->lattice_n1;
+    if (mode == GENPK_DEPOSIT_AUTO && n < (1 << 16))
         mode = GENPK_DEPOSIT_DIRECT;
-    if (mode != GENPK_DEPOSIT_DIRECT) {
+    if (mode == GENPK_DEPOSIT_AUTO || (mode == GENPK_DEPOSIT_MARCH && n0 <= 0)) {
+        OrderInfo info;
+        if (int rc = probe_order(ctx, pos, n, a.units, &info))
+            return rc;
+        ctx->last_order[0] = info.coherent;
+        ctx->last_order[1] = info.lattice;
+        ctx->last_order[2] = info.n0;
+        ctx->last_order[3] = info.n1;
+        ctx->last_order[4] = info.score_z;
+        ctx->last_order[5] = info.score_y;
+        ctx->last_order[6] = info.score_x;
+        n0 = info.lattice ? info.n0 : 0;
+        n1 = info.lattice ? info.n1 : 0;
+        if (mode == GENPK_DEPOSIT_AUTO)
+            mode = info.lattice ? GENPK_DEPOSIT_MARCH
+                                : ((info.coherent || fits_l2) ? GENPK_DEPOSIT_DIRECT : GENPK_DEPOSIT_SORTED);
+    }
+    if (mode == GENPK_DEPOSIT_MARCH)
+        return launch_march(ctx, a, n0, n1);
+    if (mode == GENPK_DEPOSIT_SORTED) {
         const BrickMap bm = choose_bricks(ctx, a.units);
         if (bm.nbricks > 1 && bm.nbricks <= SORT_MAX_KEYS) {
             stage_begin(ctx, ST_SORT);
             if (int rc = ensure_sorted_scratch(ctx, n, masses != nullptr))
                 return rc;
-            const int *enabled = nullptr;
-            if (mode == GENPK_DEPOSIT_AUTO) {
-                coherence_probe_kernel<<<1, 1024, 0, ctx->stream>>>(pos, n, a.units, g.dims, ctx->d_use_sorted);
-                ctx->launches++;
-                enabled = ctx->d_use_sorted;
-            }
-            if (int rc = sort_by_brick(ctx, pos, masses, n, bm, ctx->d_sorted_pos, ctx->d_sorted_mass, nullptr, enabled))
+            if (int rc = sort_by_brick(ctx, pos, masses, n, bm, ctx->d_sorted_pos, ctx->d_sorted_mass, nullptr))
                 return rc;
             stage_end(ctx, ST_SORT);
-            if (enabled) {
-                a.use_sorted = enabled;
-                a.sorted_pos = ctx->d_sorted_pos;
-                a.sorted_mass = ctx->d_sorted_mass;
-            } else {
-                a.pos = ctx->d_sorted_pos;
-                a.mass = masses ? ctx->d_sorted_mass : nullptr;
-            }
+            a.pos = ctx->d_sorted_pos;
+            a.mass = masses ? ctx->d_sorted_mass : nullptr;
         }
     }
     return launch_direct(ctx, a);
@@ -575,9 +470,6 @@ int fieldize_host_shim(double boxsize, int dims, double *out, int64_t n, const f
         a.plane = (size_t)dims * fd;
         a.grid = d_grid;
         a.errors = d_err;
-        a.use_sorted = nullptr;
-        a.sorted_pos = nullptr;
-        a.sorted_mass = nullptr;
         const int threads = 256;
         const int64_t blocks = (n + threads - 1) / threads;
         if (blocks > 0x7fffffffLL) break;

@@ -47,8 +47,17 @@ extern "C" {
 #define GENPK_DEPOSIT_AUTO       0     /* pick from particle density and spatial coherence */
 #define GENPK_DEPOSIT_DIRECT     1     /* one thread per particle, 8 global red.add          */
 #define GENPK_DEPOSIT_SORTED     2     /* counting sort into L2-sized bricks, then deposit   */
-#define GENPK_DEPOSIT_TILED      3     /* sort into bricks, shared-memory tile accumulation  */
+#define GENPK_DEPOSIT_TILED      3     /* reserved (alias of AUTO)                              */
+#define GENPK_DEPOSIT_MARCH      4     /* lattice-ordered input: neighbour contributions merged in
+                                          registers along z, y and x before one red.add per particle */
 #define GENPK_OPT_SCALE_BITS     2     /* fixed-point mode: q = llrint(w * 2^bits), default 40 */
+/* Lattice hint for GENPK_DEPOSIT_MARCH / AUTO: particle p sits near lattice site
+ * (ix,iy,iz) with p = (ix*N1 + iy)*N0 + iz.  0 = let the order probe find it.  Only
+ * ever a performance hint: results do not depend on it. */
+#define GENPK_OPT_LATTICE_N0     4
+#define GENPK_OPT_LATTICE_N1     5
+#define GENPK_OPT_MARCH_RY       6     /* lattice rows one warp marches over (default 8)   */
+#define GENPK_OPT_MARCH_RX       7     /* lattice planes one warp marches over (default 8) */
 /* ---- binning pass selection (genpk_set_option(ctx, GENPK_OPT_POWER, v)) ------------ */
 #define GENPK_OPT_POWER          3
 #define GENPK_POWER_CACHED       0     /* sum|k| and mode counts per bin depend on the grid only: computed
@@ -142,7 +151,8 @@ void *genpk_grid_device_ptr(genpk_ctx *ctx, int which);
 #define GENPK_STAGE_DEPOSIT 0
 #define GENPK_STAGE_FFT     1
 #define GENPK_STAGE_POWER   2
-#define GENPK_STAGE_SORT    3
+#define GENPK_STAGE_SORT    3   /* part of DEPOSIT: the brick sort */
+#define GENPK_STAGE_ZERO    4   /* genpk_grid_zero */
 int genpk_stage_ms(genpk_ctx *ctx, int stage, float *ms);
 /* Sum over the (up to 128 most recent) recorded instances of a stage since
  * genpk_stage_reset, and how many were summed.  Recording never synchronises
@@ -150,6 +160,9 @@ int genpk_stage_ms(genpk_ctx *ctx, int stage, float *ms);
 int genpk_stage_total_ms(genpk_ctx *ctx, int stage, float *total_ms, int64_t *records);
 int genpk_stage_reset(genpk_ctx *ctx);
 int64_t genpk_launch_count(const genpk_ctx *ctx);
+/* Verdict of the last order probe of this context: {coherent, lattice, n0, n1,
+ * score_z, score_y, score_x} (scores per mille; diagnostics for the bench line). */
+int genpk_last_order(const genpk_ctx *ctx, int64_t out[7]);
 
 /* ================= 3. slab stages for the multi-GPU pipeline ======================== */
 /* Rank `rank` of `nranks` owns x-planes [rank*dims/nranks, (rank+1)*dims/nranks)
