@@ -302,20 +302,35 @@ int genpk_power_finalize(const double *sums, int nrbins, double total_mass, doub
     return 0;
 }
 
-int genpk_power(genpk_ctx *ctx, int a, int b, int nrbins, double *power, int *count, double *keffs, double total_mass,
-                double total_mass2)
+static int power_on(genpk_ctx *ctx, const double *spec_a, const double *spec_b, int nrbins, double *power, int *count,
+                    double *keffs, double total_mass, double total_mass2)
 {
-    if (!check_which(ctx, a, "genpk_power") || !check_which(ctx, b, "genpk_power")) return 1;
     if (nrbins < 1 || !power || !count || !keffs) { set_error("genpk_power: bad arguments"); return 1; }
     if (ctx->g.nranks != 1) { set_error("genpk_power: slab contexts use genpk_slab_power_partial"); return 1; }
     if (int rc = ensure_tables(ctx, nrbins)) return rc;
     stage_begin(ctx, ST_POWER);
-    if (int rc = power_raw(ctx, ctx->grid[a], ctx->grid[b], ctx->g.dims, 0, ctx->g.dims, 0, nrbins, ctx->d_sums)) return rc;
+    if (int rc = power_raw(ctx, spec_a, spec_b, ctx->g.dims, 0, ctx->g.dims, 0, nrbins, ctx->d_sums)) return rc;
     stage_end(ctx, ST_POWER);
     GENPK_CUDA_OK(cudaMemcpyAsync(ctx->h_sums, ctx->d_sums, (size_t)3 * nrbins * sizeof(double), cudaMemcpyDeviceToHost,
                                   ctx->stream));
     GENPK_CUDA_OK(cudaStreamSynchronize(ctx->stream));
     return genpk_power_finalize(ctx->h_sums, nrbins, total_mass, total_mass2, power, count, keffs);
+}
+
+int genpk_power(genpk_ctx *ctx, int a, int b, int nrbins, double *power, int *count, double *keffs, double total_mass,
+                double total_mass2)
+{
+    if (!check_which(ctx, a, "genpk_power") || !check_which(ctx, b, "genpk_power")) return 1;
+    return power_on(ctx, ctx->grid[a], ctx->grid[b], nrbins, power, count, keffs, total_mass, total_mass2);
+}
+
+int genpk_power_dev(genpk_ctx *ctx, const void *spec_a_dev, const void *spec_b_dev, int nrbins, double *power,
+                    int *count, double *keffs, double total_mass, double total_mass2)
+{
+    if (!ctx || !spec_a_dev) { set_error("genpk_power_dev: bad arguments"); return 1; }
+    const double *a = reinterpret_cast<const double *>(spec_a_dev);
+    const double *b = spec_b_dev ? reinterpret_cast<const double *>(spec_b_dev) : a;
+    return power_on(ctx, a, b, nrbins, power, count, keffs, total_mass, total_mass2);
 }
 
 int genpk_pk_from_particles(genpk_ctx *ctx, const float *positions, const float *masses, int64_t n, double mass,

@@ -129,6 +129,12 @@ int genpk_fft(genpk_ctx *ctx, int which);
 int genpk_power(genpk_ctx *ctx, int a, int b, int nrbins, double *power, int *count, double *keffs,
                 double total_mass, double total_mass2);
 
+/* The same binning on two device-resident spectra [dims][dims][dims/2+1] that need
+ * not be this context's own grids (e.g. the spectrum of another context on the same
+ * GPU: the two-snapshot cross spectrum of gen-pk.cpp:295-297).  spec_b_dev NULL = auto. */
+int genpk_power_dev(genpk_ctx *ctx, const void *spec_a_dev, const void *spec_b_dev, int nrbins,
+                    double *power, int *count, double *keffs, double total_mass, double total_mass2);
+
 /* Whole per-type step of gen-pk.cpp:208-234 in one call on host particle
  * arrays: zero, deposit, FFT, binning, results on the host. */
 int genpk_pk_from_particles(genpk_ctx *ctx, const float *positions, const float *masses, int64_t n,

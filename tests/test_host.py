@@ -182,3 +182,20 @@ def test_print_pk_matches_reference_bytes(tmp_path):
     lib.ref_print_pk(str(b).encode(), n, keffs.ctypes.data_as(C.c_void_p), power.ctypes.data_as(C.c_void_p),
                      count.ctypes.data_as(C.c_void_p))
     assert a.read_bytes() == b.read_bytes()
+
+
+def test_dropin_exports_the_reference_link_symbols(built):
+    """libgenpk_dropin.so must define exactly what gen-pk's other objects import from
+    fieldize.o, powerspectrum.o and libfftw3 (gen-pk.h:93-119; gen-pk.cpp:176-193,233,363)."""
+    import subprocess
+    path = os.path.join(ROOT, "genpk_b200", "libgenpk_dropin.so")
+    assert os.path.exists(path)
+    out = subprocess.run(["nm", "-D", "--defined-only", path], capture_output=True, text=True, check=True).stdout
+    defined = {line.split()[-1] for line in out.splitlines() if line.strip()}
+    for sym in ("_Z8fieldizediPdlPfS0_di", "invwindow", "powerspectrum", "fftw_malloc", "fftw_free", "fftw_init_threads",
+                "fftw_plan_with_nthreads", "fftw_plan_dft_r2c_3d", "fftw_execute", "fftw_destroy_plan"):
+        assert sym in defined, sym
+    refhost = os.path.join(ROOT, "oracle", "_ref", "libgenpk_refhost.so")
+    if os.path.exists(refhost):
+        und = subprocess.run(["nm", "-D", "--undefined-only", refhost], capture_output=True, text=True, check=True).stdout
+        assert "_Z8fieldizediPdlPfS0_di" in und      # the reference's reader really imports fieldize()
