@@ -59,6 +59,8 @@ def parse_args():
     ap.add_argument("--lattice-hint", action="store_true", help="pass the lattice extents instead of probing them")
     ap.add_argument("--march-ry", type=int, default=0)
     ap.add_argument("--march-rx", type=int, default=0)
+    ap.add_argument("--ghost-planes", type=int, default=16,
+                    help="multi-GPU: ghost planes on each side of a slab (0 = always route particles)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
@@ -300,7 +302,9 @@ def run_ours(args):
         def step_host(hpos):
             return ctx.pk_from_particles_ptr(hpos.data_ptr(), count, 1.0, BOX, total_mass, nrbins)
     else:
-        stages = CudaStages(dims, world, rank, dev, flags)
+        # wide-ghost slabs: index-range shards of lattice-ordered sets are deposited where they are
+        ghost = min(args.ghost_planes, dims // world, (dims - dims // world) // 2)
+        stages = CudaStages(dims, world, rank, dev, flags, ghost)
         stages.ctx.set_deposit_mode(mode)
         stages.ctx.set_power_mode(api.POWER_FUSED if args.power == "fused" else api.POWER_CACHED)
         ctx = stages.ctx
@@ -409,7 +413,8 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl["label"], "particles": n_total, "grid": dims, "nrbins": nrbins, "box": BOX,
                    "accumulation": "int64 fixed-point" if args.fixed_point else "fp64 red.add",
-                   "deposit_mode": args.deposit, "order_probe": ctx.last_order(), "binning_mode": args.power, "parallelism": f"x-slab x{world}" if world > 1 else "single GPU",
+                   "deposit_mode": args.deposit, "order_probe": ctx.last_order(), "binning_mode": args.power, "parallelism": (f"x-slab x{world}, {ghost} ghost planes, particles {pipe.placement}" if world > 1
+                                   else "single GPU"),
                    "l2": "inputs larger than L2 (no flush needed)"},
         "pk_time_ms": ms_step,
         "stage_ms": stage_ms,

@@ -54,6 +54,11 @@ SIGNATURES = {
     "genpk_last_order": (C.c_int, [C.c_void_p, c_i64p]),
     # 3. slab stages
     "genpk_create_slab": (C.c_void_p, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint]),
+    "genpk_create_slab_wide": (C.c_void_p, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint, C.c_int]),
+    "genpk_grid_owned_offset": (C.c_size_t, [C.c_void_p]),
+    "genpk_take_rejected": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "genpk_ghost_side_ptr": (C.c_void_p, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
+    "genpk_ghost_side_accumulate": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "genpk_route_particles": (C.c_int, [C.c_void_p, c_f32p, c_f32p, C.c_int64, C.c_double, c_f32p, c_f32p, c_i64p]),
     "genpk_ghost_ptr": (C.c_void_p, [C.c_void_p, C.c_int, C.POINTER(C.c_size_t)]),
     "genpk_ghost_accumulate": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),

@@ -120,13 +120,16 @@ def powerspectrum(dims, outfield, outfield2, nrbins, power, count, keffs, total_
 class Context:
     """One GPU, one grid (or x-slab of it) resident in HBM: zero -> deposit* -> fft -> power."""
 
-    def __init__(self, dims: int, device: int = -1, flags: int = 0, nranks: int = 1, rank: int = 0):
+    def __init__(self, dims: int, device: int = -1, flags: int = 0, nranks: int = 1, rank: int = 0,
+                 ghost_planes: int = 0):
         self.lib = _lib.load()
         self.dims, self.nranks, self.rank, self.flags = int(dims), int(nranks), int(rank), int(flags)
+        self.ghost_planes = int(ghost_planes) if nranks > 1 else 0
         if nranks == 1:
             self.h = self.lib.genpk_create(self.dims, int(device), self.flags)
         else:
-            self.h = self.lib.genpk_create_slab(self.dims, int(device), self.nranks, self.rank, self.flags)
+            self.h = self.lib.genpk_create_slab_wide(self.dims, int(device), self.nranks, self.rank, self.flags,
+                                                     self.ghost_planes)
         if not self.h:
             raise _lib.GenPKError("genpk_create failed: " + _lib.last_error())
         self.nc = self.dims // 2 + 1
@@ -293,6 +296,25 @@ class Context:
     def route_particles(self, pos_ptr, mass_ptr, n, boxsize, spos_ptr, smass_ptr, counts_ptr):
         check(self.lib.genpk_route_particles(self.h, pos_ptr, mass_ptr or None, int(n), float(boxsize), spos_ptr,
                                              smass_ptr or None, counts_ptr), "genpk_route_particles")
+
+    def take_rejected(self) -> int:
+        """Particles the deposits rejected since the last call (waits for the stream)."""
+        n = C.c_uint64(0)
+        check(self.lib.genpk_take_rejected(self.h, C.byref(n)), "genpk_take_rejected")
+        return int(n.value)
+
+    def owned_offset(self) -> int:
+        return int(self.lib.genpk_grid_owned_offset(self.h))
+
+    def ghost_side_ptr(self, side: int, which: int = 0):
+        nbytes = C.c_size_t(0)
+        p = self.lib.genpk_ghost_side_ptr(self.h, which, side, C.byref(nbytes))
+        if not p:
+            raise _lib.GenPKError(_lib.last_error())
+        return p, nbytes.value
+
+    def ghost_side_accumulate(self, side: int, recv_ptr: int, which: int = 0):
+        check(self.lib.genpk_ghost_side_accumulate(self.h, which, side, recv_ptr), "genpk_ghost_side_accumulate")
 
     def ghost_ptr(self, which: int = 0):
         nbytes = C.c_size_t(0)

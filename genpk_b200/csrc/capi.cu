@@ -36,8 +36,14 @@ static bool check_which(const genpk_ctx *ctx, int which, const char *fn)
     return true;
 }
 
-static genpk_ctx *create_common(int dims, int device, int nranks, int rank, unsigned flags)
+static genpk_ctx *create_common(int dims, int device, int nranks, int rank, unsigned flags, int ghost_planes)
 {
+    if (ghost_planes < 0 || (nranks > 1 && dims % nranks == 0 &&
+                             (ghost_planes > dims / nranks || dims / nranks + 2 * ghost_planes > dims))) {
+        set_error("genpk_create: ghost_planes=%d must satisfy ghost <= dims/nranks and dims/nranks + 2*ghost <= dims",
+                  ghost_planes);
+        return nullptr;
+    }
     if (dims < 1 || nranks < 1 || rank < 0 || rank >= nranks || dims % nranks != 0) {
         set_error("genpk_create: bad geometry dims=%d nranks=%d rank=%d (dims must be divisible by nranks)", dims,
                   nranks, rank);
@@ -71,7 +77,11 @@ static genpk_ctx *create_common(int dims, int device, int nranks, int rank, unsi
     g.rank = rank;
     g.nx = dims / nranks;
     g.x0 = rank * g.nx;
-    g.ghost = nranks > 1 ? 1 : 0;
+    // plain slab: one ghost plane above (CIC reaches one plane up).  Wide slab: G planes on both
+    // sides, so a rank can deposit a slab-local particle shard whose stragglers sit up to G planes
+    // outside its slab without any particle exchange.
+    g.ghost_lo = nranks > 1 ? ghost_planes : 0;
+    g.ghost_hi = nranks > 1 ? (ghost_planes > 0 ? ghost_planes : 1) : 0;
     g.nc = dims / 2 + 1;
     g.fd = 2 * g.nc;
     const int ngrids = (flags & GENPK_FLAG_TWO_FIELDS) ? 2 : 1;
@@ -104,11 +114,16 @@ extern "C" {
 const char *genpk_last_error(void) { return g_error; }
 int genpk_abi_version(void) { return GENPK_ABI_VERSION; }
 
-genpk_ctx *genpk_create(int dims, int device, unsigned flags) { return create_common(dims, device, 1, 0, flags); }
+genpk_ctx *genpk_create(int dims, int device, unsigned flags) { return create_common(dims, device, 1, 0, flags, 0); }
 
 genpk_ctx *genpk_create_slab(int dims, int device, int nranks, int rank, unsigned flags)
 {
-    return create_common(dims, device, nranks, rank, flags);
+    return create_common(dims, device, nranks, rank, flags, 0);
+}
+
+genpk_ctx *genpk_create_slab_wide(int dims, int device, int nranks, int rank, unsigned flags, int ghost_planes)
+{
+    return create_common(dims, device, nranks, rank, flags, ghost_planes);
 }
 
 void genpk_destroy(genpk_ctx *ctx)
@@ -198,6 +213,18 @@ int genpk_synchronize(genpk_ctx *ctx)
         set_error("%llu particles rejected (non-finite position, or outside this rank's x-slab)", bad);
         return 3;
     }
+    return 0;
+}
+
+int genpk_take_rejected(genpk_ctx *ctx, uint64_t *rejected)
+{
+    if (!ctx || !rejected) { set_error("genpk_take_rejected: bad arguments"); return 1; }
+    GENPK_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    unsigned long long bad = 0;
+    GENPK_CUDA_OK(cudaMemcpy(&bad, ctx->d_errors, sizeof(bad), cudaMemcpyDeviceToHost));
+    if (bad)
+        GENPK_CUDA_OK(cudaMemset(ctx->d_errors, 0, sizeof(bad)));
+    *rejected = bad;
     return 0;
 }
 
@@ -345,6 +372,8 @@ int genpk_pk_from_particles(genpk_ctx *ctx, const float *positions, const float 
 
 size_t genpk_grid_doubles(const genpk_ctx *ctx) { return ctx ? ctx->g.grid_doubles() : 0; }
 
+size_t genpk_grid_owned_offset(const genpk_ctx *ctx) { return ctx ? ctx->g.owned_offset() : 0; }
+
 void *genpk_grid_device_ptr(genpk_ctx *ctx, int which)
 {
     return check_which(ctx, which, "genpk_grid_device_ptr") ? ctx->grid[which] : nullptr;
@@ -448,18 +477,31 @@ int genpk_route_particles(genpk_ctx *ctx, const float *pos_dev, const float *mas
     return route_particles(ctx, pos_dev, mass_dev, n, boxsize, sorted_pos_dev, sorted_mass_dev, counts_dev);
 }
 
-void *genpk_ghost_ptr(genpk_ctx *ctx, int which, size_t *bytes)
+void *genpk_ghost_side_ptr(genpk_ctx *ctx, int which, int side, size_t *bytes)
 {
-    if (!check_which(ctx, which, "genpk_ghost_ptr")) return nullptr;
-    if (!ctx->g.ghost) { set_error("genpk_ghost_ptr: single-rank context has no ghost plane"); return nullptr; }
-    if (bytes) *bytes = ctx->g.plane() * sizeof(double);
-    return ctx->grid[which] + ctx->g.owned_doubles();
+    if (!check_which(ctx, which, "genpk_ghost_side_ptr")) return nullptr;
+    const SlabGeom &g = ctx->g;
+    const int planes = side ? g.ghost_hi : g.ghost_lo;
+    if (side < 0 || side > 1 || planes == 0) {
+        set_error("genpk_ghost_side_ptr: this context stores no ghost planes on side %d", side);
+        return nullptr;
+    }
+    if (bytes) *bytes = g.plane() * sizeof(double) * (size_t)planes;
+    return ctx->grid[which] + (side ? g.owned_offset() + g.owned_doubles() : 0);
+}
+
+void *genpk_ghost_ptr(genpk_ctx *ctx, int which, size_t *bytes) { return genpk_ghost_side_ptr(ctx, which, 1, bytes); }
+
+int genpk_ghost_side_accumulate(genpk_ctx *ctx, int which, int side, const void *recv_planes_dev)
+{
+    if (!check_which(ctx, which, "genpk_ghost_side_accumulate")) return 1;
+    if (side < 0 || side > 1 || !recv_planes_dev) { set_error("genpk_ghost_side_accumulate: bad arguments"); return 1; }
+    return ghost_accumulate(ctx, which, side, recv_planes_dev);
 }
 
 int genpk_ghost_accumulate(genpk_ctx *ctx, int which, const void *recv_plane_dev)
 {
-    if (!check_which(ctx, which, "genpk_ghost_accumulate")) return 1;
-    return ghost_accumulate(ctx, which, recv_plane_dev);
+    return genpk_ghost_side_accumulate(ctx, which, 0, recv_plane_dev);
 }
 
 int genpk_slab_fft_yz(genpk_ctx *ctx, int which)

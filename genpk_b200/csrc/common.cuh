@@ -51,12 +51,14 @@ struct SlabGeom {
     int nranks = 1, rank = 0;
     int nx = 0;        // local x planes (dims / nranks)
     int x0 = 0;        // first global x plane
-    int ghost = 0;     // 1 when a high-x ghost plane is stored (nranks > 1)
+    int ghost_lo = 0;  // ghost planes stored below the owned ones (wide-ghost slabs)
+    int ghost_hi = 0;  // ghost planes stored above: 1 for plain slabs (CIC reaches one plane up), G for wide ones
     int fd = 0;        // padded z stride in doubles, 2*(dims/2+1)
     int nc = 0;        // complex z extent, dims/2+1
     size_t plane() const { return (size_t)dims * fd; }                    // doubles per x plane
-    size_t grid_doubles() const { return plane() * (size_t)(nx + ghost); }
+    size_t grid_doubles() const { return plane() * (size_t)(ghost_lo + nx + ghost_hi); }
     size_t owned_doubles() const { return plane() * (size_t)nx; }
+    size_t owned_offset() const { return plane() * (size_t)ghost_lo; }    // first owned plane inside the allocation
 };
 
 enum Stage { ST_DEPOSIT = 0, ST_FFT = 1, ST_POWER = 2, ST_SORT = 3, ST_ZERO = 4, ST_COUNT = 5 };
@@ -140,7 +142,7 @@ void fft_release(genpk_ctx *ctx);
 // slab.cu
 int route_particles(genpk_ctx *ctx, const float *pos, const float *mass, int64_t n, double boxsize,
                     float *spos, float *smass, int64_t *counts);
-int ghost_accumulate(genpk_ctx *ctx, int which, const void *recv);
+int ghost_accumulate(genpk_ctx *ctx, int which, int side, const void *recv);
 int slab_pack(genpk_ctx *ctx, int which, void *send);
 
 inline void stage_begin(genpk_ctx *ctx, int st)

@@ -42,10 +42,11 @@ __global__ void __launch_bounds__(256) deposit_direct_kernel(DepositArgs a)
     const AxisCell cx = axis_cell(px, a.units, a.dims);
     const AxisCell cy = axis_cell(py, a.units, a.dims);
     const AxisCell cz = axis_cell(pz, a.units, a.dims);
-    int xl = cx.lo - a.x0, xh;
+    int xl = cx.lo, xh;
     bool ok = live && cx.ok && cy.ok && cz.ok;
-    if (a.ghost) {                           // slab: the +1 neighbour may be the ghost plane
-        ok = ok && xl >= 0 && xl < a.nx;
+    if (a.slab) {                            // slab: the +1 neighbour may be a ghost plane
+        xl = slab_plane(cx.lo, a.x0, a.ghost_lo, a.dims);
+        ok = ok && xl >= 0 && xl <= a.xl_max;
         xh = xl + 1;
     } else {
         xh = cx.hi;
@@ -362,8 +363,9 @@ int deposit_device(genpk_ctx *ctx, int which, const float *pos, const float *mas
     a.dims = g.dims;
     a.fd = g.fd;
     a.x0 = g.x0;
-    a.nx = g.nx;
-    a.ghost = g.ghost;
+    a.slab = g.nranks > 1 ? 1 : 0;
+    a.ghost_lo = g.ghost_lo;
+    a.xl_max = g.ghost_lo + g.nx + g.ghost_hi - 2;
     a.plane = g.plane();
     a.grid = ctx->grid[which];
     a.errors = ctx->d_errors;
@@ -465,8 +467,9 @@ int fieldize_host_shim(double boxsize, int dims, double *out, int64_t n, const f
         a.dims = dims;
         a.fd = fd;
         a.x0 = 0;
-        a.nx = dims;
-        a.ghost = 0;
+        a.slab = 0;
+        a.ghost_lo = 0;
+        a.xl_max = dims - 1;
         a.plane = (size_t)dims * fd;
         a.grid = d_grid;
         a.errors = d_err;

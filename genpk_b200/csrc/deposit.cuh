@@ -12,7 +12,10 @@ struct DepositArgs {
     double units;          // dims / boxsize
     double scale;          // 2^scale_bits (fixed-point mode)
     int dims, fd;
-    int x0, nx, ghost;     // slab: owned planes [x0, x0+nx), ghost plane stored at local index nx
+    int x0;                // slab: first owned global x plane
+    int slab;              // 1: the grid is a slab with ghost planes, 0: the whole periodic grid
+    int ghost_lo;          // ghost planes below the owned ones; local plane = (X - x0) + ghost_lo
+    int xl_max;            // largest admissible local plane of the low-x corner (its +1 neighbour must exist)
     size_t plane;          // doubles per x plane = dims*fd
     void *grid;
     unsigned long long *errors;
@@ -51,6 +54,18 @@ __device__ __forceinline__ AxisCell axis_cell(float p, double units, int dims)
     c.lo = f;
     c.hi = (f + 1 == dims) ? 0 : f + 1;
     return c;
+}
+
+// Local plane index of global cell X in a slab whose first owned plane is x0 and that
+// stores ghost_lo ghost planes below it: the periodic image of X - x0 nearest to the slab.
+__device__ __forceinline__ int slab_plane(int X, int x0, int ghost_lo, int dims)
+{
+    int d = X - x0;
+    if (d < -ghost_lo)
+        d += dims;
+    else if (d >= dims - ghost_lo)
+        d -= dims;
+    return d + ghost_lo;
 }
 
 // A contribution is a double (fp64 mode) or llrint(w*2^S) as int64 (fixed-point mode);

@@ -234,12 +234,14 @@ __global__ void __launch_bounds__(MARCH_THREADS, GENPK_MARCH_MINB) deposit_march
             fy = wrap_cell(fy, dims);
             fz = wrap_cell(fz, dims);
         }
-        int xl = fx - a.x0;
+        int xl = fx;
         int xstep = 1;                                                       // planes from the low-x to the high-x corner
-        if (a.ghost)
-            ok = ok && xl >= 0 && xl < a.nx;                                 // slab: the +1 neighbour may be the ghost plane
-        else if (fx + 1 == dims)
+        if (a.slab) {                                                        // slab: the +1 neighbour may be a ghost plane
+            xl = slab_plane(fx, a.x0, a.ghost_lo, dims);
+            ok = ok && xl >= 0 && xl <= a.xl_max;
+        } else if (fx + 1 == dims) {
             xstep = 1 - dims;
+        }
         if (live && !ok && owner_lane)
             atomicAdd(a.errors, 1ull);
         const int ystep = fy + 1 == dims ? 1 - dims : 1;

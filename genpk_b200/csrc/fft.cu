@@ -64,7 +64,8 @@ int fft_yz(genpk_ctx *ctx, int which)
         if (int rc = attach_work(ctx)) return rc;
     }
     GENPK_CUFFT_OK(cufftSetStream(ctx->plan_yz, ctx->stream));
-    GENPK_CUFFT_OK(cufftExecD2Z(ctx->plan_yz, ctx->grid[which], reinterpret_cast<cufftDoubleComplex *>(ctx->grid[which])));
+    double *owned = ctx->grid[which] + g.owned_offset();
+    GENPK_CUFFT_OK(cufftExecD2Z(ctx->plan_yz, owned, reinterpret_cast<cufftDoubleComplex *>(owned)));
     ctx->lib_calls++;
     return 0;
 }

@@ -20,15 +20,22 @@ __global__ void plane_add_i64_kernel(long long *dst, const long long *src, size_
         dst[i] += src[i];
 }
 
-int ghost_accumulate(genpk_ctx *ctx, int which, const void *recv)
+// side 0: planes received from rank-1 (its high ghosts) are added into my first owned planes;
+// side 1: planes received from rank+1 (its low ghosts) into my last owned planes.
+int ghost_accumulate(genpk_ctx *ctx, int which, int side, const void *recv)
 {
-    const size_t n = ctx->g.plane();
+    const SlabGeom &g = ctx->g;
+    const int planes = side ? g.ghost_lo : g.ghost_hi;       // what the neighbour on that side sends
+    if (planes == 0)
+        return 0;
+    const size_t n = g.plane() * (size_t)planes;
+    double *dst = ctx->grid[which] + g.owned_offset() + (side ? g.plane() * (size_t)(g.nx - planes) : 0);
     const int blocks = ctx->sm_count * 8;
     if (ctx->grid_is_fixed[which])
-        plane_add_i64_kernel<<<blocks, 256, 0, ctx->stream>>>(reinterpret_cast<long long *>(ctx->grid[which]),
+        plane_add_i64_kernel<<<blocks, 256, 0, ctx->stream>>>(reinterpret_cast<long long *>(dst),
                                                               reinterpret_cast<const long long *>(recv), n);
     else
-        plane_add_f64_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->grid[which], reinterpret_cast<const double *>(recv), n);
+        plane_add_f64_kernel<<<blocks, 256, 0, ctx->stream>>>(dst, reinterpret_cast<const double *>(recv), n);
     ctx->launches++;
     GENPK_CUDA_OK(cudaGetLastError());
     return 0;
@@ -55,7 +62,7 @@ int slab_pack(genpk_ctx *ctx, int which, void *send)
 {
     const SlabGeom &g = ctx->g;
     const int ny = g.dims / g.nranks;
-    slab_pack_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(reinterpret_cast<const double2 *>(ctx->grid[which]),
+    slab_pack_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(reinterpret_cast<const double2 *>(ctx->grid[which] + g.owned_offset()),
                                                                 reinterpret_cast<double2 *>(send), g.nx, g.dims, g.nc, ny);
     ctx->launches++;
     GENPK_CUDA_OK(cudaGetLastError());

@@ -32,10 +32,11 @@ class _DevMem:
 class CudaStages:
     """Compute stages of one rank, on its GPU, through the C ABI."""
 
-    def __init__(self, dims: int, nranks: int, rank: int, device: torch.device, flags: int = 0):
+    def __init__(self, dims: int, nranks: int, rank: int, device: torch.device, flags: int = 0, ghost_planes: int = 0):
         self.device = device
         torch.cuda.set_device(device)
-        self.ctx = api.Context(dims, device.index, flags, nranks, rank)
+        self.ctx = api.Context(dims, device.index, flags, nranks, rank, ghost_planes)
+        self.ghost_planes = self.ctx.ghost_planes          # > 0: ghosts on both sides, slab-local shards need no routing
         self.ctx.set_stream(torch.cuda.current_stream(device).cuda_stream)
         self.dims, self.nranks, self.rank = dims, nranks, rank
         self.nc = dims // 2 + 1
@@ -69,12 +70,17 @@ class CudaStages:
             self.ctx.deposit_dev(pos.data_ptr(), n, mass.data_ptr() if mass is not None else 0, cmass, boxsize, which)
 
     # -- ghost plane ---------------------------------------------------------------
-    def ghost_plane(self, which=0) -> torch.Tensor:
-        ptr, nbytes = self.ctx.ghost_ptr(which)
+    def ghost_plane(self, which=0, side=1) -> torch.Tensor:
+        """Ghost planes on the high-x (side 1) or low-x (side 0) side of the slab."""
+        ptr, nbytes = self.ctx.ghost_side_ptr(side, which)
         return torch.as_tensor(_DevMem(ptr, nbytes), device=self.device)
 
-    def ghost_accumulate(self, recv: torch.Tensor, which=0):
-        self.ctx.ghost_accumulate(recv.data_ptr(), which)
+    def ghost_accumulate(self, recv: torch.Tensor, which=0, side=0):
+        """side 0: planes from rank-1 into my first owned planes; side 1: from rank+1 into my last."""
+        self.ctx.ghost_side_accumulate(side, recv.data_ptr(), which)
+
+    def rejected(self) -> int:
+        return self.ctx.take_rejected()
 
     # -- FFT -----------------------------------------------------------------------
     def fft_yz(self, which=0):
@@ -118,6 +124,9 @@ class SlabPipeline:
             raise ValueError(f"grid side {dims} is not divisible by {self.P} ranks")
         self.dims, self.stages = dims, stages
         self.timings = {}
+        # wide-ghost stages: deposit the shard as it is and only route when a rank had stragglers
+        # beyond its ghosts ("local" until that happens once, then "route" for good)
+        self.placement = "local" if getattr(stages, "ghost_planes", 0) > 0 and self.P > 1 else "route"
 
     # ---- exchange steps ---------------------------------------------------------------
     def exchange_particles(self, spos, smass, counts):
@@ -140,15 +149,22 @@ class SlabPipeline:
         """Ring shift of the high-x ghost plane into the next rank's first plane."""
         if self.P == 1:
             return
-        ghost = self.stages.ghost_plane(which)
-        recv = torch.empty_like(ghost)
         nxt, prv = (self.r + 1) % self.P, (self.r - 1) % self.P
         if self.group is not None:
             nxt, prv = dist.get_global_rank(self.group, nxt), dist.get_global_rank(self.group, prv)
-        ops = [dist.P2POp(dist.isend, ghost, nxt, self.group), dist.P2POp(dist.irecv, recv, prv, self.group)]
+        up = self.stages.ghost_plane(which, 1)                     # my high ghosts belong to rank+1
+        from_prev = torch.empty_like(up)
+        ops = [dist.P2POp(dist.isend, up, nxt, self.group), dist.P2POp(dist.irecv, from_prev, prv, self.group)]
+        from_next = None
+        if getattr(self.stages, "ghost_planes", 0) > 0:            # wide slabs: low ghosts go down as well
+            down = self.stages.ghost_plane(which, 0)
+            from_next = torch.empty_like(down)
+            ops += [dist.P2POp(dist.isend, down, prv, self.group), dist.P2POp(dist.irecv, from_next, nxt, self.group)]
         for req in dist.batch_isend_irecv(ops):
             req.wait()
-        self.stages.ghost_accumulate(recv, which)
+        self.stages.ghost_accumulate(from_prev, which, 0)
+        if from_next is not None:
+            self.stages.ghost_accumulate(from_next, which, 1)
 
     def transpose(self, which=0):
         """[x_local][y][kz] on every rank -> [x][y_local][kz] on every rank."""
@@ -165,10 +181,22 @@ class SlabPipeline:
         if zero:
             self.stages.zero(which)
         if routed or self.P == 1:
-            rpos, rmass = pos, mass
-        else:
-            spos, smass, counts = self.stages.route(pos, mass, boxsize)
-            rpos, rmass = self.exchange_particles(spos, smass, counts)
+            self.stages.deposit(pos, mass, cmass, boxsize, which)
+            return
+        if self.placement == "local":
+            # optimistic: every particle of the shard lies in this rank's slab or its ghosts
+            self.stages.deposit(pos, mass, cmass, boxsize, which)
+            bad = torch.tensor([self.stages.rejected()], dtype=torch.int64, device=pos.device)
+            dist.all_reduce(bad, group=self.group)
+            if int(bad.item()) == 0:
+                return
+            if not zero:
+                raise RuntimeError(f"{int(bad.item())} particles lie outside their rank's slab and ghost planes and the "
+                                   "grid already holds earlier deposits: route the particles (placement='route')")
+            self.placement = "route"                                # redo this deposit, and route from now on
+            self.stages.zero(which)
+        spos, smass, counts = self.stages.route(pos, mass, boxsize)
+        rpos, rmass = self.exchange_particles(spos, smass, counts)
         self.stages.deposit(rpos, rmass, cmass, boxsize, which)
 
     def spectrum(self, which=0):

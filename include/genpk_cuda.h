@@ -189,6 +189,21 @@ int genpk_last_order(const genpk_ctx *ctx, int64_t out[7]);
  */
 genpk_ctx *genpk_create_slab(int dims, int device, int nranks, int rank, unsigned flags);
 
+/* Wide-ghost slab: ghost_planes planes are stored on BOTH sides of the owned ones
+ * (ghost_planes <= dims/nranks).  A rank whose particle shard is already slab-local
+ * up to stragglers -- snapshot / lattice order sharded by index range -- deposits it
+ * without any particle exchange: contributions up to ghost_planes planes outside the
+ * slab land in the ghosts and travel with the two-sided ghost exchange below.
+ * Particles further out are counted by genpk_take_rejected() and NOT deposited; the
+ * caller then falls back to genpk_route_particles.  ghost_planes = 0 is genpk_create_slab. */
+genpk_ctx *genpk_create_slab_wide(int dims, int device, int nranks, int rank, unsigned flags, int ghost_planes);
+/* Doubles between the start of the grid allocation (genpk_grid_device_ptr,
+ * genpk_grid_download) and the first owned plane: ghost_planes * dims * fd. */
+size_t genpk_grid_owned_offset(const genpk_ctx *ctx);
+/* Waits for the context's stream, then returns and clears the number of particles the
+ * deposits rejected (outside the slab + ghosts, or non-finite). */
+int genpk_take_rejected(genpk_ctx *ctx, uint64_t *rejected);
+
 /* Destination rank of every particle: floor(x*dims/box) wrapped, / (dims/nranks).
  * Writes counts[nranks] (device int64) and the particles grouped by destination
  * into sorted_pos (device, n*3 floats) / sorted_mass (or NULL). */
@@ -200,6 +215,11 @@ int genpk_route_particles(genpk_ctx *ctx, const float *pos_dev, const float *mas
  * shift), and accumulation of a received plane into local plane 0. */
 void *genpk_ghost_ptr(genpk_ctx *ctx, int which, size_t *bytes);
 int genpk_ghost_accumulate(genpk_ctx *ctx, int which, const void *recv_plane_dev);
+/* The same for either side of a (wide-ghost) slab.  side 1 = high-x ghosts, sent to rank+1,
+ * which adds them into its first owned planes with accumulate(side 0); side 0 = low-x ghosts,
+ * sent to rank-1, which adds them into its last owned planes with accumulate(side 1). */
+void *genpk_ghost_side_ptr(genpk_ctx *ctx, int which, int side, size_t *bytes);
+int genpk_ghost_side_accumulate(genpk_ctx *ctx, int which, int side, const void *recv_planes_dev);
 
 /* Batched 2-D D2Z over the local x-planes (in place). */
 int genpk_slab_fft_yz(genpk_ctx *ctx, int which);

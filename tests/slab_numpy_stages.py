@@ -10,8 +10,12 @@ from oracle.oracle import Oracle, padded_shape
 
 
 class NumpyStages:
-    def __init__(self, dims, nranks, rank):
+    def __init__(self, dims, nranks, rank, ghost_planes=0):
         self.dims, self.nranks, self.rank = dims, nranks, rank
+        self.ghost_planes = ghost_planes if nranks > 1 else 0     # > 0: ghosts on both sides (wide slabs)
+        self.glo = self.ghost_planes
+        self.ghi = (self.ghost_planes or 1) if nranks > 1 else 1
+        self._rejected = 0
         self.nc, self.fd = dims // 2 + 1, 2 * (dims // 2 + 1)
         self.nx = dims // nranks
         self.x0 = rank * self.nx
@@ -33,28 +37,49 @@ class NumpyStages:
         return spos, smass, torch.from_numpy(counts)
 
     def zero(self, which=0):
-        self.grid = np.zeros((self.nx + 1, self.dims, self.fd))
+        self.grid = np.zeros((self.glo + self.nx + self.ghi, self.dims, self.fd))
 
     def deposit(self, pos, mass, cmass, boxsize, which=0):
         p = pos.numpy().reshape(-1, 3)
         if len(p) == 0:
             return
-        ix = self._cell_x(p, boxsize)
-        assert np.all((ix >= self.x0) & (ix < self.x0 + self.nx)), "particle routed to the wrong slab"
+        m = None if mass is None else mass.numpy()
+        # local plane of the low-x corner: periodic image of X - x0 nearest to the slab
+        d = self._cell_x(p, boxsize) - self.x0
+        d = np.where(d < -self.glo, d + self.dims, np.where(d >= self.dims - self.glo, d - self.dims, d))
+        ok = (d >= -self.glo) & (d <= self.nx + self.ghi - 2) if self.nranks > 1 else np.ones(len(p), bool)
+        self._rejected += int((~ok).sum())
+        p, m = p[ok], (None if m is None else m[ok])
+        if len(p) == 0:
+            return
         full = np.zeros(padded_shape(self.dims))
-        self.orc.fieldize(boxsize, self.dims, full, p, None if mass is None else mass.numpy(), cmass, 1)
-        self.grid[: self.nx] += full[self.x0: self.x0 + self.nx]
-        if self.nranks > 1:             # with one rank the periodic wrap already landed in plane 0
-            self.grid[self.nx] += full[(self.x0 + self.nx) % self.dims]
+        self.orc.fieldize(boxsize, self.dims, full, np.ascontiguousarray(p), None if m is None else np.ascontiguousarray(m), cmass, 1)
+        if self.nranks == 1:            # the periodic wrap already landed in plane 0
+            self.grid[: self.nx] += full
+            return
+        # every plane the kept particles can touch, [x0 - glo, x0 + nx + ghi), is distinct modulo dims
+        # as long as glo + nx + ghi <= dims; the caller guarantees it (ghost_planes <= nx, P >= 2 ... see test)
+        planes = (np.arange(-self.glo, self.nx + self.ghi) + self.x0) % self.dims
+        assert len(set(planes.tolist())) == len(planes)
+        self.grid += full[planes]
 
-    def ghost_plane(self, which=0):
-        return torch.from_numpy(self.grid[self.nx].reshape(-1))
+    def rejected(self):
+        r, self._rejected = self._rejected, 0
+        return r
 
-    def ghost_accumulate(self, recv, which=0):
-        self.grid[0] += recv.numpy().reshape(self.dims, self.fd)
+    def ghost_plane(self, which=0, side=1):
+        g = self.grid[self.glo + self.nx:] if side else self.grid[: self.glo]
+        return torch.from_numpy(np.ascontiguousarray(g).reshape(-1))
+
+    def ghost_accumulate(self, recv, which=0, side=0):
+        r = recv.numpy().reshape(-1, self.dims, self.fd)
+        if side == 0:
+            self.grid[self.glo: self.glo + len(r)] += r
+        else:
+            self.grid[self.glo + self.nx - len(r): self.glo + self.nx] += r
 
     def fft_yz(self, which=0):
-        self.spec2d = np.fft.rfft2(self.grid[: self.nx, :, : self.dims], axes=(1, 2))
+        self.spec2d = np.fft.rfft2(self.grid[self.glo: self.glo + self.nx, :, : self.dims], axes=(1, 2))
 
     def pack(self, which=0):
         ny = self.dims // self.nranks

@@ -27,6 +27,54 @@ def _particles(n, box, seed, var_mass):
     return pos, masses
 
 
+def _slab_local_particles(n, box, dims, seed, jitter_cells):
+    """Sorted by x, so index-range shards are x-slabs up to a jitter of a few cells."""
+    rng = np.random.default_rng(seed)
+    pos = (rng.random((n, 3)) * box).astype(np.float32)
+    pos = pos[np.argsort(pos[:, 0], kind="stable")]
+    pos[:, 0] = np.mod(pos[:, 0] + rng.uniform(-jitter_cells, jitter_cells, n) * (box / dims), box).astype(np.float32)
+    return np.ascontiguousarray(pos)
+
+
+def _wide_worker(rank, world, port, dims, n, box, ghost, jitter, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from genpk_b200.distributed import SlabPipeline
+        from tests.slab_numpy_stages import NumpyStages
+        pos = _slab_local_particles(n, box, dims, 9, jitter)
+        lo, hi = rank * n // world, (rank + 1) * n // world
+        pipe = SlabPipeline(dims, NumpyStages(dims, world, rank, ghost))
+        assert pipe.placement == "local"
+        shard = torch.from_numpy(pos[lo:hi].reshape(-1).copy())
+        p, c, k = pipe.pk(shard, None, 0.5, box, 0.5 * n, dims)
+        first = pipe.placement
+        p2, c2, k2 = pipe.pk(shard, None, 0.5, box, 0.5 * n, dims)         # the decision is sticky
+        assert np.array_equal(c, c2) and np.allclose(p, p2, rtol=1e-12)
+        if rank == 0:
+            np.savez(os.path.join(out_dir, "out.npz"), p=p, c=c, k=k, placement=first)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,dims,ghost,jitter,expect", [(2, 32, 4, 2.5, "local"), (4, 32, 3, 2.0, "local"),
+                                                            (2, 32, 2, 6.0, "route"), (4, 16, 1, 3.0, "route")])
+def test_wide_ghost_slabs_skip_the_particle_exchange(tmp_path, port, world, dims, ghost, jitter, expect):
+    """Slab-local shards (sorted by x, stragglers within the ghosts) are deposited without
+    routing; stragglers beyond the ghosts make every rank fall back to the routed path."""
+    n, box = 8000, 64.0
+    mp.spawn(_wide_worker, args=(world, _free_port(), dims, n, box, ghost, jitter, str(tmp_path)), nprocs=world, join=True)
+    got = np.load(tmp_path / "out.npz")
+    assert str(got["placement"]) == expect
+    pos = _slab_local_particles(n, box, dims, 9, jitter)
+    _, pr, cr, kr = port.pk(box, dims, pos, None, 0.5, 0.5 * n, dims)
+    assert np.array_equal(got["c"], cr)
+    nz = cr > 0
+    np.testing.assert_allclose(got["p"][nz], pr[nz], rtol=1e-9)
+
+
 def _worker(rank, world, port, dims, n, box, var_mass, out_dir):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"

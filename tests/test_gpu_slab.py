@@ -156,3 +156,101 @@ def test_slab_pipeline_over_nccl(tmp_path, port):
     nz = cr > 0
     np.testing.assert_allclose(got["p"][nz], pr[nz], rtol=1e-5)
     np.testing.assert_allclose(got["k"][nz], kr[nz], rtol=1e-5)
+
+
+@pytest.mark.parametrize("P,ghost", [(2, 6), (4, 8), (8, 4)])
+def test_wide_ghost_slabs_emulated_on_one_gpu(port, P, ghost):
+    """Wide-ghost slab contexts: every rank deposits its index-range shard of a displaced
+    lattice as it is (no particle exchange); stragglers up to `ghost` planes outside the slab
+    land in the ghost planes on either side and the two-sided ghost exchange puts them where
+    they belong.  Fixed-point mode: the assembled grid equals the single-GPU grid bit for bit."""
+    import torch
+    from genpk_b200.distributed import CudaStages
+    dev = torch.device("cuda", 0)
+    n_side = dims = 64
+    box = 640.0
+    n = n_side ** 3
+    d = torch.empty(3 * n, dtype=torch.float32, device=dev)
+    api.synth_particles_dev(api.SYNTH_LATTICE, 1, n_side, 0, n, box, dims, d.data_ptr())
+    torch.cuda.synchronize()
+    rng = np.random.default_rng(8)
+    pos = d.cpu().numpy().reshape(-1, 3)
+    pos[:, 0] = np.mod(pos[:, 0] + rng.uniform(-(ghost - 1.5), ghost - 1.5, n).astype(np.float32) * np.float32(box / dims), box)
+    pos[:, 1:] += rng.uniform(-3, 3, (n, 2)).astype(np.float32)
+    pos = np.ascontiguousarray(pos, np.float32)
+    want = np.zeros(padded_shape(dims), np.int64)
+    port.fieldize_fixed(box, dims, want, pos, None, 1.0, 1, 40)
+    per = n // P
+    st = [CudaStages(dims, P, r, dev, api.FLAG_FIXED_POINT, ghost) for r in range(P)]
+    nx = dims // P
+    try:
+        for r in range(P):
+            st[r].zero()
+            st[r].deposit(torch.from_numpy(pos[r * per:(r + 1) * per].reshape(-1).copy()).to(dev), None, 1.0, box)
+            assert st[r].rejected() == 0
+        up = [st[r].ghost_plane(0, 1).clone() for r in range(P)]
+        down = [st[r].ghost_plane(0, 0).clone() for r in range(P)]
+        for r in range(P):
+            st[(r + 1) % P].ghost_accumulate(up[r], 0, 0)
+            st[(r - 1) % P].ghost_accumulate(down[r], 0, 1)
+        for r in range(P):
+            part = st[r].ctx.grid_download_fixed().reshape(nx + 2 * ghost, dims, 2 * (dims // 2 + 1))
+            assert np.array_equal(part[ghost:ghost + nx], want[r * nx:(r + 1) * nx]), f"slab {r} differs"
+        # a straggler beyond the ghosts is rejected, not silently dropped or misplaced
+        far = np.array([[((0 * nx + nx + ghost + 2) % dims + 0.5) * box / dims, 1.0, 1.0]], np.float32)
+        st[0].deposit(torch.from_numpy(far.reshape(-1)).to(dev), None, 1.0, box)
+        assert st[0].rejected() == 1
+    finally:
+        for s in st:
+            s.close()
+
+
+def _nccl_wide_worker(rank, world, port, dims, n_side, box, ghost, out_dir):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from genpk_b200.distributed import CudaStages, SlabPipeline
+        n = n_side ** 3
+        first, count = rank * n // world, (rank + 1) * n // world - rank * n // world
+        dpos = torch.empty(3 * count, dtype=torch.float32, device=dev)
+        api.synth_particles_dev(api.SYNTH_CLUSTERED, 42, n_side, first, count, box, dims, dpos.data_ptr())
+        torch.cuda.synchronize()
+        stages = CudaStages(dims, world, rank, dev, 0, ghost)
+        pipe = SlabPipeline(dims, stages)
+        p, c, k = pipe.pk(dpos, None, 1.0, box, float(n), dims)
+        stages.check()
+        if rank == 0:
+            np.savez(os.path.join(out_dir, "out.npz"), p=p, c=c, k=k, placement=pipe.placement)
+        stages.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_wide_ghost_pipeline_over_nccl(tmp_path, port):
+    """The clustered lattice sharded by index range over the GPUs of the box, no particle
+    exchange (placement stays 'local'), against the single-process oracle."""
+    import torch
+    import torch.multiprocessing as mp
+    world = min(torch.cuda.device_count(), 8)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
+    n_side = dims = 128
+    box, ghost = 1000.0, 16
+    mp.spawn(_nccl_wide_worker, args=(world, _free_port(), dims, n_side, box, ghost, str(tmp_path)), nprocs=world, join=True)
+    got = np.load(tmp_path / "out.npz")
+    assert str(got["placement"]) == "local"
+    n = n_side ** 3
+    d = torch.empty(3 * n, dtype=torch.float32, device="cuda:0")
+    api.synth_particles_dev(api.SYNTH_CLUSTERED, 42, n_side, 0, n, box, dims, d.data_ptr())
+    torch.cuda.synchronize()
+    _, pr, cr, kr = port.pk(box, dims, d.cpu().numpy().reshape(-1, 3), None, 1.0, float(n), dims)
+    assert np.array_equal(got["c"], cr)
+    nz = cr > 0
+    np.testing.assert_allclose(got["p"][nz], pr[nz], rtol=1e-5)
+    np.testing.assert_allclose(got["k"][nz], kr[nz], rtol=1e-5)
