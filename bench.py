@@ -61,6 +61,8 @@ def parse_args():
     ap.add_argument("--march-rx", type=int, default=0)
     ap.add_argument("--ghost-planes", type=int, default=16,
                     help="multi-GPU: ghost planes on each side of a slab (0 = always route particles)")
+    ap.add_argument("--no-fused-xpass", action="store_true",
+                    help="cuFFT x pass + bin_power_kernel instead of the fused x-pass/binning kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
@@ -296,8 +298,7 @@ def run_ours(args):
         def step_device():
             ctx.grid_zero()
             ctx.deposit_dev(dpos.data_ptr(), count, 0, 1.0, BOX)
-            ctx.fft()
-            return ctx.power(nrbins, total_mass, total_mass)          # raw sums D2H + normalisation inside
+            return ctx.fft_power(nrbins, total_mass, total_mass)      # raw sums D2H + normalisation inside
 
         def step_host(hpos):
             return ctx.pk_from_particles_ptr(hpos.data_ptr(), count, 1.0, BOX, total_mass, nrbins)
@@ -317,6 +318,9 @@ def run_ours(args):
             d = hpos.to(dev, non_blocking=True)
             return pipe.pk(d, None, 1.0, BOX, total_mass, nrbins)
 
+    if args.no_fused_xpass:
+        ctx.set_option(api.OPT_FUSED_XPASS, 0)
+    fused = ctx.fused_xpass_supported(nrbins)
     if args.lattice_hint and wl["kind"] != "uniform":
         ctx.set_lattice_hint(n_side, n_side)
     if args.march_ry:
@@ -404,7 +408,8 @@ def run_ours(args):
     roofline = dict(roof[dom])
     roofline["kernel"] = {"deposit": "deposit stage (grid zero + order probe + deposit_march_kernel | brick sort + "
                                      "deposit_direct_kernel)",
-                          "binning": "bin_power_kernel"}[dom]
+                          "binning": ("fftx_power_kernel (x pass of the FFT fused with the binning)" if fused
+                                      else "bin_power_kernel")}[dom]
     roofline["peak_source"] = peak_src
 
     line = {
@@ -413,7 +418,8 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl["label"], "particles": n_total, "grid": dims, "nrbins": nrbins, "box": BOX,
                    "accumulation": "int64 fixed-point" if args.fixed_point else "fp64 red.add",
-                   "deposit_mode": args.deposit, "order_probe": ctx.last_order(), "binning_mode": args.power, "parallelism": (f"x-slab x{world}, {ghost} ghost planes, particles {pipe.placement}" if world > 1
+                   "deposit_mode": args.deposit, "order_probe": ctx.last_order(), "binning_mode": args.power,
+                   "x_pass": "fused with binning (fftx_power_kernel)" if fused else "cuFFT", "parallelism": (f"x-slab x{world}, {ghost} ghost planes, particles {pipe.placement}" if world > 1
                                    else "single GPU"),
                    "l2": "inputs larger than L2 (no flush needed)"},
         "pk_time_ms": ms_step,
@@ -422,7 +428,7 @@ def run_ours(args):
         "binning_gcells_per_s": (dims ** 2 * (dims // 2 + 1) / (stage_ms["binning"] * 1e-3) / 1e9)
         if stage_ms["binning"] else None,
         "roofline": roofline, "roofline_all": roof,
-        "gpu_launches": int(launches), "cufft_execs_per_step": 1 if world == 1 else 2,
+        "gpu_launches": int(launches), "cufft_execs_per_step": 1 if (world == 1 or fused) else 2,
         "e2e": e2e, "clocks": clocks,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -40,6 +40,8 @@ SIGNATURES = {
     "genpk_power": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_f64p, c_i32p, c_f64p, C.c_double, C.c_double]),
     "genpk_power_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, c_f64p, c_i32p, c_f64p, C.c_double,
                                   C.c_double]),
+    "genpk_fft_power": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_f64p, c_i32p, c_f64p, C.c_double, C.c_double]),
+    "genpk_fused_xpass_supported": (C.c_int, [C.c_void_p, C.c_int]),
     "genpk_pk_from_particles": (C.c_int, [C.c_void_p, c_f32p, c_f32p, C.c_int64, C.c_double, C.c_double, C.c_double,
                                           C.c_int, c_f64p, c_i32p, c_f64p]),
     "genpk_grid_doubles": (C.c_size_t, [C.c_void_p]),
@@ -67,6 +69,7 @@ SIGNATURES = {
     "genpk_slab_fft_x": (C.c_int, [C.c_void_p, C.c_void_p]),
     "genpk_slab_spectrum_bytes": (C.c_size_t, [C.c_void_p]),
     "genpk_slab_power_partial": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, c_f64p]),
+    "genpk_slab_fftx_power_partial": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, c_f64p]),
     "genpk_power_finalize": (C.c_int, [c_f64p, C.c_int, C.c_double, C.c_double, c_f64p, c_i32p, c_f64p]),
     "genpk_bin_thresholds": (C.c_int, [C.c_int, C.c_int, C.c_uint, C.c_void_p]),
     # synthetic particle sets

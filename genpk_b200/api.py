@@ -18,6 +18,7 @@ FLAG_TWO_FIELDS = 0x2
 FLAG_BINRULE_SOURCE = 0x4
 OPT_DEPOSIT, OPT_SCALE_BITS, OPT_POWER = 1, 2, 3
 OPT_LATTICE_N0, OPT_LATTICE_N1, OPT_MARCH_RY, OPT_MARCH_RX = 4, 5, 6, 7
+OPT_FUSED_XPASS = 8
 POWER_CACHED, POWER_FUSED = 0, 1
 DEPOSIT_AUTO, DEPOSIT_DIRECT, DEPOSIT_SORTED, DEPOSIT_TILED, DEPOSIT_MARCH = 0, 1, 2, 3, 4
 STAGE_DEPOSIT, STAGE_FFT, STAGE_POWER, STAGE_SORT, STAGE_ZERO = 0, 1, 2, 3, 4
@@ -237,6 +238,22 @@ class Context:
                                    float(total_mass), float(total_mass2)), "genpk_power")
         return power, count, keffs
 
+    def fft_power(self, nrbins=None, total_mass=1.0, total_mass2=None, which: int = 0):
+        """genpk_fft + genpk_power as one call; the x transform and the binning share one
+        kernel when the grid side allows (the grid then holds the (y,z)-transformed planes)."""
+        nrbins = self.dims if nrbins is None else int(nrbins)
+        total_mass2 = total_mass if total_mass2 is None else total_mass2
+        power = np.zeros(nrbins, np.float64)
+        count = np.zeros(nrbins, np.int32)
+        keffs = np.zeros(nrbins, np.float64)
+        check(self.lib.genpk_fft_power(self.h, which, nrbins, power.ctypes.data, count.ctypes.data, keffs.ctypes.data,
+                                       float(total_mass), float(total_mass2)), "genpk_fft_power")
+        return power, count, keffs
+
+    def fused_xpass_supported(self, nrbins=None) -> bool:
+        nrbins = self.dims if nrbins is None else int(nrbins)
+        return bool(self.lib.genpk_fused_xpass_supported(self.h, nrbins))
+
     def pk_from_particles(self, positions, masses=None, mass=1.0, boxsize=1.0, total_mass=None, nrbins=None):
         positions = _f32(positions)
         n = positions.size // 3
@@ -341,6 +358,11 @@ class Context:
     def slab_power_partial(self, spec_a_ptr: int, spec_b_ptr: int, nrbins: int, sums_ptr: int):
         check(self.lib.genpk_slab_power_partial(self.h, spec_a_ptr, spec_b_ptr or None, int(nrbins), sums_ptr),
               "genpk_slab_power_partial")
+
+
+    def slab_fftx_power_partial(self, spec_yz_ptr: int, nrbins: int, sums_ptr: int):
+        check(self.lib.genpk_slab_fftx_power_partial(self.h, spec_yz_ptr, int(nrbins), sums_ptr),
+              "genpk_slab_fftx_power_partial")
 
 
 def power_finalize(sums: np.ndarray, nrbins: int, total_mass: float, total_mass2: float):

@@ -326,16 +326,9 @@ static int launch_power(genpk_ctx *ctx, const PowerArgs &A, size_t smem)
     return 0;
 }
 
-// Raw per-bin sums of a spectrum block [n_outer][n_mid][nc] whose first outer
-// (mid) index is global FFT index outer0 (mid0).  sums_dev: 3*nrbins doubles.
-int power_raw(genpk_ctx *ctx, const double *spec_a, const double *spec_b, int n_outer, int outer0, int n_mid,
-              int mid0, int nrbins, double *sums_dev)
+static void fill_power_args(genpk_ctx *ctx, PowerArgs &A, int n_outer, int outer0, int n_mid, int mid0, int nrbins)
 {
-    if (int rc = ensure_tables(ctx, nrbins))
-        return rc;
-    PowerArgs A;
-    A.a = reinterpret_cast<const double2 *>(spec_a);
-    A.b = reinterpret_cast<const double2 *>(spec_b);
+    A.a = A.b = nullptr;
     A.dims = ctx->g.dims;
     A.nc = ctx->g.nc;
     A.n_outer = n_outer;
@@ -355,34 +348,64 @@ int power_raw(genpk_ctx *ctx, const double *spec_a, const double *spec_b, int n_
     A.iw1d = ctx->d_iw1d;
     A.thresh = ctx->d_thresh;
     A.half_bpu = nrbins > 1 ? (float)(0.5 * (nrbins - 1) / log(sqrt(3.0) * A.dims / 2.0)) : 0.f;
-    A.sums = sums_dev;
-    const size_t smem = (size_t)nrbins * (8 + 8 + 4) + (size_t)(nrbins + 1) * 4 + (size_t)(A.dims / 2 + 1) * 4 + 16;
-    const bool cross = spec_b != spec_a;
-    const size_t sums_bytes = (size_t)3 * nrbins * sizeof(double);
+    A.sums = nullptr;
+}
 
-    if (ctx->power_mode == GENPK_POWER_FUSED) {
-        GENPK_CUDA_OK(cudaMemsetAsync(sums_dev, 0, sums_bytes, ctx->stream));
-        return cross ? launch_power<PK_FUSED, true>(ctx, A, smem) : launch_power<PK_FUSED, false>(ctx, A, smem);
-    }
-    // geometry sums cached per block of the spectrum
+static size_t power_smem(const PowerArgs &A)
+{
+    return (size_t)A.nrbins * (8 + 8 + 4) + (size_t)(A.nrbins + 1) * 4 + (size_t)(A.dims / 2 + 1) * 4 + 16;
+}
+
+// sums_dev = {0, K, N}: the P part cleared, sum|k| and the mode counts of the block
+// [n_outer][n_mid][nc] copied from the geometry pass cached in the context (run here on a miss).
+int power_seed_sums(genpk_ctx *ctx, int n_outer, int outer0, int n_mid, int mid0, int nrbins, double *sums_dev)
+{
+    if (int rc = ensure_tables(ctx, nrbins))
+        return rc;
+    const size_t sums_bytes = (size_t)3 * nrbins * sizeof(double);
     const long long key[5] = {nrbins, n_outer, outer0, n_mid, mid0};
     bool hit = ctx->geom_valid;
     for (int i = 0; i < 5 && hit; i++)
         hit = ctx->geom_key[i] == key[i];
     if (!hit) {
         GENPK_CUDA_OK(cudaMemsetAsync(ctx->d_geom, 0, sums_bytes, ctx->stream));
-        PowerArgs G = A;
+        PowerArgs G;
+        fill_power_args(ctx, G, n_outer, outer0, n_mid, mid0, nrbins);
         G.sums = ctx->d_geom;
-        if (int rc = launch_power<PK_GEOM, false>(ctx, G, smem))
+        if (int rc = launch_power<PK_GEOM, false>(ctx, G, power_smem(G)))
             return rc;
         for (int i = 0; i < 5; i++)
             ctx->geom_key[i] = key[i];
         ctx->geom_valid = true;
     }
-    // P from the data pass; K and N copied from the cache
     GENPK_CUDA_OK(cudaMemsetAsync(sums_dev, 0, (size_t)nrbins * sizeof(double), ctx->stream));
     GENPK_CUDA_OK(cudaMemcpyAsync(sums_dev + nrbins, ctx->d_geom + nrbins, (size_t)2 * nrbins * sizeof(double),
                                   cudaMemcpyDeviceToDevice, ctx->stream));
+    return 0;
+}
+
+// Raw per-bin sums of a spectrum block [n_outer][n_mid][nc] whose first outer
+// (mid) index is global FFT index outer0 (mid0).  sums_dev: 3*nrbins doubles.
+int power_raw(genpk_ctx *ctx, const double *spec_a, const double *spec_b, int n_outer, int outer0, int n_mid,
+              int mid0, int nrbins, double *sums_dev)
+{
+    if (int rc = ensure_tables(ctx, nrbins))
+        return rc;
+    PowerArgs A;
+    fill_power_args(ctx, A, n_outer, outer0, n_mid, mid0, nrbins);
+    A.a = reinterpret_cast<const double2 *>(spec_a);
+    A.b = reinterpret_cast<const double2 *>(spec_b);
+    A.sums = sums_dev;
+    const size_t smem = power_smem(A);
+    const bool cross = spec_b != spec_a;
+
+    if (ctx->power_mode == GENPK_POWER_FUSED) {
+        GENPK_CUDA_OK(cudaMemsetAsync(sums_dev, 0, (size_t)3 * nrbins * sizeof(double), ctx->stream));
+        return cross ? launch_power<PK_FUSED, true>(ctx, A, smem) : launch_power<PK_FUSED, false>(ctx, A, smem);
+    }
+    // P from the data pass; K and N from the geometry sums cached per block of the spectrum
+    if (int rc = power_seed_sums(ctx, n_outer, outer0, n_mid, mid0, nrbins, sums_dev))
+        return rc;
     return cross ? launch_power<PK_DATA, true>(ctx, A, smem) : launch_power<PK_DATA, false>(ctx, A, smem);
 }
 

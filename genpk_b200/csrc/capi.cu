@@ -70,6 +70,7 @@ static genpk_ctx *create_common(int dims, int device, int nranks, int rank, unsi
     if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) {
         ctx->sm_count = prop.multiProcessorCount;
         ctx->l2_bytes = (size_t)prop.l2CacheSize;
+        ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
     }
     SlabGeom &g = ctx->g;
     g.dims = dims;
@@ -149,6 +150,7 @@ void genpk_destroy(genpk_ctx *ctx)
     if (ctx->d_brick_counts) cudaFree(ctx->d_brick_counts);
     if (ctx->d_errors) cudaFree(ctx->d_errors);
     if (ctx->d_order) cudaFree(ctx->d_order);
+    if (ctx->d_twiddle) cudaFree(ctx->d_twiddle);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (int i = 0; i < ST_COUNT; i++)
         for (int s = 0; s < genpk_ctx::EV_SLOTS; s++) {
@@ -196,6 +198,10 @@ int genpk_set_option(genpk_ctx *ctx, int option, int64_t value)
     case GENPK_OPT_POWER:
         if (value != GENPK_POWER_CACHED && value != GENPK_POWER_FUSED) break;
         ctx->power_mode = (int)value;
+        return 0;
+    case GENPK_OPT_FUSED_XPASS:
+        if (value != 0 && value != 1) break;
+        ctx->fused_xpass = (int)value;
         return 0;
     }
     set_error("genpk_set_option: bad option %d / value %lld", option, (long long)value);
@@ -271,12 +277,20 @@ int genpk_deposit(genpk_ctx *ctx, int which, const float *positions, const float
     } else {
         // Host particles: chunks go up on the copy stream into two device staging
         // buffers while the previous chunk is being deposited (chunk loop of
-        // read_fieldize.cpp:51-93, overlapped).
+        // read_fieldize.cpp:51-93, overlapped).  The deposit is planned once, on the first
+        // chunk (the only host synchronisation of the loop); when that finds a lattice the
+        // following chunks end on lattice-plane (or row) boundaries so every chunk marches
+        // from a row start.
         const int64_t chunk = n < ((int64_t)1 << 23) ? n : ((int64_t)1 << 23);
         if ((rc = ensure_stage(ctx, chunk, masses != nullptr))) return rc;
         int buf = 0;
-        for (int64_t off = 0; off < n && !rc; off += chunk, buf ^= 1) {
-            const int64_t m = (n - off) < chunk ? (n - off) : chunk;
+        DepositPlan plan;
+        bool planned = false;
+        int64_t unit = 1;
+        for (int64_t off = 0; off < n && !rc; buf ^= 1) {
+            int64_t m = (n - off) < chunk ? (n - off) : chunk;
+            if (planned && off + m < n && m > unit)
+                m = m / unit * unit;
             GENPK_CUDA_OK(cudaStreamWaitEvent(ctx->copy_stream, ctx->stage_free[buf], 0));
             GENPK_CUDA_OK(cudaMemcpyAsync(ctx->d_stage_pos[buf], positions + 3 * off, (size_t)m * 3 * sizeof(float),
                                           cudaMemcpyHostToDevice, ctx->copy_stream));
@@ -288,9 +302,20 @@ int genpk_deposit(genpk_ctx *ctx, int which, const float *positions, const float
             GENPK_CUDA_OK(cudaEventRecord(up, ctx->copy_stream));
             GENPK_CUDA_OK(cudaStreamWaitEvent(ctx->stream, up, 0));
             GENPK_CUDA_OK(cudaEventDestroy(up));
+            if (!planned) {
+                if ((rc = deposit_plan(ctx, ctx->d_stage_pos[buf], m, boxsize, &plan))) break;
+                planned = true;
+                if (plan.mode == GENPK_DEPOSIT_MARCH && plan.n0 > 0) {
+                    const int64_t plane = plan.n1 > 0 ? plan.n0 * plan.n1 : 0;
+                    unit = (plane > 0 && plane <= chunk) ? plane : (plan.n0 <= chunk ? plan.n0 : 1);
+                    if (off + m < n && m > unit)
+                        m = m / unit * unit;           // the tail of this upload goes up again with the next chunk
+                }
+            }
             rc = deposit_device(ctx, which, ctx->d_stage_pos[buf], masses ? ctx->d_stage_mass[buf] : nullptr, m, mass,
-                                boxsize);
+                                boxsize, &plan);
             GENPK_CUDA_OK(cudaEventRecord(ctx->stage_free[buf], ctx->stream));
+            off += m;
         }
     }
     stage_end(ctx, ST_DEPOSIT);
@@ -360,13 +385,38 @@ int genpk_power_dev(genpk_ctx *ctx, const void *spec_a_dev, const void *spec_b_d
     return power_on(ctx, a, b, nrbins, power, count, keffs, total_mass, total_mass2);
 }
 
+int genpk_fft_power(genpk_ctx *ctx, int which, int nrbins, double *power, int *count, double *keffs, double total_mass,
+                    double total_mass2)
+{
+    if (!check_which(ctx, which, "genpk_fft_power")) return 1;
+    if (nrbins < 1 || !power || !count || !keffs) { set_error("genpk_fft_power: bad arguments"); return 1; }
+    if (ctx->g.nranks != 1) { set_error("genpk_fft_power: slab contexts use genpk_slab_fftx_power_partial"); return 1; }
+    if (!fftx_supported(ctx, nrbins)) {                    // other grid sides: the library transform + the binning pass
+        if (int rc = genpk_fft(ctx, which)) return rc;
+        return genpk_power(ctx, which, which, nrbins, power, count, keffs, total_mass, total_mass2);
+    }
+    if (int rc = ensure_tables(ctx, nrbins)) return rc;
+    stage_begin(ctx, ST_FFT);
+    if (int rc = fixed_to_double(ctx, which)) return rc;
+    if (int rc = fft_yz(ctx, which)) return rc;
+    stage_end(ctx, ST_FFT);
+    stage_begin(ctx, ST_POWER);
+    if (int rc = fftx_power_raw(ctx, ctx->grid[which], ctx->g.dims, 0, nrbins, ctx->d_sums)) return rc;
+    stage_end(ctx, ST_POWER);
+    GENPK_CUDA_OK(cudaMemcpyAsync(ctx->h_sums, ctx->d_sums, (size_t)3 * nrbins * sizeof(double), cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+    GENPK_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    return genpk_power_finalize(ctx->h_sums, nrbins, total_mass, total_mass2, power, count, keffs);
+}
+
+int genpk_fused_xpass_supported(const genpk_ctx *ctx, int nrbins) { return ctx && fftx_supported(ctx, nrbins) ? 1 : 0; }
+
 int genpk_pk_from_particles(genpk_ctx *ctx, const float *positions, const float *masses, int64_t n, double mass,
                             double boxsize, double total_mass, int nrbins, double *power, int *count, double *keffs)
 {
     if (int rc = genpk_grid_zero(ctx, 0)) return rc;
     if (int rc = genpk_deposit(ctx, 0, positions, masses, n, mass, boxsize, 0)) return rc;
-    if (int rc = genpk_fft(ctx, 0)) return rc;
-    if (int rc = genpk_power(ctx, 0, 0, nrbins, power, count, keffs, total_mass, total_mass)) return rc;
+    if (int rc = genpk_fft_power(ctx, 0, nrbins, power, count, keffs, total_mass, total_mass)) return rc;
     return genpk_synchronize(ctx);
 }
 
@@ -539,6 +589,16 @@ int genpk_slab_power_partial(genpk_ctx *ctx, const void *spec_a_dev, const void 
     if (int rc = power_raw(ctx, (const double *)spec_a_dev, (const double *)(spec_b_dev ? spec_b_dev : spec_a_dev),
                            ctx->g.dims, 0, ny, ctx->g.rank * ny, nrbins, sums_dev))
         return rc;
+    stage_end(ctx, ST_POWER);
+    return 0;
+}
+
+int genpk_slab_fftx_power_partial(genpk_ctx *ctx, const void *spec_yz_dev, int nrbins, double *sums_dev)
+{
+    if (!ctx || !spec_yz_dev || !sums_dev || nrbins < 1) { set_error("genpk_slab_fftx_power_partial: bad arguments"); return 1; }
+    const int ny = ctx->g.dims / ctx->g.nranks;
+    stage_begin(ctx, ST_POWER);
+    if (int rc = fftx_power_raw(ctx, (const double *)spec_yz_dev, ny, ctx->g.rank * ny, nrbins, sums_dev)) return rc;
     stage_end(ctx, ST_POWER);
     return 0;
 }

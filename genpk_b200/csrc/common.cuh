@@ -114,6 +114,12 @@ struct genpk_ctx {
     void *d_order = nullptr;                  // OrderInfo written by the order probe
     long long lattice_n0 = 0, lattice_n1 = 0; // caller's hint: particles per lattice row, rows per plane
     int march_ry = 8, march_rx = 8;           // rows / planes one warp marches over
+
+    // fused x pass (fftx_power.cu)
+    int fused_xpass = 1;                      // 0: always cuFFT's x pass + bin_power_kernel
+    int smem_optin = 0;                       // opt-in shared memory per CTA of this device
+    double *d_twiddle = nullptr;              // exp(-2 pi i t/dims), t < dims
+    int twiddle_n = 0;
     long long last_order[7] = {0, 0, 0, 0, 0, 0, 0};   // last probe verdict (diagnostics)
 
     // timing: a ring of event pairs per stage, summed on request (no host sync while recording)
@@ -127,13 +133,23 @@ struct genpk_ctx {
 namespace genpk {
 
 // deposit.cu
+struct DepositPlan {
+    int mode = 0;                 // GENPK_DEPOSIT_DIRECT / SORTED / MARCH
+    long long n0 = 0, n1 = 0;     // lattice row length / rows per plane (MARCH)
+};
+int deposit_plan(genpk_ctx *ctx, const float *pos, int64_t n, double boxsize, DepositPlan *plan);
+// plan == nullptr: planned here (one order probe, one small D2H)
 int deposit_device(genpk_ctx *ctx, int which, const float *pos, const float *masses, int64_t n,
-                   double mass, double boxsize);
+                   double mass, double boxsize, const DepositPlan *plan = nullptr);
 int fixed_to_double(genpk_ctx *ctx, int which);
 // binpower.cu
 int ensure_tables(genpk_ctx *ctx, int nrbins);
 int power_raw(genpk_ctx *ctx, const double *spec_a, const double *spec_b, int n_outer, int outer0,
               int n_mid, int mid0, int nrbins, double *sums_dev);
+int power_seed_sums(genpk_ctx *ctx, int n_outer, int outer0, int n_mid, int mid0, int nrbins, double *sums_dev);
+// fftx_power.cu
+bool fftx_supported(const genpk_ctx *ctx, int nrbins);
+int fftx_power_raw(genpk_ctx *ctx, const double *spec_yz, int n_mid, int mid0, int nrbins, double *sums_dev);
 // fft.cu
 int fft_3d(genpk_ctx *ctx, int which);
 int fft_yz(genpk_ctx *ctx, int which);

@@ -344,7 +344,7 @@ int route_particles(genpk_ctx *ctx, const float *pos, const float *mass, int64_t
 }
 
 int deposit_device(genpk_ctx *ctx, int which, const float *pos, const float *masses, int64_t n,
-                   double mass, double boxsize)
+                   double mass, double boxsize, const DepositPlan *plan)
 {
     const SlabGeom &g = ctx->g;
     if (n <= 0)
@@ -376,6 +376,36 @@ int deposit_device(genpk_ctx *ctx, int which, const float *pos, const float *mas
     // MARCH: lattice-march kernel (deposit_march.cu).  AUTO: a probe of the head of
     // the stream decides -- lattice order => MARCH, merely coherent (or a grid that
     // fits in L2) => DIRECT, incoherent => SORTED.  The verdict is one small D2H.
+    DepositPlan local;
+    if (!plan) {
+        if (int rc = deposit_plan(ctx, pos, n, boxsize, &local))
+            return rc;
+        plan = &local;
+    }
+    if (plan->mode == GENPK_DEPOSIT_MARCH)
+        return launch_march(ctx, a, plan->n0, plan->n1);
+    if (plan->mode == GENPK_DEPOSIT_SORTED) {
+        const BrickMap bm = choose_bricks(ctx, a.units);
+        if (bm.nbricks > 1 && bm.nbricks <= SORT_MAX_KEYS) {
+            stage_begin(ctx, ST_SORT);
+            if (int rc = ensure_sorted_scratch(ctx, n, masses != nullptr))
+                return rc;
+            if (int rc = sort_by_brick(ctx, pos, masses, n, bm, ctx->d_sorted_pos, ctx->d_sorted_mass, nullptr))
+                return rc;
+            stage_end(ctx, ST_SORT);
+            a.pos = ctx->d_sorted_pos;
+            a.mass = masses ? ctx->d_sorted_mass : nullptr;
+        }
+    }
+    return launch_direct(ctx, a);
+}
+
+// Which kernels a deposit of these particles will use (the order probe runs here when the
+// mode is AUTO or MARCH without a hint).  A plan may be reused for the following chunks of
+// the same stream: it is only ever a performance choice, every kernel is exact for any input.
+int deposit_plan(genpk_ctx *ctx, const float *pos, int64_t n, double boxsize, DepositPlan *plan)
+{
+    const SlabGeom &g = ctx->g;
     int mode = ctx->deposit_mode;
     if (mode == GENPK_DEPOSIT_TILED)
         mode = GENPK_DEPOSIT_AUTO;
@@ -386,7 +416,7 @@ int deposit_device(genpk_ctx *ctx, int which, const float *pos, const float *mas
         mode = GENPK_DEPOSIT_DIRECT;
     if (mode == GENPK_DEPOSIT_AUTO || (mode == GENPK_DEPOSIT_MARCH && n0 <= 0)) {
         OrderInfo info;
-        if (int rc = probe_order(ctx, pos, n, a.units, &info))
+        if (int rc = probe_order(ctx, pos, n, g.dims / boxsize, &info))
             return rc;
         ctx->last_order[0] = info.coherent;
         ctx->last_order[1] = info.lattice;
@@ -401,22 +431,10 @@ int deposit_device(genpk_ctx *ctx, int which, const float *pos, const float *mas
             mode = info.lattice ? GENPK_DEPOSIT_MARCH
                                 : ((info.coherent || fits_l2) ? GENPK_DEPOSIT_DIRECT : GENPK_DEPOSIT_SORTED);
     }
-    if (mode == GENPK_DEPOSIT_MARCH)
-        return launch_march(ctx, a, n0, n1);
-    if (mode == GENPK_DEPOSIT_SORTED) {
-        const BrickMap bm = choose_bricks(ctx, a.units);
-        if (bm.nbricks > 1 && bm.nbricks <= SORT_MAX_KEYS) {
-            stage_begin(ctx, ST_SORT);
-            if (int rc = ensure_sorted_scratch(ctx, n, masses != nullptr))
-                return rc;
-            if (int rc = sort_by_brick(ctx, pos, masses, n, bm, ctx->d_sorted_pos, ctx->d_sorted_mass, nullptr))
-                return rc;
-            stage_end(ctx, ST_SORT);
-            a.pos = ctx->d_sorted_pos;
-            a.mass = masses ? ctx->d_sorted_mass : nullptr;
-        }
-    }
-    return launch_direct(ctx, a);
+    plan->mode = mode;
+    plan->n0 = n0;
+    plan->n1 = n1;
+    return 0;
 }
 
 int fixed_to_double(genpk_ctx *ctx, int which)

@@ -1,0 +1,260 @@
+// Thread-level pieces of the fused x-pass: a length-N complex FFT along x of a
+// tile [N][C] of the spectrum (C adjacent kz columns, N*C = 8192 modes), followed by
+// the |delta_k|^2 binning of powerspectrum.c:35-110 on the tile -- so the x-transformed
+// spectrum is never written back to HBM.
+//
+// This header compiles for the device (fftx_power.cu) AND for the host
+// (tests/fftx_emu.cpp, which runs the phases thread by thread over a plain array in
+// place of shared memory and checks them against numpy): the index maps, twiddles,
+// butterflies, swizzles and the bin walk are verified on the CPU, the kernel adds only
+// the data movement and the barriers between phases.
+//
+// FFT: N = R1*R2*R3 (Cooley-Tukey, three register passes, two exchanges), forward and
+// unnormalised, exp(-2 pi i n k / N) -- the convention of FFTW/cuFFT (gen-pk.cpp:193,233).
+// A thread owns 16 elements in every pass; T = N/16 threads work on one column.
+//
+//   n = M1*j + n2        (M1 = R2*R3)   pass 1: DFT-R1 over j,  times W_N^(n2*k1)
+//   n2 = R3*m1 + m2                     pass 2: DFT-R2 over m1, times W_N^(R1*m2*q1)
+//                                       pass 3: DFT-R3 over m2
+//   k = k1 + R1*(q1 + R2*q2)
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define FX_HD __host__ __device__ __forceinline__
+#else
+#define FX_HD inline
+#endif
+
+namespace genpk {
+namespace fftx {
+
+#if defined(__CUDACC__)
+typedef double2 cd;
+#else
+struct alignas(16) cd {
+    double x, y;
+};
+#endif
+
+FX_HD cd cadd(cd a, cd b) { cd r; r.x = a.x + b.x; r.y = a.y + b.y; return r; }
+FX_HD cd csub(cd a, cd b) { cd r; r.x = a.x - b.x; r.y = a.y - b.y; return r; }
+FX_HD cd cmul(cd a, cd w)
+{
+    cd r;
+    r.x = a.x * w.x - a.y * w.y;
+    r.y = a.x * w.y + a.y * w.x;
+    return r;
+}
+
+// a * exp(-2 pi i K/16), K in [0, 8), constants folded at compile time
+template <int K> FX_HD cd mulw16(cd a)
+{
+    const double c1 = 0.92387953251128673848, s1 = 0.38268343236508978178, h = 0.70710678118654752440;
+    cd r;
+    if (K == 0) { r = a; }
+    else if (K == 4) { r.x = a.y; r.y = -a.x; }
+    else if (K == 2) { r.x = (a.x + a.y) * h; r.y = (a.y - a.x) * h; }
+    else if (K == 6) { r.x = (a.y - a.x) * h; r.y = -(a.x + a.y) * h; }
+    else if (K == 1) { r.x = a.x * c1 + a.y * s1; r.y = a.y * c1 - a.x * s1; }
+    else if (K == 3) { r.x = a.x * s1 + a.y * c1; r.y = a.y * s1 - a.x * c1; }
+    else if (K == 5) { r.x = a.y * c1 - a.x * s1; r.y = -(a.y * s1) - a.x * c1; }
+    else { r.x = a.y * s1 - a.x * c1; r.y = -(a.y * c1) - a.x * s1; }
+    return r;
+}
+
+template <int R> struct Dft;
+template <int R, int K> struct Comb {
+    static FX_HD void run(cd *v, const cd *e, const cd *o)
+    {
+        const cd t = mulw16<K * (16 / R)>(o[K]);
+        v[K] = cadd(e[K], t);
+        v[K + R / 2] = csub(e[K], t);
+        Comb<R, K - 1>::run(v, e, o);
+    }
+};
+template <int R> struct Comb<R, -1> {
+    static FX_HD void run(cd *, const cd *, const cd *) {}
+};
+// forward DFT of R values in place, natural order in and out (radix-2 decimation in time,
+// fully unrolled: every index below is a compile-time constant)
+template <int R> struct Dft {
+    static FX_HD void run(cd *v)
+    {
+        cd e[R / 2], o[R / 2];
+#pragma unroll
+        for (int k = 0; k < R / 2; k++) {
+            e[k] = v[2 * k];
+            o[k] = v[2 * k + 1];
+        }
+        Dft<R / 2>::run(e);
+        Dft<R / 2>::run(o);
+        Comb<R, R / 2 - 1>::run(v, e, o);
+    }
+};
+template <> struct Dft<1> {
+    static FX_HD void run(cd *) {}
+};
+
+constexpr int TILE_MODES = 8192;      // modes per tile: 128 KB of complex doubles
+constexpr int EPT = 16;               // elements per thread
+constexpr int CTA_THREADS = TILE_MODES / EPT;
+
+template <int R1_, int R2_, int R3_> struct Plan {
+    static constexpr int R1 = R1_, R2 = R2_, R3 = R3_;
+    static constexpr int N = R1 * R2 * R3;
+    static constexpr int M1 = R2 * R3;
+    static constexpr int T = N / EPT;             // threads per column
+    static constexpr int C = TILE_MODES / N;      // columns per tile
+    static constexpr int LOG_R1 = R1 == 16 ? 4 : (R1 == 8 ? 3 : (R1 == 4 ? 2 : 1));
+    static_assert(EPT % R1 == 0 && EPT % R2 == 0 && EPT % R3 == 0, "a thread owns whole butterflies");
+    static_assert(R2 >= 4 && R3 >= 4, "the exchange swizzle uses two bits");
+
+    // x index of a thread's i-th element before pass 1
+    static FX_HD int load_n(int t, int i) { return M1 * (i % R1) + t + T * (i / R1); }
+
+    static FX_HD void pass1(cd *v, int t, const cd *tw)
+    {
+#pragma unroll
+        for (int u = 0; u < EPT / R1; u++) {
+            Dft<R1>::run(v + u * R1);
+            const int n2 = t + T * u;
+#pragma unroll
+            for (int k1 = 1; k1 < R1; k1++)
+                v[u * R1 + k1] = cmul(v[u * R1 + k1], tw[n2 * k1]);
+        }
+    }
+    // exchange 1: y[k1][n2]
+    static FX_HD int ex1_w(int t, int i) { return (i % R1) * M1 + t + T * (i / R1); }
+    static FX_HD int ex1_r(int t, int i)
+    {
+        const int v2 = t + T * (i / R2), m1 = i % R2;
+        return (v2 / R3) * M1 + R3 * m1 + (v2 % R3);
+    }
+    static FX_HD void pass2(cd *w, int t, const cd *tw)
+    {
+#pragma unroll
+        for (int u = 0; u < EPT / R2; u++) {
+            Dft<R2>::run(w + u * R2);
+            const int m2 = (t + T * u) % R3;
+#pragma unroll
+            for (int q1 = 1; q1 < R2; q1++)
+                w[u * R2 + q1] = cmul(w[u * R2 + q1], tw[R1 * m2 * q1]);
+        }
+    }
+    // exchange 2: z[k1][q1][m2], m2 swizzled by q1 so that both the writers (lanes along
+    // m2) and the readers (lanes along q1) spread over the banks
+    static FX_HD int ex2_w(int t, int i)
+    {
+        const int v2 = t + T * (i / R2), q1 = i % R2;
+        return (v2 / R3) * M1 + q1 * R3 + ((v2 % R3) ^ (q1 & 3));
+    }
+    static FX_HD int ex2_r(int t, int i)
+    {
+        const int v3 = t + T * (i / R3), m2 = i % R3;
+        const int q1 = v3 % R2;
+        return (v3 / R2) * M1 + q1 * R3 + (m2 ^ (q1 & 3));
+    }
+    static FX_HD void pass3(cd *v)
+    {
+#pragma unroll
+        for (int u = 0; u < EPT / R3; u++)
+            Dft<R3>::run(v + u * R3);
+    }
+    // FFT index of a thread's i-th element after pass 3
+    static FX_HD int out_k(int t, int i)
+    {
+        const int v3 = t + T * (i / R3), q2 = i % R3;
+        return (v3 / R2) + R1 * ((v3 % R2) + R2 * q2);
+    }
+    // where |X[k]|^2 waits for the bin walk (bank swizzle only; any bijection is correct)
+    static FX_HD int slot(int k) { return k ^ (((k >> 3) ^ (R1 == 8 ? 0 : (k >> LOG_R1))) & 3); }
+};
+
+// ---------------------------------------------------------------------------------
+// Bin walk (powerspectrum.c:56-99 for one (ky, kz) column of the tile): thread t owns
+// |kx| = 8t+1 .. 8t+8 (thread 0 also kx = 0); the +kx and -kx modes share bin and window,
+// so their |X|^2 are added first.  Along the walk |k| grows slowly and the thread keeps a
+// run (bin, sum) in registers, touching the CTA's histogram only when the bin changes.
+// ---------------------------------------------------------------------------------
+struct Run {
+    int bin;
+    unsigned lo, hi;      // thresh[bin], thresh[bin+1]; hi == 0: no run yet
+    double p;
+    int n;
+};
+
+#if defined(__CUDA_ARCH__)
+#define FX_HIST_ADD(ptr, val) atomicAdd((ptr), (val))
+#define FX_LOGF(x) __logf(x)
+#else
+#define FX_HIST_ADD(ptr, val) (*(ptr) += (val))
+#define FX_LOGF(x) logf(x)
+#endif
+
+FX_HD void run_flush(const Run &r, int mult, double *sP)
+{
+    if (r.n)
+        FX_HIST_ADD(&sP[r.bin], r.p * mult);
+}
+
+FX_HD void run_seek(Run &r, unsigned k2, const unsigned *sT, int nrbins, float half_bpu)
+{
+    int b = r.bin;
+    if (r.hi == 0) {                                   // first guess only; the walk below makes it exact
+        b = (int)(half_bpu * FX_LOGF((float)k2));
+        b = b < 0 ? 0 : (b > nrbins - 1 ? nrbins - 1 : b);
+    }
+    while (k2 >= sT[b + 1]) b++;
+    while (k2 < sT[b]) b--;
+    r.bin = b;
+    r.lo = sT[b];
+    r.hi = sT[b + 1];
+    r.p = 0.0;
+    r.n = 0;
+}
+
+// one |kx| step: mod2sum = |X[kx]|^2 (+ |X[-kx]|^2), fwin = (iwx*iwy)*iwz in float (fieldize.cpp:129-132)
+FX_HD void run_add(Run &r, unsigned k2, double mod2sum, float fwin, int mult, const unsigned *sT, int nrbins,
+                   float half_bpu, double *sP)
+{
+    if (k2 == 0)
+        return;                                        // DC mode, powerspectrum.c:63
+    if (k2 < r.lo || k2 >= r.hi) {
+        run_flush(r, mult, sP);
+        run_seek(r, k2, sT, nrbins, half_bpu);
+    }
+    double w = (double)fwin;                           // float product promoted, fieldize.cpp:132
+    w = w * w;                                         // invwindow() = prod^2
+    w = w * w;                                         // pow(invwindow,2), powerspectrum.c:68
+    r.p = fma(mod2sum, w, r.p);
+    r.n = 1;
+}
+
+// P: the tile's |X|^2 in slot order, [N][C] doubles.  c: column of this thread, kz its global kz.
+template <class PL>
+FX_HD void bin_walk(const double *P, int t, int c, int kj, int kz, int dims_half, const float *sW, const unsigned *sT,
+                    int nrbins, float half_bpu, double *sP)
+{
+    constexpr int N = PL::N, C = PL::C;
+    const int mult = (kz == 0 || kz == dims_half) ? 1 : 2;          // powerspectrum.c:59-89
+    const float fj = sW[kj < 0 ? -kj : kj], fz = sW[kz];
+    const unsigned base2 = (unsigned)(kj * kj) + (unsigned)(kz * kz);
+    Run r;
+    r.bin = 0; r.lo = 0; r.hi = 0; r.p = 0.0; r.n = 0;
+    if (t == 0)
+        run_add(r, base2, P[PL::slot(0) * C + c], (sW[0] * fj) * fz, mult, sT, nrbins, half_bpu, sP);
+#pragma unroll
+    for (int s = 1; s <= 8; s++) {
+        const int a = 8 * t + s;                                    // |kx|
+        double m = P[PL::slot(a) * C + c];
+        if (a < N / 2)
+            m += P[PL::slot(N - a) * C + c];
+        run_add(r, base2 + (unsigned)(a * a), m, (sW[a] * fj) * fz, mult, sT, nrbins, half_bpu, sP);
+    }
+    run_flush(r, mult, sP);
+}
+
+}  // namespace fftx
+}  // namespace genpk

@@ -1,0 +1,247 @@
+// Fused x-pass: the last 1-D transform of the r2c FFT (gen-pk.cpp:233) and the
+// |delta_k|^2 binning of powerspectrum() (powerspectrum.c:35-110) in ONE kernel.
+//
+// Input: the spectrum after the batched 2-D (y,z) transform, [x][n_mid][nc] complex
+// doubles.  A tile is the N x-values of C adjacent kz columns of one ky row (N*C = 8192
+// modes = 128 KB).  One persistent CTA of 512 threads per SM:
+//
+//   cp.async   next tile  -> shared memory (128 KB, natural [x][c] layout)   } overlapped with
+//   registers  <- this tile; three register passes of the length-N FFT       } the passes below
+//   two exchanges between the passes through a 64 KB shared buffer (real and imaginary
+//     halves one after the other; layouts chosen so that both sides are conflict free)
+//   |X|^2 -> the same buffer in kx order; bin walk along |kx| with the +-kx modes folded
+//     (same run/threshold scheme as bin_power_kernel) into the CTA's histogram
+//
+// so the x-transformed spectrum is never written and never re-read: this pass moves
+// 16 B/mode once (8.6 GB at 1024^3) where cuFFT's in-place x pass plus bin_power_kernel
+// move 48 B/mode.  Thread-level arithmetic lives in fftx_core.cuh, which is also compiled
+// for the host and checked against numpy (tests/test_fftx_core.py).
+//
+// Supported: dims in {256, 512, 1024, 2048}, auto spectra.  Everything else (other sizes,
+// cross spectra, callers that want the transformed grid) keeps the cuFFT + bin_power path.
+#include "common.cuh"
+#include "fftx_core.cuh"
+
+namespace genpk {
+
+using namespace fftx;
+
+struct FftxArgs {
+    const double2 *spec;      // [dims][n_mid][nc]
+    const double2 *tw;        // exp(-2 pi i t / dims), t < dims
+    int dims, nc, n_mid, mid0;
+    long long x_stride;       // modes between consecutive x: n_mid * nc
+    int groups;               // column groups per (x, mid) row: ceil(nc / C)
+    long long n_tiles;        // n_mid * groups
+    int nrbins;
+    const float *iw1d;
+    const uint32_t *thresh;
+    float half_bpu;
+    double *sums;             // nrbins P sums, accumulated into
+};
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+template <class PL>
+__global__ void __launch_bounds__(CTA_THREADS, 1) fftx_power_kernel(const __grid_constant__ FftxArgs A)
+{
+    constexpr int N = PL::N, C = PL::C;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2 *const stage = reinterpret_cast<double2 *>(smem_raw);                       // [N][C], next tile
+    double *const E = reinterpret_cast<double *>(smem_raw + (size_t)TILE_MODES * 16);   // [N][C] exchange / |X|^2
+    double *const sP = E + TILE_MODES;
+    unsigned *const sT = reinterpret_cast<unsigned *>(sP + A.nrbins);                   // nrbins + 1
+    float *const sW = reinterpret_cast<float *>(sT + A.nrbins + 1);                     // dims/2 + 1
+
+    const int tid = threadIdx.x;
+    const int c = tid % C, t = tid / C;
+    for (int i = tid; i < A.nrbins; i += CTA_THREADS)
+        sP[i] = 0.0;
+    for (int i = tid; i <= A.nrbins; i += CTA_THREADS)
+        sT[i] = A.thresh[i];
+    for (int i = tid; i <= N / 2; i += CTA_THREADS)
+        sW[i] = A.iw1d[i];
+
+    // a thread copies exactly the 16 staging slots it later reads: no barrier guards the staging buffer
+    auto issue = [&](long long tile) {
+        if (tile < A.n_tiles) {
+            const int g = (int)(tile % A.groups);
+            const long long m = tile / A.groups;
+            const int kz = g * C + c;
+            if (kz < A.nc) {
+                const double2 *src = A.spec + (size_t)m * A.nc + kz;
+#pragma unroll
+                for (int i = 0; i < EPT; i++) {
+                    const int n = PL::load_n(t, i);
+                    cp_async16(stage + n * C + c, src + (size_t)n * A.x_stride);
+                }
+            }
+        }
+        cp_async_commit_group();
+    };
+
+    long long tile = blockIdx.x;
+    issue(tile);
+    for (; tile < A.n_tiles; tile += gridDim.x) {
+        const int g = (int)(tile % A.groups);
+        const int m = (int)(tile / A.groups);
+        const int kz = g * C + c;
+        const bool valid = kz < A.nc;
+        int kj = A.mid0 + m;
+        kj = kj <= A.dims / 2 ? kj : kj - A.dims;                    // KVAL, powerspectrum.c:33
+
+        cd v[EPT], w[EPT];
+        cp_async_wait_all();
+#pragma unroll
+        for (int i = 0; i < EPT; i++) {
+            v[i] = valid ? stage[PL::load_n(t, i) * C + c] : make_double2(0.0, 0.0);
+        }
+        PL::pass1(v, t, A.tw);
+        issue(tile + gridDim.x);                                     // the registers above are consumed: slots are free
+
+        __syncthreads();                                             // the previous tile's bin walk has left E
+#pragma unroll
+        for (int i = 0; i < EPT; i++) E[PL::ex1_w(t, i) * C + c] = v[i].x;
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < EPT; i++) w[i].x = E[PL::ex1_r(t, i) * C + c];
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < EPT; i++) E[PL::ex1_w(t, i) * C + c] = v[i].y;
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < EPT; i++) w[i].y = E[PL::ex1_r(t, i) * C + c];
+        PL::pass2(w, t, A.tw);
+
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < EPT; i++) E[PL::ex2_w(t, i) * C + c] = w[i].x;
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < EPT; i++) v[i].x = E[PL::ex2_r(t, i) * C + c];
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < EPT; i++) E[PL::ex2_w(t, i) * C + c] = w[i].y;
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < EPT; i++) v[i].y = E[PL::ex2_r(t, i) * C + c];
+        PL::pass3(v);
+
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < EPT; i++)
+            E[PL::slot(PL::out_k(t, i)) * C + c] = fma(v[i].x, v[i].x, v[i].y * v[i].y);
+        __syncthreads();
+        if (valid)
+            bin_walk<PL>(E, t, c, kj, kz, A.dims / 2, sW, sT, A.nrbins, A.half_bpu, sP);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    for (int i = tid; i < A.nrbins; i += CTA_THREADS)
+        if (sP[i] != 0.0)
+            atomicAdd(&A.sums[i], sP[i]);
+}
+
+size_t fftx_smem_bytes(int dims, int nrbins)
+{
+    return (size_t)TILE_MODES * 16 + (size_t)TILE_MODES * 8 + (size_t)nrbins * 8 + (size_t)(nrbins + 1) * 4 +
+           (size_t)(dims / 2 + 1) * 4 + 16;
+}
+
+bool fftx_supported(const genpk_ctx *ctx, int nrbins)
+{
+    const int d = ctx->g.dims;
+    if (ctx->fused_xpass == 0)
+        return false;
+    if (d != 256 && d != 512 && d != 1024 && d != 2048)
+        return false;
+    return nrbins >= 1 && fftx_smem_bytes(d, nrbins) <= (size_t)ctx->smem_optin;
+}
+
+static int ensure_twiddles(genpk_ctx *ctx)
+{
+    const int d = ctx->g.dims;
+    if (ctx->d_twiddle && ctx->twiddle_n == d)
+        return 0;
+    if (ctx->d_twiddle) cudaFree(ctx->d_twiddle);
+    ctx->d_twiddle = nullptr;
+    std::vector<double> h(2 * (size_t)d);
+    const long double tau = 6.283185307179586476925286766559005768L;
+    for (int t = 0; t < d; t++) {
+        // exact values on the axes and diagonals, long-double libm elsewhere
+        const long double a = tau * (long double)t / (long double)d;
+        double cr = (double)cosl(a), si = (double)sinl(a);
+        if (4 * t % d == 0) {
+            const int q = 4 * t / d;                       // multiples of pi/2
+            cr = q == 0 ? 1.0 : (q == 2 ? -1.0 : 0.0);
+            si = q == 1 ? 1.0 : (q == 3 ? -1.0 : 0.0);
+        }
+        h[2 * (size_t)t] = cr;
+        h[2 * (size_t)t + 1] = -si;
+    }
+    GENPK_CUDA_OK(cudaMalloc(&ctx->d_twiddle, h.size() * sizeof(double)));
+    GENPK_CUDA_OK(cudaMemcpyAsync(ctx->d_twiddle, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    GENPK_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    ctx->twiddle_n = d;
+    return 0;
+}
+
+template <class PL> static int launch_fftx(genpk_ctx *ctx, const FftxArgs &A, size_t smem)
+{
+    auto kern = fftx_power_kernel<PL>;
+    GENPK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long ctas = ctx->sm_count;
+    if (ctas > A.n_tiles) ctas = A.n_tiles;
+    if (ctas < 1) ctas = 1;
+    kern<<<(int)ctas, CTA_THREADS, smem, ctx->stream>>>(A);
+    ctx->launches++;
+    GENPK_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// P sums of the block [dims][n_mid][nc] of a (y,z)-transformed spectrum whose first mid
+// row is global ky index mid0, with the x transform done on the fly.  sums_dev: 3*nrbins
+// doubles (P from this pass, K and N from the cached geometry pass).
+int fftx_power_raw(genpk_ctx *ctx, const double *spec_yz, int n_mid, int mid0, int nrbins, double *sums_dev)
+{
+    if (!fftx_supported(ctx, nrbins)) {
+        set_error("fused x pass: unsupported grid side %d / nrbins %d", ctx->g.dims, nrbins);
+        return 1;
+    }
+    if (int rc = ensure_tables(ctx, nrbins)) return rc;
+    if (int rc = ensure_twiddles(ctx)) return rc;
+    if (int rc = power_seed_sums(ctx, ctx->g.dims, 0, n_mid, mid0, nrbins, sums_dev)) return rc;
+    FftxArgs A;
+    A.spec = reinterpret_cast<const double2 *>(spec_yz);
+    A.tw = reinterpret_cast<const double2 *>(ctx->d_twiddle);
+    A.dims = ctx->g.dims;
+    A.nc = ctx->g.nc;
+    A.n_mid = n_mid;
+    A.mid0 = mid0;
+    A.x_stride = (long long)n_mid * A.nc;
+    A.nrbins = nrbins;
+    A.iw1d = ctx->d_iw1d;
+    A.thresh = ctx->d_thresh;
+    A.half_bpu = nrbins > 1 ? (float)(0.5 * (nrbins - 1) / log(sqrt(3.0) * A.dims / 2.0)) : 0.f;
+    A.sums = sums_dev;
+    const size_t smem = fftx_smem_bytes(A.dims, nrbins);
+    auto tiles = [&](int C) {
+        A.groups = (A.nc + C - 1) / C;
+        A.n_tiles = (long long)n_mid * A.groups;
+    };
+    switch (A.dims) {
+    case 256: tiles(Plan<4, 8, 8>::C); return launch_fftx<Plan<4, 8, 8>>(ctx, A, smem);
+    case 512: tiles(Plan<8, 8, 8>::C); return launch_fftx<Plan<8, 8, 8>>(ctx, A, smem);
+    case 1024: tiles(Plan<16, 8, 8>::C); return launch_fftx<Plan<16, 8, 8>>(ctx, A, smem);
+    case 2048: tiles(Plan<16, 16, 8>::C); return launch_fftx<Plan<16, 16, 8>>(ctx, A, smem);
+    }
+    return 1;
+}
+
+}  // namespace genpk

@@ -109,6 +109,16 @@ class CudaStages:
                                     self._sums.data_ptr())
         return self._sums
 
+    def fused_xpass(self, nrbins: int) -> bool:
+        return self.ctx.fused_xpass_supported(nrbins)
+
+    def fftx_power_partial(self, spec_yz: torch.Tensor, nrbins: int) -> torch.Tensor:
+        """x transform + binning of the transposed (y,z)-transformed block in one kernel."""
+        if self._sums is None or self._sums.numel() != 3 * nrbins:
+            self._sums = torch.empty(3 * nrbins, dtype=torch.float64, device=self.device)
+        self.ctx.slab_fftx_power_partial(spec_yz.data_ptr(), nrbins, self._sums.data_ptr())
+        return self._sums
+
     def check(self):
         self.ctx.synchronize()
 
@@ -199,23 +209,33 @@ class SlabPipeline:
         rpos, rmass = self.exchange_particles(spos, smass, counts)
         self.stages.deposit(rpos, rmass, cmass, boxsize, which)
 
-    def spectrum(self, which=0):
+    def spectrum(self, which=0, x_pass=True):
         self.exchange_ghost(which)
         self.stages.fft_yz(which)
         spec = self.transpose(which)
-        self.stages.fft_x(spec)
+        if x_pass:
+            self.stages.fft_x(spec)
         return spec
 
-    def power(self, spec_a, spec_b, nrbins, total_mass, total_mass2):
-        sums = self.stages.power_partial(spec_a, spec_b, nrbins)
+    def _reduce_finalize(self, sums, nrbins, total_mass, total_mass2):
         if self.P > 1:
             dist.all_reduce(sums, group=self.group)
         host = sums.cpu().numpy()
         return api.power_finalize(host, nrbins, total_mass, total_mass2)
 
+    def power(self, spec_a, spec_b, nrbins, total_mass, total_mass2):
+        sums = self.stages.power_partial(spec_a, spec_b, nrbins)
+        return self._reduce_finalize(sums, nrbins, total_mass, total_mass2)
+
     def pk(self, pos, mass=None, cmass=1.0, boxsize=1.0, total_mass=1.0, nrbins=None, routed=False):
         """The per-type step of gen-pk.cpp:208-234 on this rank's particle shard."""
         nrbins = self.dims if nrbins is None else nrbins
         self.deposit(pos, mass, cmass, boxsize, 0, True, routed)
+        fused = getattr(self.stages, "fused_xpass", None)
+        if fused is not None and fused(nrbins):
+            # the x transform and the binning of the transposed block share one kernel
+            spec = self.spectrum(0, x_pass=False)
+            sums = self.stages.fftx_power_partial(spec, nrbins)
+            return self._reduce_finalize(sums, nrbins, total_mass, total_mass)
         spec = self.spectrum(0)
         return self.power(spec, None, nrbins, total_mass, total_mass)

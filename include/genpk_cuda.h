@@ -64,6 +64,9 @@ extern "C" {
                                           on the GPU once per (dims, nrbins) and cached in the context;
                                           the per-spectrum pass accumulates P alone (default)          */
 #define GENPK_POWER_FUSED        1     /* P, sum|k| and counts in one pass every call                  */
+/* ---- fused x pass (genpk_fft_power, genpk_slab_fftx_power_partial) ------------------ */
+#define GENPK_OPT_FUSED_XPASS    8     /* 1 (default): last FFT pass and binning in one kernel when the
+                                          grid side allows; 0: always cuFFT's x pass + the binning pass */
 
 typedef struct genpk_ctx genpk_ctx;
 
@@ -134,6 +137,18 @@ int genpk_power(genpk_ctx *ctx, int a, int b, int nrbins, double *power, int *co
  * GPU: the two-snapshot cross spectrum of gen-pk.cpp:295-297).  spec_b_dev NULL = auto. */
 int genpk_power_dev(genpk_ctx *ctx, const void *spec_a_dev, const void *spec_b_dev, int nrbins,
                     double *power, int *count, double *keffs, double total_mass, double total_mass2);
+
+/* fftw_execute() + powerspectrum() of gen-pk.cpp:233-234 as one call on grid `which` (auto
+ * spectrum).  For grid sides 256/512/1024/2048 the batched 2-D (y,z) cuFFT transform is
+ * followed by ONE kernel that does the x transform and the binning, so the x-transformed
+ * spectrum is never written to memory: afterwards the grid holds the (y,z)-transformed
+ * planes, not the 3-D spectrum (call genpk_fft + genpk_power when the spectrum itself is
+ * wanted).  Other grid sides run genpk_fft + genpk_power.  Same results as those two calls
+ * up to the summation order inside a bin. */
+int genpk_fft_power(genpk_ctx *ctx, int which, int nrbins, double *power, int *count, double *keffs,
+                    double total_mass, double total_mass2);
+/* 1 when genpk_fft_power / genpk_slab_fftx_power_partial take the fused path for this context. */
+int genpk_fused_xpass_supported(const genpk_ctx *ctx, int nrbins);
 
 /* Whole per-type step of gen-pk.cpp:208-234 in one call on host particle
  * arrays: zero, deposit, FFT, binning, results on the host. */
@@ -234,6 +249,11 @@ size_t genpk_slab_spectrum_bytes(const genpk_ctx *ctx);
  * below 2^53).  spec_a/spec_b are [dims][ny_local][dims/2+1] device arrays. */
 int genpk_slab_power_partial(genpk_ctx *ctx, const void *spec_a_dev, const void *spec_b_dev, int nrbins,
                              double *sums_dev);
+
+/* genpk_slab_fft_x + genpk_slab_power_partial in one kernel (auto spectrum): spec_yz_dev is
+ * the received [dims][ny_local][dims/2+1] array BEFORE the x transform and is left
+ * untouched.  Fails (nonzero) when genpk_fused_xpass_supported() is 0. */
+int genpk_slab_fftx_power_partial(genpk_ctx *ctx, const void *spec_yz_dev, int nrbins, double *sums_dev);
 
 /* Normalisation of powerspectrum.c:102-108 applied to reduced raw sums (host). */
 int genpk_power_finalize(const double *sums_host, int nrbins, double total_mass, double total_mass2,

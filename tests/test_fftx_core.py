@@ -1,0 +1,89 @@
+"""CPU check of the fused x-pass (genpk_b200/csrc/fftx_core.cuh): the kernel's own phase
+functions -- index maps, twiddles, butterflies, exchange swizzles, +-kx folding and the bin
+walk -- compiled for the host (tests/fftx_emu.cpp) and run thread by thread, against
+numpy.fft and a direct restatement of powerspectrum.c:56-99 on the tile."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from genpk_b200 import api
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    out = tmp_path_factory.mktemp("fftx") / "libfftx_emu.so"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", str(out),
+                    os.path.join(HERE, "fftx_emu.cpp")], check=True)
+    lib = ctypes.CDLL(str(out))
+    lib.fftx_emu_columns.restype = ctypes.c_int
+    lib.fftx_emu_tile.restype = ctypes.c_int
+    return lib
+
+
+def _tables(n, nrbins):
+    thresh = api.bin_thresholds(n, nrbins).astype(np.uint32)
+    k = np.arange(n // 2 + 1, dtype=np.float64)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        iw = np.where(k > 0, np.pi * k / (n * np.sin(np.pi * k / np.float32(n))), 1.0)
+    return thresh, iw.astype(np.float32)
+
+
+def _direct_bins(spec, n, kj, kz0, nc, thresh, iw, nrbins):
+    """powerspectrum.c:56-99 on the tile's columns."""
+    p = np.zeros(nrbins)
+    ncols = spec.shape[1]
+    idx = np.arange(n)
+    kx = np.where(idx <= n // 2, idx, idx - n)
+    for c in range(ncols):
+        kz = kz0 + c
+        if kz >= nc:
+            continue
+        mult = 1 if kz in (0, n // 2) else 2
+        k2 = kx.astype(np.int64) ** 2 + kj * kj + kz * kz
+        w = (iw[np.abs(kx)] * iw[abs(kj)]) * iw[kz]                 # float32 products, fieldize.cpp:129-132
+        w = w.astype(np.float64) ** 4
+        mod2 = spec[:, c].real ** 2 + spec[:, c].imag ** 2
+        ok = k2 > 0
+        b = np.searchsorted(thresh, k2[ok], side="right") - 1
+        np.add.at(p, b, mult * mod2[ok] * w[ok])
+    return p
+
+
+@pytest.mark.parametrize("n", [256, 512, 1024, 2048])
+@pytest.mark.parametrize("kj,kz0", [(0, 0), (-3, 8), (5, None)])
+def test_tile_fft_and_bins(emu, n, kj, kz0):
+    ncols = emu.fftx_emu_columns(n)
+    assert ncols * n == 8192
+    nc = n // 2 + 1
+    if kz0 is None:                                              # the last column group: only the Nyquist column is valid
+        kz0 = (nc // ncols) * ncols
+    rng = np.random.default_rng(n + 7 * kj + kz0)
+    tile = rng.standard_normal((n, ncols)) + 1j * rng.standard_normal((n, ncols))
+    tile *= np.exp(rng.uniform(-6, 6, (n, 1)))                   # a wide dynamic range
+    tw = np.exp(-2j * np.pi * np.arange(n) / n)
+    nrbins = n
+    thresh, iw = _tables(n, nrbins)
+    half_bpu = np.float32(0.5 * (nrbins - 1) / np.log(np.sqrt(3.0) * n / 2.0))
+    spec = np.zeros((n, ncols), dtype=np.complex128)
+    mod2 = np.zeros((n, ncols))
+    sp = np.zeros(nrbins)
+    tin = np.ascontiguousarray(tile)
+    twc = np.ascontiguousarray(tw)
+    rc = emu.fftx_emu_tile(ctypes.c_int(n), tin.ctypes.data_as(ctypes.c_void_p), twc.ctypes.data_as(ctypes.c_void_p),
+                           spec.ctypes.data_as(ctypes.c_void_p), mod2.ctypes.data_as(ctypes.c_void_p),
+                           ctypes.c_int(kj), ctypes.c_int(kz0), ctypes.c_int(nc),
+                           iw.ctypes.data_as(ctypes.c_void_p), thresh.ctypes.data_as(ctypes.c_void_p),
+                           ctypes.c_int(nrbins), ctypes.c_float(half_bpu), sp.ctypes.data_as(ctypes.c_void_p))
+    assert rc == 0
+    ref = np.fft.fft(tile, axis=0)
+    scale = np.abs(ref).max()
+    assert np.abs(spec - ref).max() <= 1e-13 * scale
+    want = _direct_bins(ref, n, kj, kz0, nc, thresh, iw, nrbins)
+    nz = want > 0
+    assert np.array_equal(sp > 0, nz)
+    assert np.allclose(sp[nz], want[nz], rtol=1e-11, atol=0)

@@ -181,3 +181,26 @@ def test_march_in_slab_contexts(port, P):
     finally:
         for s in st:
             s.close()
+
+
+@pytest.mark.parametrize("n_side,dims", [(210, 210), (256, 256)])
+def test_host_chunks_of_a_lattice_bit_exact(n_side, dims):
+    """genpk_deposit on HOST particles uploads 2^23-particle chunks and plans the deposit once,
+    on the first chunk; with a lattice the later chunks are cut on lattice-plane boundaries
+    (210^2 does not divide 2^23).  Fixed-point sums must equal the one-launch device deposit."""
+    box = 640.0
+    dpos, pos = synth(api.SYNTH_CLUSTERED, n_side, dims, box)
+    n = n_side ** 3
+    assert n > (1 << 23)
+    with gp.Context(dims, flags=api.FLAG_FIXED_POINT) as ctx:
+        ctx.grid_zero()
+        ctx.deposit_dev(dpos.data_ptr(), n, 0, 1.0, box)
+        want = ctx.grid_download_fixed()
+        ctx.grid_zero()
+        ctx.deposit(pos, None, 1.0, box)                 # numpy array = host buffer
+        got = ctx.grid_download_fixed()
+        ctx.synchronize()
+        o = ctx.last_order()
+    assert o["lattice"] == 1 and o["n0"] == n_side, o
+    assert np.array_equal(got, want)
+    assert int(want.sum()) == n << 40
