@@ -97,16 +97,19 @@ template <> struct Dft<1> {
     static FX_HD void run(cd *) {}
 };
 
-constexpr int TILE_MODES = 8192;      // modes per tile: 128 KB of complex doubles
 constexpr int EPT = 16;               // elements per thread
-constexpr int CTA_THREADS = TILE_MODES / EPT;
 
-template <int R1_, int R2_, int R3_> struct Plan {
+// TILE: modes per tile (16 B each).  4096 -> 256 threads and ~110 KB of shared memory per
+// CTA, two CTAs per SM whose barriers and exchanges interleave; 8192 -> one CTA of 512.
+template <int R1_, int R2_, int R3_, int TILE_> struct Plan {
     static constexpr int R1 = R1_, R2 = R2_, R3 = R3_;
     static constexpr int N = R1 * R2 * R3;
     static constexpr int M1 = R2 * R3;
+    static constexpr int TILE = TILE_;
+    static constexpr int THREADS = TILE / EPT;
     static constexpr int T = N / EPT;             // threads per column
-    static constexpr int C = TILE_MODES / N;      // columns per tile
+    static constexpr int C = TILE / N;            // columns per tile
+    static_assert(C >= 4, "a tile row is at least 64 contiguous bytes");
     static constexpr int LOG_R1 = R1 == 16 ? 4 : (R1 == 8 ? 3 : (R1 == 4 ? 2 : 1));
     static_assert(EPT % R1 == 0 && EPT % R2 == 0 && EPT % R3 == 0, "a thread owns whole butterflies");
     static_assert(R2 >= 4 && R3 >= 4, "the exchange swizzle uses two bits");

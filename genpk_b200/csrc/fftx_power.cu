@@ -2,12 +2,13 @@
 // |delta_k|^2 binning of powerspectrum() (powerspectrum.c:35-110) in ONE kernel.
 //
 // Input: the spectrum after the batched 2-D (y,z) transform, [x][n_mid][nc] complex
-// doubles.  A tile is the N x-values of C adjacent kz columns of one ky row (N*C = 8192
-// modes = 128 KB).  One persistent CTA of 512 threads per SM:
+// doubles.  A tile is the N x-values of C adjacent kz columns of one ky row: N*C = 4096
+// modes = 64 KB (8192 at N = 2048).  Persistent CTAs of 256 threads, two per SM, so that one
+// CTA's barriers and exchanges overlap the other's arithmetic (registers allow no more):
 //
-//   cp.async   next tile  -> shared memory (128 KB, natural [x][c] layout)   } overlapped with
+//   cp.async   next tile  -> shared memory (64 KB, natural [x][c] layout)    } overlapped with
 //   registers  <- this tile; three register passes of the length-N FFT       } the passes below
-//   two exchanges between the passes through a 64 KB shared buffer (real and imaginary
+//   two exchanges between the passes through a 32 KB shared buffer (real and imaginary
 //     halves one after the other; layouts chosen so that both sides are conflict free)
 //   |X|^2 -> the same buffer in kx order; bin walk along |kx| with the +-kx modes folded
 //     (same run/threshold scheme as bin_power_kernel) into the CTA's histogram
@@ -49,9 +50,9 @@ __device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 template <class PL>
-__global__ void __launch_bounds__(CTA_THREADS, 1) fftx_power_kernel(const __grid_constant__ FftxArgs A)
+__global__ void __launch_bounds__(PL::THREADS, PL::TILE == 4096 ? 2 : 1) fftx_power_kernel(const __grid_constant__ FftxArgs A)
 {
-    constexpr int N = PL::N, C = PL::C;
+    constexpr int N = PL::N, C = PL::C, TILE_MODES = PL::TILE, CTA_THREADS = PL::THREADS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2 *const stage = reinterpret_cast<double2 *>(smem_raw);                       // [N][C], next tile
     double *const E = reinterpret_cast<double *>(smem_raw + (size_t)TILE_MODES * 16);   // [N][C] exchange / |X|^2
@@ -148,10 +149,19 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) fftx_power_kernel(const __grid
             atomicAdd(&A.sums[i], sP[i]);
 }
 
-size_t fftx_smem_bytes(int dims, int nrbins)
+// 4096-mode tiles (two CTAs per SM) where a tile row stays >= 64 B; fused_xpass == 2 asks for
+// the 8192-mode tile at 1024 (one CTA of 512 threads per SM; kept for A/B measurements)
+static int fftx_tile_modes(const genpk_ctx *ctx)
 {
-    return (size_t)TILE_MODES * 16 + (size_t)TILE_MODES * 8 + (size_t)nrbins * 8 + (size_t)(nrbins + 1) * 4 +
-           (size_t)(dims / 2 + 1) * 4 + 16;
+    const int dims = ctx->g.dims;
+    return (dims == 2048 || (dims == 1024 && ctx->fused_xpass == 2)) ? 8192 : 4096;
+}
+
+size_t fftx_smem_bytes(const genpk_ctx *ctx, int nrbins)
+{
+    const int dims = ctx->g.dims;
+    const size_t tile = (size_t)fftx_tile_modes(ctx);
+    return tile * 16 + tile * 8 + (size_t)nrbins * 8 + (size_t)(nrbins + 1) * 4 + (size_t)(dims / 2 + 1) * 4 + 16;
 }
 
 bool fftx_supported(const genpk_ctx *ctx, int nrbins)
@@ -161,7 +171,7 @@ bool fftx_supported(const genpk_ctx *ctx, int nrbins)
         return false;
     if (d != 256 && d != 512 && d != 1024 && d != 2048)
         return false;
-    return nrbins >= 1 && fftx_smem_bytes(d, nrbins) <= (size_t)ctx->smem_optin;
+    return nrbins >= 1 && fftx_smem_bytes(ctx, nrbins) <= (size_t)ctx->smem_optin;
 }
 
 static int ensure_twiddles(genpk_ctx *ctx)
@@ -196,10 +206,16 @@ template <class PL> static int launch_fftx(genpk_ctx *ctx, const FftxArgs &A, si
 {
     auto kern = fftx_power_kernel<PL>;
     GENPK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    long long ctas = ctx->sm_count;
+    int per_sm = 0;
+    GENPK_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PL::THREADS, smem));
+    if (per_sm < 1) {
+        set_error("fused x pass: %zu bytes of shared memory do not fit", smem);
+        return 1;
+    }
+    long long ctas = (long long)ctx->sm_count * per_sm;          // persistent: every CTA resident
     if (ctas > A.n_tiles) ctas = A.n_tiles;
     if (ctas < 1) ctas = 1;
-    kern<<<(int)ctas, CTA_THREADS, smem, ctx->stream>>>(A);
+    kern<<<(int)ctas, PL::THREADS, smem, ctx->stream>>>(A);
     ctx->launches++;
     GENPK_CUDA_OK(cudaGetLastError());
     return 0;
@@ -230,16 +246,26 @@ int fftx_power_raw(genpk_ctx *ctx, const double *spec_yz, int n_mid, int mid0, i
     A.thresh = ctx->d_thresh;
     A.half_bpu = nrbins > 1 ? (float)(0.5 * (nrbins - 1) / log(sqrt(3.0) * A.dims / 2.0)) : 0.f;
     A.sums = sums_dev;
-    const size_t smem = fftx_smem_bytes(A.dims, nrbins);
+    const size_t smem = fftx_smem_bytes(ctx, nrbins);
     auto tiles = [&](int C) {
         A.groups = (A.nc + C - 1) / C;
         A.n_tiles = (long long)n_mid * A.groups;
     };
+    // (tests/fftx_emu.cpp instantiates the same plans on the host)
+    typedef Plan<4, 8, 8, 4096> P256;
+    typedef Plan<8, 8, 8, 4096> P512;
+    typedef Plan<16, 8, 8, 4096> P1024;
+    typedef Plan<16, 16, 8, 8192> P2048;
+    typedef Plan<16, 8, 8, 8192> P1024W;
+    if (A.dims == 1024 && fftx_tile_modes(ctx) == 8192) {
+        tiles(P1024W::C);
+        return launch_fftx<P1024W>(ctx, A, smem);
+    }
     switch (A.dims) {
-    case 256: tiles(Plan<4, 8, 8>::C); return launch_fftx<Plan<4, 8, 8>>(ctx, A, smem);
-    case 512: tiles(Plan<8, 8, 8>::C); return launch_fftx<Plan<8, 8, 8>>(ctx, A, smem);
-    case 1024: tiles(Plan<16, 8, 8>::C); return launch_fftx<Plan<16, 8, 8>>(ctx, A, smem);
-    case 2048: tiles(Plan<16, 16, 8>::C); return launch_fftx<Plan<16, 16, 8>>(ctx, A, smem);
+    case 256: tiles(P256::C); return launch_fftx<P256>(ctx, A, smem);
+    case 512: tiles(P512::C); return launch_fftx<P512>(ctx, A, smem);
+    case 1024: tiles(P1024::C); return launch_fftx<P1024>(ctx, A, smem);
+    case 2048: tiles(P2048::C); return launch_fftx<P2048>(ctx, A, smem);
     }
     return 1;
 }

@@ -66,7 +66,8 @@ extern "C" {
 #define GENPK_POWER_FUSED        1     /* P, sum|k| and counts in one pass every call                  */
 /* ---- fused x pass (genpk_fft_power, genpk_slab_fftx_power_partial) ------------------ */
 #define GENPK_OPT_FUSED_XPASS    8     /* 1 (default): last FFT pass and binning in one kernel when the
-                                          grid side allows; 0: always cuFFT's x pass + the binning pass */
+                                          grid side allows; 0: always cuFFT's x pass + the binning pass;
+                                          2: as 1 with the one-CTA-per-SM tile shape (measurements) */
 
 typedef struct genpk_ctx genpk_ctx;
 

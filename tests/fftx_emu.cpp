@@ -15,12 +15,12 @@ static int emu_tile(const double *tile_in, const double *twiddle, double *spec_o
     constexpr int N = PL::N, C = PL::C, T = PL::T;
     const cd *in = reinterpret_cast<const cd *>(tile_in);        // [N][C]
     const cd *tw = reinterpret_cast<const cd *>(twiddle);        // [N]
-    std::vector<cd> regs((size_t)CTA_THREADS * EPT), regs2((size_t)CTA_THREADS * EPT);
+    std::vector<cd> regs((size_t)PL::THREADS * EPT), regs2((size_t)PL::THREADS * EPT);
     std::vector<double> Ere((size_t)N * C), Eim((size_t)N * C), P((size_t)N * C);
     auto col = [](int tid) { return tid % C; };
     auto thr = [](int tid) { return tid / C; };
     // fill + pass 1 + exchange-1 write
-    for (int tid = 0; tid < CTA_THREADS; tid++) {
+    for (int tid = 0; tid < PL::THREADS; tid++) {
         const int c = col(tid), t = thr(tid);
         cd *v = &regs[(size_t)tid * EPT];
         for (int i = 0; i < EPT; i++)
@@ -32,7 +32,7 @@ static int emu_tile(const double *tile_in, const double *twiddle, double *spec_o
         }
     }
     // exchange-1 read + pass 2
-    for (int tid = 0; tid < CTA_THREADS; tid++) {
+    for (int tid = 0; tid < PL::THREADS; tid++) {
         const int c = col(tid), t = thr(tid);
         cd *w = &regs2[(size_t)tid * EPT];
         for (int i = 0; i < EPT; i++) {
@@ -42,7 +42,7 @@ static int emu_tile(const double *tile_in, const double *twiddle, double *spec_o
         PL::pass2(w, t, tw);
     }
     // exchange-2 write (after every thread has read exchange 1)
-    for (int tid = 0; tid < CTA_THREADS; tid++) {
+    for (int tid = 0; tid < PL::THREADS; tid++) {
         const int c = col(tid), t = thr(tid);
         const cd *w = &regs2[(size_t)tid * EPT];
         for (int i = 0; i < EPT; i++) {
@@ -52,7 +52,7 @@ static int emu_tile(const double *tile_in, const double *twiddle, double *spec_o
     }
     // exchange-2 read + pass 3 + |X|^2
     std::vector<char> hit((size_t)N * C, 0);
-    for (int tid = 0; tid < CTA_THREADS; tid++) {
+    for (int tid = 0; tid < PL::THREADS; tid++) {
         const int c = col(tid), t = thr(tid);
         cd *v = &regs[(size_t)tid * EPT];
         for (int i = 0; i < EPT; i++) {
@@ -75,7 +75,7 @@ static int emu_tile(const double *tile_in, const double *twiddle, double *spec_o
         }
     }
     // bin walk
-    for (int tid = 0; tid < CTA_THREADS; tid++) {
+    for (int tid = 0; tid < PL::THREADS; tid++) {
         const int c = col(tid), t = thr(tid);
         if (kz0 + c < nc)
             bin_walk<PL>(P.data(), t, c, kj, kz0 + c, N / 2, sW, sT, nrbins, half_bpu, sP);
@@ -84,13 +84,21 @@ static int emu_tile(const double *tile_in, const double *twiddle, double *spec_o
     return 0;
 }
 
+// the plans fftx_power.cu launches (keep in step with fftx_power_raw)
+typedef Plan<4, 8, 8, 4096> P256;
+typedef Plan<8, 8, 8, 4096> P512;
+typedef Plan<16, 8, 8, 4096> P1024;
+typedef Plan<16, 16, 8, 8192> P2048;
+typedef Plan<16, 8, 8, 8192> P1024W;      // n = -1024: the one-CTA-per-SM tile
+
 extern "C" int fftx_emu_columns(int n)
 {
     switch (n) {
-    case 256: return Plan<4, 8, 8>::C;
-    case 512: return Plan<8, 8, 8>::C;
-    case 1024: return Plan<16, 8, 8>::C;
-    case 2048: return Plan<16, 16, 8>::C;
+    case 256: return P256::C;
+    case 512: return P512::C;
+    case 1024: return P1024::C;
+    case 2048: return P2048::C;
+    case -1024: return P1024W::C;
     }
     return 0;
 }
@@ -102,10 +110,11 @@ extern "C" int fftx_emu_tile(int n, const double *tile_in, const double *twiddle
                              double *sP)
 {
     switch (n) {
-    case 256: return emu_tile<Plan<4, 8, 8>>(tile_in, twiddle, spec_out, mod2_out, kj, kz0, nc, sW, sT, nrbins, half_bpu, sP);
-    case 512: return emu_tile<Plan<8, 8, 8>>(tile_in, twiddle, spec_out, mod2_out, kj, kz0, nc, sW, sT, nrbins, half_bpu, sP);
-    case 1024: return emu_tile<Plan<16, 8, 8>>(tile_in, twiddle, spec_out, mod2_out, kj, kz0, nc, sW, sT, nrbins, half_bpu, sP);
-    case 2048: return emu_tile<Plan<16, 16, 8>>(tile_in, twiddle, spec_out, mod2_out, kj, kz0, nc, sW, sT, nrbins, half_bpu, sP);
+    case 256: return emu_tile<P256>(tile_in, twiddle, spec_out, mod2_out, kj, kz0, nc, sW, sT, nrbins, half_bpu, sP);
+    case 512: return emu_tile<P512>(tile_in, twiddle, spec_out, mod2_out, kj, kz0, nc, sW, sT, nrbins, half_bpu, sP);
+    case 1024: return emu_tile<P1024>(tile_in, twiddle, spec_out, mod2_out, kj, kz0, nc, sW, sT, nrbins, half_bpu, sP);
+    case 2048: return emu_tile<P2048>(tile_in, twiddle, spec_out, mod2_out, kj, kz0, nc, sW, sT, nrbins, half_bpu, sP);
+    case -1024: return emu_tile<P1024W>(tile_in, twiddle, spec_out, mod2_out, kj, kz0, nc, sW, sT, nrbins, half_bpu, sP);
     }
     return -1;
 }

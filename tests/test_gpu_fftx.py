@@ -36,11 +36,12 @@ def test_fused_vs_oracle_256(port):
     np.testing.assert_allclose(k[nz], kr[nz], rtol=1e-5, atol=0)
 
 
-@pytest.mark.parametrize("dims,nrbins", [(256, 256), (256, 37), (512, 512), (1024, 1024)])
-def test_fused_vs_unfused(dims, nrbins):
+@pytest.mark.parametrize("dims,nrbins,tile", [(256, 256, 1), (256, 37, 1), (512, 512, 1), (1024, 1024, 1), (1024, 1024, 2)])
+def test_fused_vs_unfused(dims, nrbins, tile):
     box, n = 1000.0, 400000
     pos, _ = _particles(n, box, dims)
     with gp.Context(dims) as ctx:
+        ctx.set_option(api.OPT_FUSED_XPASS, tile)                    # 2: the one-CTA-per-SM tile shape
         ctx.grid_zero()
         ctx.deposit(pos, None, 1.0, box)
         ctx.fft()
@@ -60,13 +61,13 @@ def test_fused_vs_unfused(dims, nrbins):
     nz = c0 > 0
     np.testing.assert_allclose(p1[nz], p0[nz], rtol=1e-9, atol=0)
     np.testing.assert_array_equal(k1, k0)
-    np.testing.assert_allclose(p2[nz], p0[nz], rtol=1e-12, atol=0)
+    np.testing.assert_allclose(p2[nz], p0[nz], rtol=1e-10, atol=0)       # fp64 red.add order differs between deposits
 
 
 def test_unsupported_sizes_fall_back():
     dims, box, n = 96, 100.0, 20000
     pos, _ = _particles(n, box, 3)
-    with gp.Context(dims) as ctx:
+    with gp.Context(dims, flags=api.FLAG_FIXED_POINT) as ctx:         # fixed point: the two deposits are bit-identical
         assert not ctx.fused_xpass_supported(dims)
         ctx.grid_zero()
         ctx.deposit(pos, None, 1.0, box)
