@@ -64,6 +64,7 @@ def parse_args():
     ap.add_argument("--no-fused-xpass", action="store_true",
                     help="cuFFT x pass + bin_power_kernel instead of the fused x-pass/binning kernel")
     ap.add_argument("--xpass-wide-tile", action="store_true", help="fused x pass with 8192-mode tiles, one CTA per SM")
+    ap.add_argument("--fft-yz-batch", type=int, default=-1, help="x planes per 2-D cuFFT call (0 = all, -1 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
@@ -323,6 +324,8 @@ def run_ours(args):
         ctx.set_option(api.OPT_FUSED_XPASS, 0)
     elif args.xpass_wide_tile:
         ctx.set_option(api.OPT_FUSED_XPASS, 2)
+    if args.fft_yz_batch >= 0:
+        ctx.set_option(api.OPT_FFT_YZ_BATCH, args.fft_yz_batch)
     fused = ctx.fused_xpass_supported(nrbins)
     if args.lattice_hint and wl["kind"] != "uniform":
         ctx.set_lattice_hint(n_side, n_side)

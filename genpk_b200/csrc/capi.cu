@@ -199,6 +199,10 @@ int genpk_set_option(genpk_ctx *ctx, int option, int64_t value)
         if (value != GENPK_POWER_CACHED && value != GENPK_POWER_FUSED) break;
         ctx->power_mode = (int)value;
         return 0;
+    case GENPK_OPT_FFT_YZ_BATCH:
+        if (value < 0 || value > (1 << 20)) break;
+        ctx->fft_yz_batch = (int)value;
+        return 0;
     case GENPK_OPT_FUSED_XPASS:
         if (value < 0 || value > 2) break;
         ctx->fused_xpass = (int)value;

@@ -82,6 +82,8 @@ struct genpk_ctx {
     // cuFFT
     cufftHandle plan3d = 0, plan_yz = 0, plan_x = 0;
     bool have_plan3d = false, have_plan_yz = false, have_plan_x = false;
+    int fft_yz_batch = 0;             // planes per 2-D cuFFT call (0: the whole slab in one call)
+    int plan_yz_batch = 0;
     void *fft_work = nullptr;
     size_t fft_work_bytes = 0;
 

@@ -50,6 +50,16 @@ int fft_3d(genpk_ctx *ctx, int which)
 int fft_yz(genpk_ctx *ctx, int which)
 {
     const SlabGeom &g = ctx->g;
+    // Planes per cuFFT call.  One call over the whole slab runs the z pass over every plane
+    // and then the y pass over every plane: 4 trips through HBM.  Groups of a few planes
+    // (tens of MB) keep the z pass's output in L2 for the y pass: 2 trips.
+    int batch = g.nx;
+    if (ctx->fft_yz_batch > 0 && ctx->fft_yz_batch < g.nx && g.nx % ctx->fft_yz_batch == 0)
+        batch = ctx->fft_yz_batch;
+    if (ctx->have_plan_yz && ctx->plan_yz_batch != batch) {
+        cufftDestroy(ctx->plan_yz);
+        ctx->have_plan_yz = false;
+    }
     if (!ctx->have_plan_yz) {
         size_t ws = 0;
         long long n[2] = {g.dims, g.dims};
@@ -58,15 +68,19 @@ int fft_yz(genpk_ctx *ctx, int which)
         GENPK_CUFFT_OK(cufftCreate(&ctx->plan_yz));
         GENPK_CUFFT_OK(cufftSetAutoAllocation(ctx->plan_yz, 0));
         GENPK_CUFFT_OK(cufftMakePlanMany64(ctx->plan_yz, 2, n, inembed, 1, (long long)g.dims * g.fd, onembed, 1,
-                                           (long long)g.dims * g.nc, CUFFT_D2Z, g.nx, &ws));
+                                           (long long)g.dims * g.nc, CUFFT_D2Z, batch, &ws));
         ctx->have_plan_yz = true;
+        ctx->plan_yz_batch = batch;
         if (int rc = grow_work(ctx, ws)) return rc;
         if (int rc = attach_work(ctx)) return rc;
     }
     GENPK_CUFFT_OK(cufftSetStream(ctx->plan_yz, ctx->stream));
     double *owned = ctx->grid[which] + g.owned_offset();
-    GENPK_CUFFT_OK(cufftExecD2Z(ctx->plan_yz, owned, reinterpret_cast<cufftDoubleComplex *>(owned)));
-    ctx->lib_calls++;
+    for (int x = 0; x < g.nx; x += batch) {
+        double *p = owned + (size_t)x * g.plane();
+        GENPK_CUFFT_OK(cufftExecD2Z(ctx->plan_yz, p, reinterpret_cast<cufftDoubleComplex *>(p)));
+        ctx->lib_calls++;
+    }
     return 0;
 }
 

@@ -171,6 +171,19 @@ template <int R1_, int R2_, int R3_, int TILE_> struct Plan {
         const int v3 = t + T * (i / R3), q2 = i % R3;
         return (v3 / R2) + R1 * ((v3 % R2) + R2 * q2);
     }
+    // The same maps split into a per-thread base and a compile-time part, base(t) + part(i),
+    // which is what the kernel keeps in registers (tests/fftx_emu.cpp checks them against
+    // the definitions above for every t and i).
+    static_assert(T % R2 == 0 && T % R3 == 0, "a thread's units share m2 (pass 2) and q1 (pass 3)");
+    static FX_HD int ex1_w_part(int i) { return (i % R1) * M1 + T * (i / R1); }                       // base: t
+    static FX_HD int ex1_r_base(int t) { return (t / R3) * M1 + (t % R3); }
+    static FX_HD int ex1_r_part(int i) { return ((T * (i / R2)) / R3) * M1 + R3 * (i % R2); }
+    static FX_HD int ex2_w_base(int t, int s) { return (t / R3) * M1 + ((t % R3) ^ s); }             // s = (i % R2) & 3
+    static FX_HD int ex2_w_part(int i) { return ((T * (i / R2)) / R3) * M1 + (i % R2) * R3; }
+    static FX_HD int ex2_r_base(int t, int j) { return (t / R2) * M1 + (t % R2) * R3 + (j ^ (t & 3)); }   // j = (i % R3) & 3
+    static FX_HD int ex2_r_part(int i) { return ((T * (i / R3)) / R2) * M1 + ((i % R3) & ~3); }
+    static FX_HD int out_k_base(int t) { return t / R2 + R1 * (t % R2); }
+    static FX_HD int out_k_part(int i) { return (T / R2) * (i / R3) + R1 * R2 * (i % R3); }
     // where |X[k]|^2 waits for the bin walk (bank swizzle only; any bijection is correct)
     static FX_HD int slot(int k) { return k ^ (((k >> 3) ^ (R1 == 8 ? 0 : (k >> LOG_R1))) & 3); }
 };

@@ -2,14 +2,12 @@
 // |delta_k|^2 binning of powerspectrum() (powerspectrum.c:35-110) in ONE kernel.
 //
 // Input: the spectrum after the batched 2-D (y,z) transform, [x][n_mid][nc] complex
-// doubles.  A tile is the N x-values of C adjacent kz columns of one ky row: N*C = 4096
-// modes = 64 KB (8192 at N = 2048).  Persistent CTAs of 256 threads, two per SM, so that one
-// CTA's barriers and exchanges overlap the other's arithmetic (registers allow no more):
+// doubles.  A tile is the N x-values of C adjacent kz columns of one ky row (N*C = 4096 or
+// 8192 modes).  Persistent CTAs, 16 modes per thread, the whole tile lives in registers:
 //
-//   cp.async   next tile  -> shared memory (64 KB, natural [x][c] layout)    } overlapped with
-//   registers  <- this tile; three register passes of the length-N FFT       } the passes below
-//   two exchanges between the passes through a 32 KB shared buffer (real and imaginary
-//     halves one after the other; layouts chosen so that both sides are conflict free)
+//   ld.global.cs  next tile -> registers, issued before the bin walk of this tile
+//   three register passes of the length-N FFT with two exchanges through one shared
+//     buffer of complex doubles (layouts chosen so that both sides are conflict free)
 //   |X|^2 -> the same buffer in kx order; bin walk along |kx| with the +-kx modes folded
 //     (same run/threshold scheme as bin_power_kernel) into the CTA's histogram
 //
@@ -41,22 +39,23 @@ struct FftxArgs {
     double *sums;             // nrbins P sums, accumulated into
 };
 
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
+// 16-byte streaming load (the spectrum is read exactly once)
+__device__ __forceinline__ double2 ld_stream(const double2 *p)
 {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+    double2 r;
+    asm volatile("ld.global.cs.v2.f64 {%0, %1}, [%2];\n" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
 }
-__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 template <class PL>
 __global__ void __launch_bounds__(PL::THREADS, PL::TILE == 4096 ? 2 : 1) fftx_power_kernel(const __grid_constant__ FftxArgs A)
 {
     constexpr int N = PL::N, C = PL::C, TILE_MODES = PL::TILE, CTA_THREADS = PL::THREADS;
+    constexpr int R2 = PL::R2, R3 = PL::R3;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double2 *const stage = reinterpret_cast<double2 *>(smem_raw);                       // [N][C], next tile
-    double *const E = reinterpret_cast<double *>(smem_raw + (size_t)TILE_MODES * 16);   // [N][C] exchange / |X|^2
-    double *const sP = E + TILE_MODES;
+    cd *const E = reinterpret_cast<cd *>(smem_raw);                                     // [N][C] complex exchange
+    double *const P = reinterpret_cast<double *>(smem_raw);                             // [N][C] |X|^2, same bytes
+    double *const sP = reinterpret_cast<double *>(smem_raw + (size_t)TILE_MODES * 16);
     unsigned *const sT = reinterpret_cast<unsigned *>(sP + A.nrbins);                   // nrbins + 1
     float *const sW = reinterpret_cast<float *>(sT + A.nrbins + 1);                     // dims/2 + 1
 
@@ -69,26 +68,37 @@ __global__ void __launch_bounds__(PL::THREADS, PL::TILE == 4096 ? 2 : 1) fftx_po
     for (int i = tid; i <= N / 2; i += CTA_THREADS)
         sW[i] = A.iw1d[i];
 
-    // a thread copies exactly the 16 staging slots it later reads: no barrier guards the staging buffer
-    auto issue = [&](long long tile) {
-        if (tile < A.n_tiles) {
-            const int g = (int)(tile % A.groups);
-            const long long m = tile / A.groups;
-            const int kz = g * C + c;
-            if (kz < A.nc) {
-                const double2 *src = A.spec + (size_t)m * A.nc + kz;
+    // per-thread bases of the exchange maps, in elements of E (index * C + c)
+    const int b_ex1w = t * C + c;
+    const int b_ex1r = PL::ex1_r_base(t) * C + c;
+    int b_ex2w[4], b_ex2r[4];
 #pragma unroll
-                for (int i = 0; i < EPT; i++) {
-                    const int n = PL::load_n(t, i);
-                    cp_async16(stage + n * C + c, src + (size_t)n * A.x_stride);
-                }
-            }
+    for (int s = 0; s < 4; s++) {
+        b_ex2w[s] = PL::ex2_w_base(t, s) * C + c;
+        b_ex2r[s] = PL::ex2_r_base(t, s) * C + c;
+    }
+    const int kb = PL::out_k_base(t);
+
+    cd v[EPT], w[EPT];
+    // this thread's 16 elements of a tile, straight into registers
+    auto load_tile = [&](long long tile) {
+        const int g = (int)(tile % A.groups);
+        const long long m = tile / A.groups;
+        const int kz = g * C + c;
+        if (tile < A.n_tiles && kz < A.nc) {
+            const double2 *src = A.spec + (size_t)m * A.nc + kz;
+#pragma unroll
+            for (int i = 0; i < EPT; i++)
+                v[i] = ld_stream(src + (size_t)PL::load_n(t, i) * A.x_stride);
+        } else {
+#pragma unroll
+            for (int i = 0; i < EPT; i++)
+                v[i] = make_double2(0.0, 0.0);
         }
-        cp_async_commit_group();
     };
 
     long long tile = blockIdx.x;
-    issue(tile);
+    load_tile(tile);
     for (; tile < A.n_tiles; tile += gridDim.x) {
         const int g = (int)(tile % A.groups);
         const int m = (int)(tile / A.groups);
@@ -97,52 +107,30 @@ __global__ void __launch_bounds__(PL::THREADS, PL::TILE == 4096 ? 2 : 1) fftx_po
         int kj = A.mid0 + m;
         kj = kj <= A.dims / 2 ? kj : kj - A.dims;                    // KVAL, powerspectrum.c:33
 
-        cd v[EPT], w[EPT];
-        cp_async_wait_all();
-#pragma unroll
-        for (int i = 0; i < EPT; i++) {
-            v[i] = valid ? stage[PL::load_n(t, i) * C + c] : make_double2(0.0, 0.0);
-        }
         PL::pass1(v, t, A.tw);
-        issue(tile + gridDim.x);                                     // the registers above are consumed: slots are free
-
-        __syncthreads();                                             // the previous tile's bin walk has left E
+        __syncthreads();                                             // the previous tile's bin walk has left P
 #pragma unroll
-        for (int i = 0; i < EPT; i++) E[PL::ex1_w(t, i) * C + c] = v[i].x;
+        for (int i = 0; i < EPT; i++) E[b_ex1w + PL::ex1_w_part(i) * C] = v[i];
         __syncthreads();
 #pragma unroll
-        for (int i = 0; i < EPT; i++) w[i].x = E[PL::ex1_r(t, i) * C + c];
-        __syncthreads();
-#pragma unroll
-        for (int i = 0; i < EPT; i++) E[PL::ex1_w(t, i) * C + c] = v[i].y;
-        __syncthreads();
-#pragma unroll
-        for (int i = 0; i < EPT; i++) w[i].y = E[PL::ex1_r(t, i) * C + c];
+        for (int i = 0; i < EPT; i++) w[i] = E[b_ex1r + PL::ex1_r_part(i) * C];
         PL::pass2(w, t, A.tw);
-
         __syncthreads();
 #pragma unroll
-        for (int i = 0; i < EPT; i++) E[PL::ex2_w(t, i) * C + c] = w[i].x;
+        for (int i = 0; i < EPT; i++) E[b_ex2w[(i % R2) & 3] + PL::ex2_w_part(i) * C] = w[i];
         __syncthreads();
 #pragma unroll
-        for (int i = 0; i < EPT; i++) v[i].x = E[PL::ex2_r(t, i) * C + c];
-        __syncthreads();
-#pragma unroll
-        for (int i = 0; i < EPT; i++) E[PL::ex2_w(t, i) * C + c] = w[i].y;
-        __syncthreads();
-#pragma unroll
-        for (int i = 0; i < EPT; i++) v[i].y = E[PL::ex2_r(t, i) * C + c];
+        for (int i = 0; i < EPT; i++) v[i] = E[b_ex2r[(i % R3) & 3] + PL::ex2_r_part(i) * C];
         PL::pass3(v);
-
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < EPT; i++)
-            E[PL::slot(PL::out_k(t, i)) * C + c] = fma(v[i].x, v[i].x, v[i].y * v[i].y);
+            P[PL::slot(kb + PL::out_k_part(i)) * C + c] = fma(v[i].x, v[i].x, v[i].y * v[i].y);
         __syncthreads();
+        load_tile(tile + gridDim.x);                                 // in flight during the bin walk
         if (valid)
-            bin_walk<PL>(E, t, c, kj, kz, A.dims / 2, sW, sT, A.nrbins, A.half_bpu, sP);
+            bin_walk<PL>(P, t, c, kj, kz, A.dims / 2, sW, sT, A.nrbins, A.half_bpu, sP);
     }
-    cp_async_wait_all();
     __syncthreads();
     for (int i = tid; i < A.nrbins; i += CTA_THREADS)
         if (sP[i] != 0.0)
@@ -161,7 +149,7 @@ size_t fftx_smem_bytes(const genpk_ctx *ctx, int nrbins)
 {
     const int dims = ctx->g.dims;
     const size_t tile = (size_t)fftx_tile_modes(ctx);
-    return tile * 16 + tile * 8 + (size_t)nrbins * 8 + (size_t)(nrbins + 1) * 4 + (size_t)(dims / 2 + 1) * 4 + 16;
+    return tile * 16 + (size_t)nrbins * 8 + (size_t)(nrbins + 1) * 4 + (size_t)(dims / 2 + 1) * 4 + 16;
 }
 
 bool fftx_supported(const genpk_ctx *ctx, int nrbins)

@@ -64,6 +64,9 @@ extern "C" {
                                           on the GPU once per (dims, nrbins) and cached in the context;
                                           the per-spectrum pass accumulates P alone (default)          */
 #define GENPK_POWER_FUSED        1     /* P, sum|k| and counts in one pass every call                  */
+#define GENPK_OPT_FFT_YZ_BATCH   9     /* x planes per 2-D cuFFT call of the (y,z) transform; groups of a few
+                                          planes keep the z pass's output in L2 for the y pass (0 = all
+                                          planes in one call; must divide the local plane count) */
 /* ---- fused x pass (genpk_fft_power, genpk_slab_fftx_power_partial) ------------------ */
 #define GENPK_OPT_FUSED_XPASS    8     /* 1 (default): last FFT pass and binning in one kernel when the
                                           grid side allows; 0: always cuFFT's x pass + the binning pass;

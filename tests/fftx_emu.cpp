@@ -19,6 +19,15 @@ static int emu_tile(const double *tile_in, const double *twiddle, double *spec_o
     std::vector<double> Ere((size_t)N * C), Eim((size_t)N * C), P((size_t)N * C);
     auto col = [](int tid) { return tid % C; };
     auto thr = [](int tid) { return tid / C; };
+    // the base + part forms the kernel uses are the index maps
+    for (int t = 0; t < T; t++)
+        for (int i = 0; i < EPT; i++) {
+            if (PL::ex1_w(t, i) != t + PL::ex1_w_part(i)) return 10;
+            if (PL::ex1_r(t, i) != PL::ex1_r_base(t) + PL::ex1_r_part(i)) return 11;
+            if (PL::ex2_w(t, i) != PL::ex2_w_base(t, (i % PL::R2) & 3) + PL::ex2_w_part(i)) return 12;
+            if (PL::ex2_r(t, i) != PL::ex2_r_base(t, (i % PL::R3) & 3) + PL::ex2_r_part(i)) return 13;
+            if (PL::out_k(t, i) != PL::out_k_base(t) + PL::out_k_part(i)) return 14;
+        }
     // fill + pass 1 + exchange-1 write
     for (int tid = 0; tid < PL::THREADS; tid++) {
         const int c = col(tid), t = thr(tid);

@@ -77,7 +77,7 @@ def test_unsupported_sizes_fall_back():
         ctx.deposit(pos, None, 1.0, box)
         p1, c1, k1 = ctx.fft_power(dims, float(n), float(n))
     assert np.array_equal(c1, c0)
-    np.testing.assert_array_equal(p1, p0)
+    np.testing.assert_allclose(p1, p0, rtol=1e-12, atol=0)           # same kernels; the bin sums are atomics
 
 
 @pytest.mark.parametrize("dims,P,rank", [(256, 2, 1), (512, 4, 3), (1024, 8, 5), (2048, 8, 2), (2048, 8, 0)])
