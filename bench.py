@@ -63,7 +63,7 @@ def parse_args():
                     help="multi-GPU: ghost planes on each side of a slab (0 = always route particles)")
     ap.add_argument("--no-fused-xpass", action="store_true",
                     help="cuFFT x pass + bin_power_kernel instead of the fused x-pass/binning kernel")
-    ap.add_argument("--xpass-wide-tile", action="store_true", help="fused x pass with 8192-mode tiles, one CTA per SM")
+    ap.add_argument("--xpass-narrow-tile", action="store_true", help="fused x pass with 4096-mode tiles at 1024 (two CTAs per SM)")
     ap.add_argument("--fft-yz-batch", type=int, default=-1, help="x planes per 2-D cuFFT call (0 = all, -1 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -322,7 +322,7 @@ def run_ours(args):
 
     if args.no_fused_xpass:
         ctx.set_option(api.OPT_FUSED_XPASS, 0)
-    elif args.xpass_wide_tile:
+    elif args.xpass_narrow_tile:
         ctx.set_option(api.OPT_FUSED_XPASS, 2)
     if args.fft_yz_batch >= 0:
         ctx.set_option(api.OPT_FFT_YZ_BATCH, args.fft_yz_batch)

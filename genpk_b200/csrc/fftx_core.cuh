@@ -191,85 +191,62 @@ template <int R1_, int R2_, int R3_, int TILE_> struct Plan {
 // ---------------------------------------------------------------------------------
 // Bin walk (powerspectrum.c:56-99 for one (ky, kz) column of the tile): thread t owns
 // |kx| = 8t+1 .. 8t+8 (thread 0 also kx = 0); the +kx and -kx modes share bin and window,
-// so their |X|^2 are added first.  Along the walk |k| grows slowly and the thread keeps a
-// run (bin, sum) in registers, touching the CTA's histogram only when the bin changes.
+// so their |X|^2 are added first.  Along the walk |k| only grows, so the bin only moves
+// forward: the thread keeps a run (bin, sum) in registers and touches its column's
+// histogram when the bin changes.  Histograms are private to a tile column (hist[b*hstride]):
+// the lanes of a warp that walk the same |kx| range of neighbouring kz columns -- and so
+// change bins together -- never meet on an address.
 // ---------------------------------------------------------------------------------
-struct Run {
-    int bin;
-    unsigned lo, hi;      // thresh[bin], thresh[bin+1]; hi == 0: no run yet
-    double p;
-    int n;
-};
-
 #if defined(__CUDA_ARCH__)
 #define FX_HIST_ADD(ptr, val) atomicAdd((ptr), (val))
 #define FX_LOGF(x) __logf(x)
+#define FX_FMUL(a, b) __fmul_rn((a), (b))
 #else
 #define FX_HIST_ADD(ptr, val) (*(ptr) += (val))
 #define FX_LOGF(x) logf(x)
+#define FX_FMUL(a, b) ((a) * (b))
 #endif
-
-FX_HD void run_flush(const Run &r, int mult, double *sP)
-{
-    if (r.n)
-        FX_HIST_ADD(&sP[r.bin], r.p * mult);
-}
-
-FX_HD void run_seek(Run &r, unsigned k2, const unsigned *sT, int nrbins, float half_bpu)
-{
-    int b = r.bin;
-    if (r.hi == 0) {                                   // first guess only; the walk below makes it exact
-        b = (int)(half_bpu * FX_LOGF((float)k2));
-        b = b < 0 ? 0 : (b > nrbins - 1 ? nrbins - 1 : b);
-    }
-    while (k2 >= sT[b + 1]) b++;
-    while (k2 < sT[b]) b--;
-    r.bin = b;
-    r.lo = sT[b];
-    r.hi = sT[b + 1];
-    r.p = 0.0;
-    r.n = 0;
-}
-
-// one |kx| step: mod2sum = |X[kx]|^2 (+ |X[-kx]|^2), fwin = (iwx*iwy)*iwz in float (fieldize.cpp:129-132)
-FX_HD void run_add(Run &r, unsigned k2, double mod2sum, float fwin, int mult, const unsigned *sT, int nrbins,
-                   float half_bpu, double *sP)
-{
-    if (k2 == 0)
-        return;                                        // DC mode, powerspectrum.c:63
-    if (k2 < r.lo || k2 >= r.hi) {
-        run_flush(r, mult, sP);
-        run_seek(r, k2, sT, nrbins, half_bpu);
-    }
-    double w = (double)fwin;                           // float product promoted, fieldize.cpp:132
-    w = w * w;                                         // invwindow() = prod^2
-    w = w * w;                                         // pow(invwindow,2), powerspectrum.c:68
-    r.p = fma(mod2sum, w, r.p);
-    r.n = 1;
-}
 
 // P: the tile's |X|^2 in slot order, [N][C] doubles.  c: column of this thread, kz its global kz.
 template <class PL>
 FX_HD void bin_walk(const double *P, int t, int c, int kj, int kz, int dims_half, const float *sW, const unsigned *sT,
-                    int nrbins, float half_bpu, double *sP)
+                    int nrbins, float half_bpu, double *hist, int hstride)
 {
     constexpr int N = PL::N, C = PL::C;
-    const int mult = (kz == 0 || kz == dims_half) ? 1 : 2;          // powerspectrum.c:59-89
+    const double mult = (kz == 0 || kz == dims_half) ? 1.0 : 2.0;      // powerspectrum.c:59-89
     const float fj = sW[kj < 0 ? -kj : kj], fz = sW[kz];
     const unsigned base2 = (unsigned)(kj * kj) + (unsigned)(kz * kz);
-    Run r;
-    r.bin = 0; r.lo = 0; r.hi = 0; r.p = 0.0; r.n = 0;
-    if (t == 0)
-        run_add(r, base2, P[PL::slot(0) * C + c], (sW[0] * fj) * fz, mult, sT, nrbins, half_bpu, sP);
+    // first step: kx = 0 belongs to thread 0, and the DC mode is skipped (powerspectrum.c:63)
+    const int s0 = (t == 0 && base2 != 0) ? 0 : 1;
+    // bin of the first mode: a float guess made exact by walking the threshold table
+    const unsigned k2first = base2 + (unsigned)((8 * t + s0) * (8 * t + s0));
+    int b = (int)(half_bpu * FX_LOGF((float)k2first));
+    b = b < 0 ? 0 : (b > nrbins - 1 ? nrbins - 1 : b);
+    while (k2first >= sT[b + 1]) b++;
+    while (k2first < sT[b]) b--;
+    unsigned hi = sT[b + 1];
+    double p = 0.0;
 #pragma unroll
-    for (int s = 1; s <= 8; s++) {
-        const int a = 8 * t + s;                                    // |kx|
-        double m = P[PL::slot(a) * C + c];
-        if (a < N / 2)
-            m += P[PL::slot(N - a) * C + c];
-        run_add(r, base2 + (unsigned)(a * a), m, (sW[a] * fj) * fz, mult, sT, nrbins, half_bpu, sP);
+    for (int s = 0; s <= 8; s++) {
+        if (s >= s0) {
+            const int a = 8 * t + s;                                    // |kx|
+            const unsigned k2 = base2 + (unsigned)(a * a);
+            if (k2 >= hi) {
+                FX_HIST_ADD(&hist[b * hstride], p * mult);
+                do b++; while (k2 >= sT[b + 1]);
+                hi = sT[b + 1];
+                p = 0.0;
+            }
+            double m = P[PL::slot(a) * C + c];
+            if (s > 0 && a < N / 2)
+                m += P[PL::slot(N - a) * C + c];
+            double w = (double)FX_FMUL(FX_FMUL(sW[a], fj), fz);         // (iwx*iwy)*iwz in float, promoted: fieldize.cpp:129-132
+            w = w * w;                                                  // invwindow() = prod^2
+            w = w * w;                                                  // pow(invwindow,2), powerspectrum.c:68
+            p = fma(m, w, p);
+        }
     }
-    run_flush(r, mult, sP);
+    FX_HIST_ADD(&hist[b * hstride], p * mult);
 }
 
 }  // namespace fftx

@@ -56,13 +56,13 @@ __global__ void __launch_bounds__(PL::THREADS, PL::TILE == 4096 ? 2 : 1) fftx_po
     cd *const E = reinterpret_cast<cd *>(smem_raw);                                     // [N][C] complex exchange
     double *const P = reinterpret_cast<double *>(smem_raw);                             // [N][C] |X|^2, same bytes
     double *const sP = reinterpret_cast<double *>(smem_raw + (size_t)TILE_MODES * 16);
-    unsigned *const sT = reinterpret_cast<unsigned *>(sP + A.nrbins);                   // nrbins + 1
+    unsigned *const sT = reinterpret_cast<unsigned *>(sP + (size_t)A.nrbins * C);       // nrbins + 1
     float *const sW = reinterpret_cast<float *>(sT + A.nrbins + 1);                     // dims/2 + 1
 
     const int tid = threadIdx.x;
     const int c = tid % C, t = tid / C;
-    for (int i = tid; i < A.nrbins; i += CTA_THREADS)
-        sP[i] = 0.0;
+    for (int i = tid; i < A.nrbins * C; i += CTA_THREADS)
+        sP[i] = 0.0;                                                 // one histogram per tile column: sP[bin * C + c]
     for (int i = tid; i <= A.nrbins; i += CTA_THREADS)
         sT[i] = A.thresh[i];
     for (int i = tid; i <= N / 2; i += CTA_THREADS)
@@ -129,27 +129,34 @@ __global__ void __launch_bounds__(PL::THREADS, PL::TILE == 4096 ? 2 : 1) fftx_po
         __syncthreads();
         load_tile(tile + gridDim.x);                                 // in flight during the bin walk
         if (valid)
-            bin_walk<PL>(P, t, c, kj, kz, A.dims / 2, sW, sT, A.nrbins, A.half_bpu, sP);
+            bin_walk<PL>(P, t, c, kj, kz, A.dims / 2, sW, sT, A.nrbins, A.half_bpu, sP + c, C);
     }
     __syncthreads();
-    for (int i = tid; i < A.nrbins; i += CTA_THREADS)
-        if (sP[i] != 0.0)
-            atomicAdd(&A.sums[i], sP[i]);
+    for (int i = tid; i < A.nrbins; i += CTA_THREADS) {
+        double sum = 0.0;
+#pragma unroll
+        for (int j = 0; j < C; j++)
+            sum += sP[i * C + j];
+        if (sum != 0.0)
+            atomicAdd(&A.sums[i], sum);
+    }
 }
 
-// 4096-mode tiles (two CTAs per SM) where a tile row stays >= 64 B; fused_xpass == 2 asks for
-// the 8192-mode tile at 1024 (one CTA of 512 threads per SM; kept for A/B measurements)
+// 8192-mode tiles (one CTA of 512 threads per SM) keep a tile row at 128 B for 1024 and 64 B for
+// 2048; the smaller grids use 4096-mode tiles, two CTAs per SM.  fused_xpass == 2 asks for the
+// 4096-mode tile at 1024 as well (64-B rows: measured slower, kept for A/B measurements).
 static int fftx_tile_modes(const genpk_ctx *ctx)
 {
     const int dims = ctx->g.dims;
-    return (dims == 2048 || (dims == 1024 && ctx->fused_xpass == 2)) ? 8192 : 4096;
+    return (dims == 2048 || (dims == 1024 && ctx->fused_xpass != 2)) ? 8192 : 4096;
 }
 
 size_t fftx_smem_bytes(const genpk_ctx *ctx, int nrbins)
 {
     const int dims = ctx->g.dims;
     const size_t tile = (size_t)fftx_tile_modes(ctx);
-    return tile * 16 + (size_t)nrbins * 8 + (size_t)(nrbins + 1) * 4 + (size_t)(dims / 2 + 1) * 4 + 16;
+    const size_t cols = tile / (size_t)dims;                 // one histogram per tile column
+    return tile * 16 + (size_t)nrbins * 8 * cols + (size_t)(nrbins + 1) * 4 + (size_t)(dims / 2 + 1) * 4 + 16;
 }
 
 bool fftx_supported(const genpk_ctx *ctx, int nrbins)

@@ -70,7 +70,7 @@ extern "C" {
 /* ---- fused x pass (genpk_fft_power, genpk_slab_fftx_power_partial) ------------------ */
 #define GENPK_OPT_FUSED_XPASS    8     /* 1 (default): last FFT pass and binning in one kernel when the
                                           grid side allows; 0: always cuFFT's x pass + the binning pass;
-                                          2: as 1 with the one-CTA-per-SM tile shape (measurements) */
+                                          2: as 1 with 4096-mode tiles at 1024 (measurements) */
 
 typedef struct genpk_ctx genpk_ctx;
 

@@ -87,7 +87,7 @@ static int emu_tile(const double *tile_in, const double *twiddle, double *spec_o
     for (int tid = 0; tid < PL::THREADS; tid++) {
         const int c = col(tid), t = thr(tid);
         if (kz0 + c < nc)
-            bin_walk<PL>(P.data(), t, c, kj, kz0 + c, N / 2, sW, sT, nrbins, half_bpu, sP);
+            bin_walk<PL>(P.data(), t, c, kj, kz0 + c, N / 2, sW, sT, nrbins, half_bpu, sP, 1);
     }
     (void)T;
     return 0;

@@ -41,7 +41,7 @@ def test_fused_vs_unfused(dims, nrbins, tile):
     box, n = 1000.0, 400000
     pos, _ = _particles(n, box, dims)
     with gp.Context(dims) as ctx:
-        ctx.set_option(api.OPT_FUSED_XPASS, tile)                    # 2: the one-CTA-per-SM tile shape
+        ctx.set_option(api.OPT_FUSED_XPASS, tile)                    # 2: 4096-mode tiles at 1024
         ctx.grid_zero()
         ctx.deposit(pos, None, 1.0, box)
         ctx.fft()

@@ -17,10 +17,8 @@ torch.cuda.synchronize()
 ref = None
 with gp.Context(dims, 0) as ctx:
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
-    for name, fused, batch in [("unfused, one cuFFT call", 0, 0), ("fused narrow tile", 1, 0), ("fused wide tile", 2, 0),
-                               ("fused wide, yz batch 2", 2, 2), ("fused wide, yz batch 4", 2, 4),
-                               ("fused wide, yz batch 8", 2, 8), ("fused wide, yz batch 16", 2, 16),
-                               ("unfused, yz n/a (3-D plan)", 0, 4)]:
+    for name, fused, batch in [("unfused: cuFFT 3-D + bin_power_kernel", 0, 0), ("fused x pass (default tile)", 1, 0),
+                               ("fused x pass, 4096-mode tile", 2, 0), ("fused x pass, yz cuFFT in groups of 8 planes", 1, 8)]:
         ctx.set_option(api.OPT_FUSED_XPASS, fused)
         ctx.set_option(api.OPT_FFT_YZ_BATCH, batch)
         def step():
