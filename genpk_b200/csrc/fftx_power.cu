@@ -2,15 +2,18 @@
 // |delta_k|^2 binning of powerspectrum() (powerspectrum.c:35-110) in ONE kernel.
 //
 // Input: the spectrum after the batched 2-D (y,z) transform, [x][n_mid][nc] complex
-// doubles.  A tile is the N x-values of C adjacent kz columns of one ky row (N*C = 4096 or
-// 8192 modes).  Persistent CTAs, 16 modes per thread, the whole tile lives in registers:
+// doubles.  A tile is the N x-values of C adjacent kz columns of one ky row (N*C = 8192
+// modes = 128 KB; 4096 for the small grids).  Persistent CTAs, 16 modes per thread:
 //
-//   ld.global.cs  next tile -> registers, issued before the bin walk of this tile
-//   three register passes of the length-N FFT with two exchanges through one shared
-//     buffer of complex doubles (layouts chosen so that both sides are conflict free)
+//   cp.async   next tile  -> shared memory (natural [x][c] layout), issued after pass 1 } overlapped with
+//   registers  <- this tile; three register passes of the length-N FFT                  } everything below
+//   two exchanges between the passes through a half-tile buffer of complex doubles (lower
+//     half of the index space, then the upper; layouts chosen so both sides are conflict free)
 //   |X|^2 -> the same buffer in kx order; bin walk along |kx| with the +-kx modes folded
-//     (same run/threshold scheme as bin_power_kernel) into the CTA's histogram
+//     (forward-only threshold walk) into the CTA's histograms
 //
+// (Measured alternatives, profiles/r01: loading the next tile straight into registers during
+// the bin walk stalls on the load queue; 4096-mode tiles with two CTAs per SM at 1024 overfetch.)
 // so the x-transformed spectrum is never written and never re-read: this pass moves
 // 16 B/mode once (8.6 GB at 1024^3) where cuFFT's in-place x pass plus bin_power_kernel
 // move 48 B/mode.  Thread-level arithmetic lives in fftx_core.cuh, which is also compiled
@@ -37,14 +40,42 @@ struct FftxArgs {
     const uint32_t *thresh;
     float half_bpu;
     double *sums;             // nrbins P sums, accumulated into
+    int hists;                // histograms per CTA (1 or 2: even / odd tile columns)
 };
 
-// 16-byte streaming load (the spectrum is read exactly once)
-__device__ __forceinline__ double2 ld_stream(const double2 *p)
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
 {
-    double2 r;
-    asm volatile("ld.global.cs.v2.f64 {%0, %1}, [%2];\n" : "=d"(r.x), "=d"(r.y) : "l"(p));
-    return r;
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// One exchange through the half-size buffer E ([N/2][C] complex): the lower half of the index
+// space first, then the upper half.  WI(i) / RI(i): element index of register i on the writing /
+// reading side (for the 256..1024 plans which half an index falls in is a compile-time fact and
+// the predicates below fold away; the 2048 plan splits by thread).
+template <int N, int C, class WI, class RI>
+__device__ __forceinline__ void exchange(fftx::cd *E, const fftx::cd *src, fftx::cd *dst, int c, WI wi, RI ri)
+{
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        if (half)
+            __syncthreads();                           // the lower half has been read
+#pragma unroll
+        for (int i = 0; i < fftx::EPT; i++) {
+            const int idx = wi(i);
+            if ((idx >= N / 2) == (half == 1))
+                E[(idx - half * (N / 2)) * C + c] = src[i];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < fftx::EPT; i++) {
+            const int idx = ri(i);
+            if ((idx >= N / 2) == (half == 1))
+                dst[i] = E[(idx - half * (N / 2)) * C + c];
+        }
+    }
 }
 
 template <class PL>
@@ -53,52 +84,53 @@ __global__ void __launch_bounds__(PL::THREADS, PL::TILE == 4096 ? 2 : 1) fftx_po
     constexpr int N = PL::N, C = PL::C, TILE_MODES = PL::TILE, CTA_THREADS = PL::THREADS;
     constexpr int R2 = PL::R2, R3 = PL::R3;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    cd *const E = reinterpret_cast<cd *>(smem_raw);                                     // [N][C] complex exchange
-    double *const P = reinterpret_cast<double *>(smem_raw);                             // [N][C] |X|^2, same bytes
-    double *const sP = reinterpret_cast<double *>(smem_raw + (size_t)TILE_MODES * 16);
-    unsigned *const sT = reinterpret_cast<unsigned *>(sP + (size_t)A.nrbins * C);       // nrbins + 1
+    cd *const stage = reinterpret_cast<cd *>(smem_raw);                                 // [N][C], the next tile
+    cd *const E = reinterpret_cast<cd *>(smem_raw + (size_t)TILE_MODES * 16);           // [N/2][C] complex exchange
+    double *const P = reinterpret_cast<double *>(E);                                    // [N][C] |X|^2, same bytes
+    double *const sP = reinterpret_cast<double *>(smem_raw + (size_t)TILE_MODES * 24);  // [nrbins][hists]
+    unsigned *const sT = reinterpret_cast<unsigned *>(sP + (size_t)A.nrbins * A.hists); // nrbins + 1
     float *const sW = reinterpret_cast<float *>(sT + A.nrbins + 1);                     // dims/2 + 1
 
     const int tid = threadIdx.x;
     const int c = tid % C, t = tid / C;
-    for (int i = tid; i < A.nrbins * C; i += CTA_THREADS)
-        sP[i] = 0.0;                                                 // one histogram per tile column: sP[bin * C + c]
+    for (int i = tid; i < A.nrbins * A.hists; i += CTA_THREADS)
+        sP[i] = 0.0;
     for (int i = tid; i <= A.nrbins; i += CTA_THREADS)
         sT[i] = A.thresh[i];
     for (int i = tid; i <= N / 2; i += CTA_THREADS)
         sW[i] = A.iw1d[i];
 
-    // per-thread bases of the exchange maps, in elements of E (index * C + c)
-    const int b_ex1w = t * C + c;
-    const int b_ex1r = PL::ex1_r_base(t) * C + c;
+    // per-thread bases of the exchange maps
+    const int b_ex1r = PL::ex1_r_base(t);
     int b_ex2w[4], b_ex2r[4];
 #pragma unroll
     for (int s = 0; s < 4; s++) {
-        b_ex2w[s] = PL::ex2_w_base(t, s) * C + c;
-        b_ex2r[s] = PL::ex2_r_base(t, s) * C + c;
+        b_ex2w[s] = PL::ex2_w_base(t, s);
+        b_ex2r[s] = PL::ex2_r_base(t, s);
     }
     const int kb = PL::out_k_base(t);
+    double *const hist = sP + (c & (A.hists - 1));                   // neighbouring kz columns: different histograms
 
-    cd v[EPT], w[EPT];
-    // this thread's 16 elements of a tile, straight into registers
-    auto load_tile = [&](long long tile) {
-        const int g = (int)(tile % A.groups);
-        const long long m = tile / A.groups;
-        const int kz = g * C + c;
-        if (tile < A.n_tiles && kz < A.nc) {
-            const double2 *src = A.spec + (size_t)m * A.nc + kz;
+    // a thread copies exactly the 16 staging slots it later reads: no barrier guards the staging buffer
+    auto issue = [&](long long tile) {
+        if (tile < A.n_tiles) {
+            const int g = (int)(tile % A.groups);
+            const long long m = tile / A.groups;
+            const int kz = g * C + c;
+            if (kz < A.nc) {
+                const double2 *src = A.spec + (size_t)m * A.nc + kz;
 #pragma unroll
-            for (int i = 0; i < EPT; i++)
-                v[i] = ld_stream(src + (size_t)PL::load_n(t, i) * A.x_stride);
-        } else {
-#pragma unroll
-            for (int i = 0; i < EPT; i++)
-                v[i] = make_double2(0.0, 0.0);
+                for (int i = 0; i < EPT; i++) {
+                    const int n = PL::load_n(t, i);
+                    cp_async16(stage + n * C + c, src + (size_t)n * A.x_stride);
+                }
+            }
         }
+        cp_async_commit_group();
     };
 
     long long tile = blockIdx.x;
-    load_tile(tile);
+    issue(tile);
     for (; tile < A.n_tiles; tile += gridDim.x) {
         const int g = (int)(tile % A.groups);
         const int m = (int)(tile / A.groups);
@@ -107,36 +139,36 @@ __global__ void __launch_bounds__(PL::THREADS, PL::TILE == 4096 ? 2 : 1) fftx_po
         int kj = A.mid0 + m;
         kj = kj <= A.dims / 2 ? kj : kj - A.dims;                    // KVAL, powerspectrum.c:33
 
+        cd v[EPT], w[EPT];
+        cp_async_wait_all();
+#pragma unroll
+        for (int i = 0; i < EPT; i++)
+            v[i] = valid ? stage[PL::load_n(t, i) * C + c] : make_double2(0.0, 0.0);
         PL::pass1(v, t, A.tw);
+        issue(tile + gridDim.x);                                     // the registers above are consumed: slots are free
+
         __syncthreads();                                             // the previous tile's bin walk has left P
-#pragma unroll
-        for (int i = 0; i < EPT; i++) E[b_ex1w + PL::ex1_w_part(i) * C] = v[i];
-        __syncthreads();
-#pragma unroll
-        for (int i = 0; i < EPT; i++) w[i] = E[b_ex1r + PL::ex1_r_part(i) * C];
+        exchange<N, C>(E, v, w, c, [&](int i) { return t + PL::ex1_w_part(i); },
+                       [&](int i) { return b_ex1r + PL::ex1_r_part(i); });
         PL::pass2(w, t, A.tw);
         __syncthreads();
-#pragma unroll
-        for (int i = 0; i < EPT; i++) E[b_ex2w[(i % R2) & 3] + PL::ex2_w_part(i) * C] = w[i];
-        __syncthreads();
-#pragma unroll
-        for (int i = 0; i < EPT; i++) v[i] = E[b_ex2r[(i % R3) & 3] + PL::ex2_r_part(i) * C];
+        exchange<N, C>(E, w, v, c, [&](int i) { return b_ex2w[(i % R2) & 3] + PL::ex2_w_part(i); },
+                       [&](int i) { return b_ex2r[(i % R3) & 3] + PL::ex2_r_part(i); });
         PL::pass3(v);
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < EPT; i++)
             P[PL::slot(kb + PL::out_k_part(i)) * C + c] = fma(v[i].x, v[i].x, v[i].y * v[i].y);
         __syncthreads();
-        load_tile(tile + gridDim.x);                                 // in flight during the bin walk
         if (valid)
-            bin_walk<PL>(P, t, c, kj, kz, A.dims / 2, sW, sT, A.nrbins, A.half_bpu, sP + c, C);
+            bin_walk<PL>(P, t, c, kj, kz, A.dims / 2, sW, sT, A.nrbins, A.half_bpu, hist, A.hists);
     }
+    cp_async_wait_all();
     __syncthreads();
     for (int i = tid; i < A.nrbins; i += CTA_THREADS) {
         double sum = 0.0;
-#pragma unroll
-        for (int j = 0; j < C; j++)
-            sum += sP[i * C + j];
+        for (int j = 0; j < A.hists; j++)
+            sum += sP[i * A.hists + j];
         if (sum != 0.0)
             atomicAdd(&A.sums[i], sum);
     }
@@ -151,13 +183,21 @@ static int fftx_tile_modes(const genpk_ctx *ctx)
     return (dims == 2048 || (dims == 1024 && ctx->fused_xpass != 2)) ? 8192 : 4096;
 }
 
-size_t fftx_smem_bytes(const genpk_ctx *ctx, int nrbins)
+static size_t fftx_smem_bytes_h(const genpk_ctx *ctx, int nrbins, int hists)
 {
     const int dims = ctx->g.dims;
     const size_t tile = (size_t)fftx_tile_modes(ctx);
-    const size_t cols = tile / (size_t)dims;                 // one histogram per tile column
-    return tile * 16 + (size_t)nrbins * 8 * cols + (size_t)(nrbins + 1) * 4 + (size_t)(dims / 2 + 1) * 4 + 16;
+    // staging tile + half-size complex exchange buffer + histograms + threshold and window tables
+    return tile * 16 + tile * 8 + (size_t)nrbins * 8 * hists + (size_t)(nrbins + 1) * 4 + (size_t)(dims / 2 + 1) * 4 + 16;
 }
+
+// two histograms (even / odd tile columns) when they fit
+static int fftx_hists(const genpk_ctx *ctx, int nrbins)
+{
+    return fftx_smem_bytes_h(ctx, nrbins, 2) <= (size_t)ctx->smem_optin ? 2 : 1;
+}
+
+size_t fftx_smem_bytes(const genpk_ctx *ctx, int nrbins) { return fftx_smem_bytes_h(ctx, nrbins, fftx_hists(ctx, nrbins)); }
 
 bool fftx_supported(const genpk_ctx *ctx, int nrbins)
 {
@@ -241,6 +281,7 @@ int fftx_power_raw(genpk_ctx *ctx, const double *spec_yz, int n_mid, int mid0, i
     A.thresh = ctx->d_thresh;
     A.half_bpu = nrbins > 1 ? (float)(0.5 * (nrbins - 1) / log(sqrt(3.0) * A.dims / 2.0)) : 0.f;
     A.sums = sums_dev;
+    A.hists = fftx_hists(ctx, nrbins);
     const size_t smem = fftx_smem_bytes(ctx, nrbins);
     auto tiles = [&](int C) {
         A.groups = (A.nc + C - 1) / C;
