@@ -20,6 +20,7 @@ OPT_DEPOSIT, OPT_SCALE_BITS, OPT_POWER = 1, 2, 3
 OPT_LATTICE_N0, OPT_LATTICE_N1, OPT_MARCH_RY, OPT_MARCH_RX = 4, 5, 6, 7
 OPT_FUSED_XPASS = 8
 OPT_FFT_YZ_BATCH = 9
+OPT_OWN_YPASS = 10
 POWER_CACHED, POWER_FUSED = 0, 1
 DEPOSIT_AUTO, DEPOSIT_DIRECT, DEPOSIT_SORTED, DEPOSIT_TILED, DEPOSIT_MARCH = 0, 1, 2, 3, 4
 STAGE_DEPOSIT, STAGE_FFT, STAGE_POWER, STAGE_SORT, STAGE_ZERO = 0, 1, 2, 3, 4

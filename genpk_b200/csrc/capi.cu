@@ -203,6 +203,10 @@ int genpk_set_option(genpk_ctx *ctx, int option, int64_t value)
         if (value < 0 || value > (1 << 20)) break;
         ctx->fft_yz_batch = (int)value;
         return 0;
+    case GENPK_OPT_OWN_YPASS:
+        if (value != 0 && value != 1) break;
+        ctx->own_ypass = (int)value;
+        return 0;
     case GENPK_OPT_FUSED_XPASS:
         if (value < 0 || value > 2) break;
         ctx->fused_xpass = (int)value;

@@ -80,8 +80,8 @@ struct genpk_ctx {
     bool grid_is_fixed[2] = {false, false};   // grid currently holds int64 fixed-point sums
 
     // cuFFT
-    cufftHandle plan3d = 0, plan_yz = 0, plan_x = 0;
-    bool have_plan3d = false, have_plan_yz = false, have_plan_x = false;
+    cufftHandle plan3d = 0, plan_yz = 0, plan_x = 0, plan_z = 0;
+    bool have_plan3d = false, have_plan_yz = false, have_plan_x = false, have_plan_z = false;
     int fft_yz_batch = 0;             // planes per 2-D cuFFT call (0: the whole slab in one call)
     int plan_yz_batch = 0;
     void *fft_work = nullptr;
@@ -119,6 +119,7 @@ struct genpk_ctx {
 
     // fused x pass (fftx_power.cu)
     int fused_xpass = 1;                      // 0: always cuFFT's x pass + bin_power_kernel
+    int own_ypass = 1;                        // 1: (y,z) transform = cuFFT 1-D r2c along z + fft_cols_kernel along y
     int smem_optin = 0;                       // opt-in shared memory per CTA of this device
     double *d_twiddle = nullptr;              // exp(-2 pi i t/dims), t < dims
     int twiddle_n = 0;
@@ -152,6 +153,8 @@ int power_seed_sums(genpk_ctx *ctx, int n_outer, int outer0, int n_mid, int mid0
 // fftx_power.cu
 bool fftx_supported(const genpk_ctx *ctx, int nrbins);
 int fftx_power_raw(genpk_ctx *ctx, const double *spec_yz, int n_mid, int mid0, int nrbins, double *sums_dev);
+bool fft_cols_supported(const genpk_ctx *ctx);
+int fft_cols_y(genpk_ctx *ctx, double *spec, int n_planes);
 // fft.cu
 int fft_3d(genpk_ctx *ctx, int which);
 int fft_yz(genpk_ctx *ctx, int which);

@@ -26,6 +26,7 @@ static int attach_work(genpk_ctx *ctx)
     if (ctx->have_plan3d) GENPK_CUFFT_OK(cufftSetWorkArea(ctx->plan3d, ctx->fft_work));
     if (ctx->have_plan_yz) GENPK_CUFFT_OK(cufftSetWorkArea(ctx->plan_yz, ctx->fft_work));
     if (ctx->have_plan_x) GENPK_CUFFT_OK(cufftSetWorkArea(ctx->plan_x, ctx->fft_work));
+    if (ctx->have_plan_z) GENPK_CUFFT_OK(cufftSetWorkArea(ctx->plan_z, ctx->fft_work));
     return 0;
 }
 
@@ -47,9 +48,36 @@ int fft_3d(genpk_ctx *ctx, int which)
     return 0;
 }
 
+// (y,z) transform of the local planes as cuFFT's batched 1-D r2c along z (contiguous rows, in
+// place on the padded layout) followed by our own in-place column pass along y.
+static int fft_yz_own(genpk_ctx *ctx, int which)
+{
+    const SlabGeom &g = ctx->g;
+    if (!ctx->have_plan_z) {
+        size_t ws = 0;
+        long long n[1] = {g.dims};
+        long long inembed[1] = {g.fd};
+        long long onembed[1] = {g.nc};
+        GENPK_CUFFT_OK(cufftCreate(&ctx->plan_z));
+        GENPK_CUFFT_OK(cufftSetAutoAllocation(ctx->plan_z, 0));
+        GENPK_CUFFT_OK(cufftMakePlanMany64(ctx->plan_z, 1, n, inembed, 1, g.fd, onembed, 1, g.nc, CUFFT_D2Z,
+                                           (long long)g.nx * g.dims, &ws));
+        ctx->have_plan_z = true;
+        if (int rc = grow_work(ctx, ws)) return rc;
+        if (int rc = attach_work(ctx)) return rc;
+    }
+    GENPK_CUFFT_OK(cufftSetStream(ctx->plan_z, ctx->stream));
+    double *owned = ctx->grid[which] + g.owned_offset();
+    GENPK_CUFFT_OK(cufftExecD2Z(ctx->plan_z, owned, reinterpret_cast<cufftDoubleComplex *>(owned)));
+    ctx->lib_calls++;
+    return fft_cols_y(ctx, owned, g.nx);
+}
+
 int fft_yz(genpk_ctx *ctx, int which)
 {
     const SlabGeom &g = ctx->g;
+    if (fft_cols_supported(ctx))
+        return fft_yz_own(ctx, which);
     // Planes per cuFFT call.  One call over the whole slab runs the z pass over every plane
     // and then the y pass over every plane: 4 trips through HBM.  Groups of a few planes
     // (tens of MB) keep the z pass's output in L2 for the y pass: 2 trips.
@@ -112,7 +140,8 @@ void fft_release(genpk_ctx *ctx)
     if (ctx->have_plan3d) cufftDestroy(ctx->plan3d);
     if (ctx->have_plan_yz) cufftDestroy(ctx->plan_yz);
     if (ctx->have_plan_x) cufftDestroy(ctx->plan_x);
-    ctx->have_plan3d = ctx->have_plan_yz = ctx->have_plan_x = false;
+    if (ctx->have_plan_z) cufftDestroy(ctx->plan_z);
+    ctx->have_plan3d = ctx->have_plan_yz = ctx->have_plan_x = ctx->have_plan_z = false;
     if (ctx->fft_work) cudaFree(ctx->fft_work);
     ctx->fft_work = nullptr;
     ctx->fft_work_bytes = 0;

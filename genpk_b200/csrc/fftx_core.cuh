@@ -110,6 +110,7 @@ template <int R1_, int R2_, int R3_, int TILE_> struct Plan {
     static constexpr int T = N / EPT;             // threads per column
     static constexpr int C = TILE / N;            // columns per tile
     static_assert(C >= 4, "a tile row is at least 64 contiguous bytes");
+    static constexpr bool ONE_UNIT2 = EPT == R2;  // a thread owns one radix-R2 unit in pass 2: its 16 exchange indices share a half
     static constexpr int LOG_R1 = R1 == 16 ? 4 : (R1 == 8 ? 3 : (R1 == 4 ? 2 : 1));
     static_assert(EPT % R1 == 0 && EPT % R2 == 0 && EPT % R3 == 0, "a thread owns whole butterflies");
     static_assert(R2 >= 4 && R3 >= 4, "the exchange swizzle uses two bits");
@@ -224,12 +225,37 @@ FX_HD void bin_walk(const double *P, int t, int c, int kj, int kz, int dims_half
     b = b < 0 ? 0 : (b > nrbins - 1 ? nrbins - 1 : b);
     while (k2first >= sT[b + 1]) b++;
     while (k2first < sT[b]) b--;
+    // every operand of the walk first (independent loads), then the sequential run logic on
+    // registers: the histogram atomics below would otherwise order themselves between the loads
+    double mv[9];
+    float wv[9];
+    // |X|^2 slots of the blocks this thread reads: 8t.., 8(t+1) and the mirror block of -kx.
+    // With R1 >= 8 the swizzle of slot() is constant over an aligned block of 8.
+    const int blk_m = N / 8 - t - 1;
+    const int g0 = PL::slot(8 * t) ^ (8 * t), g1 = PL::slot(8 * t + 8) ^ (8 * t + 8), gm = PL::slot(8 * blk_m) ^ (8 * blk_m);
+#pragma unroll
+    for (int s = 0; s <= 8; s++) {
+        const int a = 8 * t + s;                                        // |kx|
+        int sa, sm;
+        if (PL::LOG_R1 >= 3) {
+            sa = s < 8 ? 8 * t + (s ^ g0) : 8 * t + 8 + g1;
+            sm = 8 * blk_m + (((8 - s) & 7) ^ gm);                      // N - a = 8*blk_m + (8 - s), s >= 1
+        } else {
+            sa = PL::slot(a);
+            sm = PL::slot(s > 0 ? N - a : 0);
+        }
+        double m = P[sa * C + c];
+        if (s > 0 && a < N / 2)
+            m += P[sm * C + c];
+        mv[s] = m;
+        wv[s] = sW[a];
+    }
     unsigned hi = sT[b + 1];
     double p = 0.0;
 #pragma unroll
     for (int s = 0; s <= 8; s++) {
         if (s >= s0) {
-            const int a = 8 * t + s;                                    // |kx|
+            const int a = 8 * t + s;
             const unsigned k2 = base2 + (unsigned)(a * a);
             if (k2 >= hi) {
                 FX_HIST_ADD(&hist[b * hstride], p * mult);
@@ -237,13 +263,10 @@ FX_HD void bin_walk(const double *P, int t, int c, int kj, int kz, int dims_half
                 hi = sT[b + 1];
                 p = 0.0;
             }
-            double m = P[PL::slot(a) * C + c];
-            if (s > 0 && a < N / 2)
-                m += P[PL::slot(N - a) * C + c];
-            double w = (double)FX_FMUL(FX_FMUL(sW[a], fj), fz);         // (iwx*iwy)*iwz in float, promoted: fieldize.cpp:129-132
+            double w = (double)FX_FMUL(FX_FMUL(wv[s], fj), fz);         // (iwx*iwy)*iwz in float, promoted: fieldize.cpp:129-132
             w = w * w;                                                  // invwindow() = prod^2
             w = w * w;                                                  // pow(invwindow,2), powerspectrum.c:68
-            p = fma(m, w, p);
+            p = fma(mv[s], w, p);
         }
     }
     FX_HIST_ADD(&hist[b * hstride], p * mult);

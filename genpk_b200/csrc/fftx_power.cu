@@ -53,27 +53,44 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 // One exchange through the half-size buffer E ([N/2][C] complex): the lower half of the index
 // space first, then the upper half.  WI(i) / RI(i): element index of register i on the writing /
-// reading side (for the 256..1024 plans which half an index falls in is a compile-time fact and
-// the predicates below fold away; the 2048 plan splits by thread).
-template <int N, int C, class WI, class RI>
+// reading side.  Which half an index falls in is a compile-time property of i (the predicates
+// fold away), except on the pass-2 side of a plan whose thread owns a single radix-R2 unit
+// (2048): there all 16 indices of a thread lie in the same half (W_UNI / R_UNI).
+template <int N, int C, bool W_UNI, bool R_UNI, class WI, class RI>
 __device__ __forceinline__ void exchange(fftx::cd *E, const fftx::cd *src, fftx::cd *dst, int c, WI wi, RI ri)
 {
 #pragma unroll
     for (int half = 0; half < 2; half++) {
         if (half)
             __syncthreads();                           // the lower half has been read
+        if (W_UNI) {
+            if ((wi(0) >= N / 2) == (half == 1)) {
 #pragma unroll
-        for (int i = 0; i < fftx::EPT; i++) {
-            const int idx = wi(i);
-            if ((idx >= N / 2) == (half == 1))
-                E[(idx - half * (N / 2)) * C + c] = src[i];
+                for (int i = 0; i < fftx::EPT; i++)
+                    E[(wi(i) - half * (N / 2)) * C + c] = src[i];
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < fftx::EPT; i++) {
+                const int idx = wi(i);
+                if ((idx >= N / 2) == (half == 1))
+                    E[(idx - half * (N / 2)) * C + c] = src[i];
+            }
         }
         __syncthreads();
+        if (R_UNI) {
+            if ((ri(0) >= N / 2) == (half == 1)) {
 #pragma unroll
-        for (int i = 0; i < fftx::EPT; i++) {
-            const int idx = ri(i);
-            if ((idx >= N / 2) == (half == 1))
-                dst[i] = E[(idx - half * (N / 2)) * C + c];
+                for (int i = 0; i < fftx::EPT; i++)
+                    dst[i] = E[(ri(i) - half * (N / 2)) * C + c];
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < fftx::EPT; i++) {
+                const int idx = ri(i);
+                if ((idx >= N / 2) == (half == 1))
+                    dst[i] = E[(idx - half * (N / 2)) * C + c];
+            }
         }
     }
 }
@@ -148,11 +165,11 @@ __global__ void __launch_bounds__(PL::THREADS, PL::TILE == 4096 ? 2 : 1) fftx_po
         issue(tile + gridDim.x);                                     // the registers above are consumed: slots are free
 
         __syncthreads();                                             // the previous tile's bin walk has left P
-        exchange<N, C>(E, v, w, c, [&](int i) { return t + PL::ex1_w_part(i); },
+        exchange<N, C, false, PL::ONE_UNIT2>(E, v, w, c, [&](int i) { return t + PL::ex1_w_part(i); },
                        [&](int i) { return b_ex1r + PL::ex1_r_part(i); });
         PL::pass2(w, t, A.tw);
         __syncthreads();
-        exchange<N, C>(E, w, v, c, [&](int i) { return b_ex2w[(i % R2) & 3] + PL::ex2_w_part(i); },
+        exchange<N, C, PL::ONE_UNIT2, false>(E, w, v, c, [&](int i) { return b_ex2w[(i % R2) & 3] + PL::ex2_w_part(i); },
                        [&](int i) { return b_ex2r[(i % R3) & 3] + PL::ex2_r_part(i); });
         PL::pass3(v);
         __syncthreads();
@@ -172,6 +189,89 @@ __global__ void __launch_bounds__(PL::THREADS, PL::TILE == 4096 ? 2 : 1) fftx_po
         if (sum != 0.0)
             atomicAdd(&A.sums[i], sum);
     }
+}
+
+// ---------------------------------------------------------------------------------
+// The same tile machinery as a plain in-place column transform: length-N FFTs along the
+// MIDDLE axis (y) of [n_planes][N][nc] complex planes, i.e. the y pass of the (y,z)
+// transform after cuFFT's batched 1-D r2c along z.  Reads and writes every mode once in
+// rows of C*16 bytes (cuFFT's strided pass reaches about half the copy bandwidth here).
+// ---------------------------------------------------------------------------------
+struct FftColsArgs {
+    double2 *spec;            // [n_planes][N][nc], transformed in place
+    const double2 *tw;
+    int nc;
+    long long plane_stride;   // modes per plane: N * nc
+    int groups;               // column groups per plane: ceil(nc / C)
+    long long n_tiles;        // n_planes * groups
+};
+
+template <class PL>
+__global__ void __launch_bounds__(PL::THREADS, PL::TILE == 4096 ? 2 : 1) fft_cols_kernel(const __grid_constant__ FftColsArgs A)
+{
+    constexpr int N = PL::N, C = PL::C, TILE_MODES = PL::TILE;
+    constexpr int R2 = PL::R2, R3 = PL::R3;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cd *const stage = reinterpret_cast<cd *>(smem_raw);                                 // [N][C], the next tile
+    cd *const E = reinterpret_cast<cd *>(smem_raw + (size_t)TILE_MODES * 16);           // [N/2][C] complex exchange
+    const int tid = threadIdx.x;
+    const int c = tid % C, t = tid / C;
+    const int b_ex1r = PL::ex1_r_base(t);
+    int b_ex2w[4], b_ex2r[4];
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+        b_ex2w[s] = PL::ex2_w_base(t, s);
+        b_ex2r[s] = PL::ex2_r_base(t, s);
+    }
+    const int kb = PL::out_k_base(t);
+
+    auto issue = [&](long long tile) {
+        if (tile < A.n_tiles) {
+            const int g = (int)(tile % A.groups);
+            const long long o = tile / A.groups;
+            const int kz = g * C + c;
+            if (kz < A.nc) {
+                const double2 *src = A.spec + (size_t)o * A.plane_stride + kz;
+#pragma unroll
+                for (int i = 0; i < EPT; i++) {
+                    const int n = PL::load_n(t, i);
+                    cp_async16(stage + n * C + c, src + (size_t)n * A.nc);
+                }
+            }
+        }
+        cp_async_commit_group();
+    };
+
+    long long tile = blockIdx.x;
+    issue(tile);
+    for (; tile < A.n_tiles; tile += gridDim.x) {
+        const int g = (int)(tile % A.groups);
+        const long long o = tile / A.groups;
+        const int kz = g * C + c;
+        const bool valid = kz < A.nc;
+        cd v[EPT], w[EPT];
+        cp_async_wait_all();
+#pragma unroll
+        for (int i = 0; i < EPT; i++)
+            v[i] = valid ? stage[PL::load_n(t, i) * C + c] : make_double2(0.0, 0.0);
+        PL::pass1(v, t, A.tw);
+        issue(tile + gridDim.x);                                     // another tile: never the rows written below
+        __syncthreads();                                             // the previous tile's last exchange read is over
+        exchange<N, C, false, PL::ONE_UNIT2>(E, v, w, c, [&](int i) { return t + PL::ex1_w_part(i); },
+                       [&](int i) { return b_ex1r + PL::ex1_r_part(i); });
+        PL::pass2(w, t, A.tw);
+        __syncthreads();
+        exchange<N, C, PL::ONE_UNIT2, false>(E, w, v, c, [&](int i) { return b_ex2w[(i % R2) & 3] + PL::ex2_w_part(i); },
+                       [&](int i) { return b_ex2r[(i % R3) & 3] + PL::ex2_r_part(i); });
+        PL::pass3(v);
+        if (valid) {
+            double2 *dst = A.spec + (size_t)o * A.plane_stride + kz;
+#pragma unroll
+            for (int i = 0; i < EPT; i++)
+                dst[(size_t)(kb + PL::out_k_part(i)) * A.nc] = v[i];
+        }
+    }
+    cp_async_wait_all();
 }
 
 // 8192-mode tiles (one CTA of 512 threads per SM) keep a tile row at 128 B for 1024 and 64 B for
@@ -303,6 +403,54 @@ int fftx_power_raw(genpk_ctx *ctx, const double *spec_yz, int n_mid, int mid0, i
     case 1024: tiles(P1024::C); return launch_fftx<P1024>(ctx, A, smem);
     case 2048: tiles(P2048::C); return launch_fftx<P2048>(ctx, A, smem);
     }
+    return 1;
+}
+
+template <class PL> static int launch_cols(genpk_ctx *ctx, FftColsArgs &A, int n_planes)
+{
+    auto kern = fft_cols_kernel<PL>;
+    const size_t smem = (size_t)PL::TILE * 24;                   // staging tile + half-size exchange buffer
+    A.groups = (A.nc + PL::C - 1) / PL::C;
+    A.n_tiles = (long long)n_planes * A.groups;
+    GENPK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    GENPK_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PL::THREADS, smem));
+    if (per_sm < 1) {
+        set_error("column FFT: %zu bytes of shared memory do not fit", smem);
+        return 1;
+    }
+    long long ctas = (long long)ctx->sm_count * per_sm;
+    if (ctas > A.n_tiles) ctas = A.n_tiles;
+    if (ctas < 1) ctas = 1;
+    kern<<<(int)ctas, PL::THREADS, smem, ctx->stream>>>(A);
+    ctx->launches++;
+    GENPK_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+bool fft_cols_supported(const genpk_ctx *ctx)
+{
+    const int d = ctx->g.dims;
+    return ctx->own_ypass != 0 && (d == 256 || d == 512 || d == 1024 || d == 2048) &&
+           (size_t)8192 * 24 <= (size_t)ctx->smem_optin;
+}
+
+// In-place FFT along y of n_planes planes [dims][nc] starting at spec.
+int fft_cols_y(genpk_ctx *ctx, double *spec, int n_planes)
+{
+    if (int rc = ensure_twiddles(ctx)) return rc;
+    FftColsArgs A;
+    A.spec = reinterpret_cast<double2 *>(spec);
+    A.tw = reinterpret_cast<const double2 *>(ctx->d_twiddle);
+    A.nc = ctx->g.nc;
+    A.plane_stride = (long long)ctx->g.dims * ctx->g.nc;
+    switch (ctx->g.dims) {
+    case 256: return launch_cols<Plan<4, 8, 8, 4096>>(ctx, A, n_planes);
+    case 512: return launch_cols<Plan<8, 8, 8, 4096>>(ctx, A, n_planes);
+    case 1024: return launch_cols<Plan<16, 8, 8, 8192>>(ctx, A, n_planes);
+    case 2048: return launch_cols<Plan<16, 16, 8, 8192>>(ctx, A, n_planes);
+    }
+    set_error("column FFT: unsupported grid side %d", ctx->g.dims);
     return 1;
 }
 

@@ -111,3 +111,34 @@ def test_fused_slab_block(dims, P, rank):
         assert np.all(f[0][~nz] == 0)
     finally:
         ctx.close()
+
+
+@pytest.mark.parametrize("dims,P", [(256, 1), (512, 1), (512, 4), (1024, 1), (2048, 16)])
+def test_own_y_pass_vs_cufft_2d(dims, P):
+    """genpk_slab_fft_yz: cuFFT 1-D r2c along z + fft_cols_kernel along y (default) against
+    cuFFT's batched 2-D plan, on the same random planes (device-resident comparison)."""
+    import torch
+    from genpk_b200.distributed import _DevMem
+    dev = torch.device("cuda", 0)
+    outs = []
+    for own in (1, 0):
+        ctx = api.Context(dims, 0, 0, P, P - 1)
+        try:
+            ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+            ctx.set_option(api.OPT_OWN_YPASS, own)
+            nd = ctx.grid_doubles()
+            grid = torch.as_tensor(_DevMem(ctx.grid_ptr(), nd * 8), device=dev)
+            gen = torch.Generator(device=dev).manual_seed(dims)
+            grid.copy_(torch.randn(nd, dtype=torch.float64, device=dev, generator=gen))
+            launches0 = ctx.launch_count()
+            ctx.slab_fft_yz()
+            torch.cuda.synchronize()
+            assert (ctx.launch_count() > launches0) == bool(own)
+            off = ctx.owned_offset()
+            owned = (dims // P) * dims * 2 * (dims // 2 + 1)
+            outs.append(grid[off:off + owned].clone())
+        finally:
+            ctx.close()
+    a, b = outs
+    scale = float(b.abs().max())
+    assert float((a - b).abs().max()) <= 1e-12 * scale

@@ -17,10 +17,10 @@ torch.cuda.synchronize()
 ref = None
 with gp.Context(dims, 0) as ctx:
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
-    for name, fused, batch in [("unfused: cuFFT 3-D + bin_power_kernel", 0, 0), ("fused x pass (default tile)", 1, 0),
-                               ("fused x pass, 4096-mode tile", 2, 0), ("fused x pass, yz cuFFT in groups of 8 planes", 1, 8)]:
+    for name, fused, own_y in [("unfused: cuFFT 3-D + bin_power_kernel", 0, 0), ("fused x pass, cuFFT 2-D (y,z)", 1, 0),
+                               ("fused x pass, cuFFT z + own y pass", 1, 1), ("fused x pass 4096-mode tile, own y pass", 2, 1)]:
         ctx.set_option(api.OPT_FUSED_XPASS, fused)
-        ctx.set_option(api.OPT_FFT_YZ_BATCH, batch)
+        ctx.set_option(api.OPT_OWN_YPASS, own_y)
         def step():
             ctx.grid_zero()
             ctx.deposit_dev(dpos.data_ptr(), n, 0, 1.0, box)
