@@ -354,6 +354,8 @@ def run_ours(args):
         out = step_device()
     barrier()
     ctx.stage_reset()
+    if pipe is not None:
+        pipe.profile = True
     launches0 = ctx.launch_count()
     sampler = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -376,6 +378,10 @@ def run_ours(args):
         tot, nrec = ctx.stage_total_ms(st)
         stage_ms[name] = tot / args.steps if nrec else 0.0
     ctx.synchronize()
+    if pipe is not None:
+        pipe.profile = False
+        for k, v in pipe.collect_timings().items():
+            stage_ms[k] = v / args.steps                     # exchange steps of rank 0 (device time)
     power, cnt, keffs = out
     assert int(cnt.astype(np.int64).sum()) == dims ** 3 - 1, "mode counts do not sum to dims^3-1"
 

@@ -134,9 +134,34 @@ class SlabPipeline:
             raise ValueError(f"grid side {dims} is not divisible by {self.P} ranks")
         self.dims, self.stages = dims, stages
         self.timings = {}
+        self.profile = False         # True: CUDA-event timing of the exchange steps into self.timings (ms, summed)
+        self._events = []
         # wide-ghost stages: deposit the shard as it is and only route when a rank had stragglers
         # beyond its ghosts ("local" until that happens once, then "route" for good)
         self.placement = "local" if getattr(stages, "ghost_planes", 0) > 0 and self.P > 1 else "route"
+
+    # ---- optional timing of the exchange steps (device time on the current stream) --------------
+    class _Timed:
+        def __init__(self, pipe, name):
+            self.pipe, self.name = pipe, name
+
+        def __enter__(self):
+            if self.pipe.profile:
+                self.e0 = torch.cuda.Event(enable_timing=True)
+                self.e1 = torch.cuda.Event(enable_timing=True)
+                self.e0.record()
+
+        def __exit__(self, *exc):
+            if self.pipe.profile:
+                self.e1.record()
+                self.pipe._events.append((self.name, self.e0, self.e1))
+
+    def collect_timings(self):
+        """Sum the recorded event pairs into self.timings (call after a synchronize)."""
+        for name, e0, e1 in self._events:
+            self.timings[name] = self.timings.get(name, 0.0) + e0.elapsed_time(e1)
+        self._events = []
+        return self.timings
 
     # ---- exchange steps ---------------------------------------------------------------
     def exchange_particles(self, spos, smass, counts):
@@ -210,17 +235,20 @@ class SlabPipeline:
         self.stages.deposit(rpos, rmass, cmass, boxsize, which)
 
     def spectrum(self, which=0, x_pass=True):
-        self.exchange_ghost(which)
+        with self._Timed(self, "ghost_exchange"):
+            self.exchange_ghost(which)
         self.stages.fft_yz(which)
-        spec = self.transpose(which)
+        with self._Timed(self, "transpose"):
+            spec = self.transpose(which)
         if x_pass:
             self.stages.fft_x(spec)
         return spec
 
     def _reduce_finalize(self, sums, nrbins, total_mass, total_mass2):
-        if self.P > 1:
-            dist.all_reduce(sums, group=self.group)
-        host = sums.cpu().numpy()
+        with self._Timed(self, "allreduce_d2h"):
+            if self.P > 1:
+                dist.all_reduce(sums, group=self.group)
+            host = sums.cpu().numpy()
         return api.power_finalize(host, nrbins, total_mass, total_mass2)
 
     def power(self, spec_a, spec_b, nrbins, total_mass, total_mass2):
