@@ -66,6 +66,7 @@ def parse_args():
     ap.add_argument("--xpass-narrow-tile", action="store_true", help="fused x pass with 4096-mode tiles at 1024 (two CTAs per SM)")
     ap.add_argument("--fft-yz-batch", type=int, default=-1, help="x planes per 2-D cuFFT call (0 = all, -1 = library default)")
     ap.add_argument("--no-own-ypass", action="store_true", help="cuFFT's 2-D (y,z) plan instead of cuFFT z + own y pass")
+    ap.add_argument("--no-scatter", action="store_true", help="multi-GPU: pack + all-to-all instead of the y pass storing into peers")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
@@ -313,6 +314,8 @@ def run_ours(args):
         stages.ctx.set_power_mode(api.POWER_FUSED if args.power == "fused" else api.POWER_CACHED)
         ctx = stages.ctx
         pipe = SlabPipeline(dims, stages)
+        if not (args.no_scatter or args.no_fused_xpass or args.no_own_ypass):
+            stages.enable_scatter()
 
         def step_device():
             return pipe.pk(dpos, None, 1.0, BOX, total_mass, nrbins)
@@ -434,7 +437,9 @@ def run_ours(args):
         "config": {"workload": wl["label"], "particles": n_total, "grid": dims, "nrbins": nrbins, "box": BOX,
                    "accumulation": "int64 fixed-point" if args.fixed_point else "fp64 red.add",
                    "deposit_mode": args.deposit, "order_probe": ctx.last_order(), "binning_mode": args.power,
-                   "x_pass": "fused with binning (fftx_power_kernel)" if fused else "cuFFT", "parallelism": (f"x-slab x{world}, {ghost} ghost planes, particles {pipe.placement}" if world > 1
+                   "x_pass": "fused with binning (fftx_power_kernel)" if fused else "cuFFT", "parallelism": (f"x-slab x{world}, {ghost} ghost planes, particles {pipe.placement}, transpose "
+                                   + ("fused into the y pass (peer stores)" if stages.scatter_ready else "pack + all-to-all")
+                                   if world > 1
                                    else "single GPU"),
                    "l2": "inputs larger than L2 (no flush needed)"},
         "pk_time_ms": ms_step,

@@ -70,6 +70,11 @@ SIGNATURES = {
     "genpk_slab_spectrum_bytes": (C.c_size_t, [C.c_void_p]),
     "genpk_slab_power_partial": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, c_f64p]),
     "genpk_slab_fftx_power_partial": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, c_f64p]),
+    "genpk_slab_recv_buffer": (C.c_void_p, [C.c_void_p, C.POINTER(C.c_size_t)]),
+    "genpk_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "genpk_slab_set_peer": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "genpk_slab_scatter_supported": (C.c_int, [C.c_void_p]),
+    "genpk_slab_fft_yz_scatter": (C.c_int, [C.c_void_p, C.c_int]),
     "genpk_power_finalize": (C.c_int, [c_f64p, C.c_int, C.c_double, C.c_double, c_f64p, c_i32p, c_f64p]),
     "genpk_bin_thresholds": (C.c_int, [C.c_int, C.c_int, C.c_uint, C.c_void_p]),
     # synthetic particle sets

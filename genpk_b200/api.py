@@ -367,6 +367,33 @@ class Context:
               "genpk_slab_fftx_power_partial")
 
 
+    # transpose fused into the y pass (peer stores)
+    IPC_HANDLE_BYTES = 64
+
+    def slab_recv_buffer(self):
+        """(device pointer, bytes) of this rank's library-owned transposed block [dims][ny][nc]."""
+        nbytes = C.c_size_t(0)
+        p = self.lib.genpk_slab_recv_buffer(self.h, C.byref(nbytes))
+        if not p:
+            raise _lib.GenPKError(_lib.last_error())
+        return p, nbytes.value
+
+    def ipc_export(self) -> bytes:
+        buf = C.create_string_buffer(self.IPC_HANDLE_BYTES)
+        check(self.lib.genpk_ipc_export(self.h, buf), "genpk_ipc_export")
+        return buf.raw
+
+    def slab_set_peer(self, rank: int, ipc_handle: bytes = None, same_process_ptr: int = 0):
+        h = C.create_string_buffer(ipc_handle, self.IPC_HANDLE_BYTES) if ipc_handle is not None else None
+        check(self.lib.genpk_slab_set_peer(self.h, int(rank), h, same_process_ptr or None), "genpk_slab_set_peer")
+
+    def slab_scatter_supported(self) -> bool:
+        return bool(self.lib.genpk_slab_scatter_supported(self.h))
+
+    def slab_fft_yz_scatter(self, which: int = 0):
+        check(self.lib.genpk_slab_fft_yz_scatter(self.h, which), "genpk_slab_fft_yz_scatter")
+
+
 def power_finalize(sums: np.ndarray, nrbins: int, total_mass: float, total_mass2: float):
     """powerspectrum.c:102-108 applied to all-reduced raw sums [3][nrbins]."""
     sums = np.ascontiguousarray(sums, np.float64)

@@ -151,6 +151,9 @@ void genpk_destroy(genpk_ctx *ctx)
     if (ctx->d_errors) cudaFree(ctx->d_errors);
     if (ctx->d_order) cudaFree(ctx->d_order);
     if (ctx->d_twiddle) cudaFree(ctx->d_twiddle);
+    for (int r = 0; r < GENPK_MAX_PEERS; r++)
+        if (ctx->peer_opened[r] && ctx->peer_recv[r]) cudaIpcCloseMemHandle(ctx->peer_recv[r]);
+    if (ctx->d_recv) cudaFree(ctx->d_recv);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (int i = 0; i < ST_COUNT; i++)
         for (int s = 0; s < genpk_ctx::EV_SLOTS; s++) {
@@ -608,6 +611,77 @@ int genpk_slab_fftx_power_partial(genpk_ctx *ctx, const void *spec_yz_dev, int n
     stage_begin(ctx, ST_POWER);
     if (int rc = fftx_power_raw(ctx, (const double *)spec_yz_dev, ny, ctx->g.rank * ny, nrbins, sums_dev)) return rc;
     stage_end(ctx, ST_POWER);
+    return 0;
+}
+
+void *genpk_slab_recv_buffer(genpk_ctx *ctx, size_t *bytes)
+{
+    if (!ctx) { set_error("genpk_slab_recv_buffer: null context"); return nullptr; }
+    const size_t n = genpk_slab_spectrum_bytes(ctx);
+    if (!ctx->d_recv && cudaMalloc(&ctx->d_recv, n) != cudaSuccess) {
+        set_error("genpk_slab_recv_buffer: cudaMalloc(%zu) failed: %s", n, cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    if (bytes) *bytes = n;
+    return ctx->d_recv;
+}
+
+int genpk_ipc_export(genpk_ctx *ctx, void *handle_out)
+{
+    if (!ctx || !handle_out) { set_error("genpk_ipc_export: bad arguments"); return 1; }
+    if (!genpk_slab_recv_buffer(ctx, nullptr)) return 1;
+    static_assert(sizeof(cudaIpcMemHandle_t) == GENPK_IPC_HANDLE_BYTES, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    GENPK_CUDA_OK(cudaIpcGetMemHandle(&h, ctx->d_recv));
+    memcpy(handle_out, &h, sizeof(h));
+    return 0;
+}
+
+int genpk_slab_set_peer(genpk_ctx *ctx, int rank, const void *ipc_handle, void *same_process_ptr)
+{
+    if (!ctx || rank < 0 || rank >= ctx->g.nranks || rank >= GENPK_MAX_PEERS || (!ipc_handle && !same_process_ptr)) {
+        set_error("genpk_slab_set_peer: bad arguments");
+        return 1;
+    }
+    if (ctx->peer_opened[rank] && ctx->peer_recv[rank]) cudaIpcCloseMemHandle(ctx->peer_recv[rank]);
+    ctx->peer_opened[rank] = false;
+    ctx->peer_recv[rank] = nullptr;
+    if (rank == ctx->g.rank) {
+        if (!genpk_slab_recv_buffer(ctx, nullptr)) return 1;
+        ctx->peer_recv[rank] = ctx->d_recv;                       // own rows: local stores
+    } else if (same_process_ptr) {
+        ctx->peer_recv[rank] = same_process_ptr;
+    } else {
+        cudaIpcMemHandle_t h;
+        memcpy(&h, ipc_handle, sizeof(h));
+        void *p = nullptr;
+        GENPK_CUDA_OK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        ctx->peer_recv[rank] = p;
+        ctx->peer_opened[rank] = true;
+    }
+    bool all = true;
+    for (int r = 0; r < ctx->g.nranks; r++)
+        all = all && ctx->peer_recv[r] != nullptr;
+    ctx->peers_set = all;
+    return 0;
+}
+
+int genpk_slab_scatter_supported(const genpk_ctx *ctx)
+{
+    if (!ctx) return 0;
+    const int ny = ctx->g.dims / ctx->g.nranks;
+    return fft_cols_supported(ctx) && ctx->g.nranks <= GENPK_MAX_PEERS && (ny & (ny - 1)) == 0 ? 1 : 0;
+}
+
+int genpk_slab_fft_yz_scatter(genpk_ctx *ctx, int which)
+{
+    if (!check_which(ctx, which, "genpk_slab_fft_yz_scatter")) return 1;
+    if (!genpk_slab_scatter_supported(ctx)) { set_error("genpk_slab_fft_yz_scatter: unsupported geometry"); return 1; }
+    stage_begin(ctx, ST_FFT);
+    if (int rc = fixed_to_double(ctx, which)) return rc;
+    if (int rc = fft_z_rows(ctx, which)) return rc;
+    if (int rc = fft_cols_y_scatter(ctx, ctx->grid[which] + ctx->g.owned_offset(), ctx->g.nx)) return rc;
+    stage_end(ctx, ST_FFT);
     return 0;
 }
 

@@ -122,6 +122,11 @@ struct genpk_ctx {
     int own_ypass = 1;                        // 1: (y,z) transform = cuFFT 1-D r2c along z + fft_cols_kernel along y
     int smem_optin = 0;                       // opt-in shared memory per CTA of this device
     double *d_twiddle = nullptr;              // exp(-2 pi i t/dims), t < dims
+    // transpose fused into the y pass: every rank's [dims][ny][nc] block (own entry = d_recv)
+    void *d_recv = nullptr;                   // library-owned transposed block of this rank
+    void *peer_recv[GENPK_MAX_PEERS] = {};
+    bool peer_opened[GENPK_MAX_PEERS] = {};   // entry came from cudaIpcOpenMemHandle
+    bool peers_set = false;
     int twiddle_n = 0;
     long long last_order[7] = {0, 0, 0, 0, 0, 0, 0};   // last probe verdict (diagnostics)
 
@@ -155,6 +160,8 @@ bool fftx_supported(const genpk_ctx *ctx, int nrbins);
 int fftx_power_raw(genpk_ctx *ctx, const double *spec_yz, int n_mid, int mid0, int nrbins, double *sums_dev);
 bool fft_cols_supported(const genpk_ctx *ctx);
 int fft_cols_y(genpk_ctx *ctx, double *spec, int n_planes);
+int fft_cols_y_scatter(genpk_ctx *ctx, double *spec, int n_planes);
+int fft_z_rows(genpk_ctx *ctx, int which);
 // fft.cu
 int fft_3d(genpk_ctx *ctx, int which);
 int fft_yz(genpk_ctx *ctx, int which);

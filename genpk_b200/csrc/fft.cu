@@ -49,8 +49,8 @@ int fft_3d(genpk_ctx *ctx, int which)
 }
 
 // (y,z) transform of the local planes as cuFFT's batched 1-D r2c along z (contiguous rows, in
-// place on the padded layout) followed by our own in-place column pass along y.
-static int fft_yz_own(genpk_ctx *ctx, int which)
+// place on the padded layout: fft_z_rows) followed by our own in-place column pass along y.
+int fft_z_rows(genpk_ctx *ctx, int which)
 {
     const SlabGeom &g = ctx->g;
     if (!ctx->have_plan_z) {
@@ -70,7 +70,13 @@ static int fft_yz_own(genpk_ctx *ctx, int which)
     double *owned = ctx->grid[which] + g.owned_offset();
     GENPK_CUFFT_OK(cufftExecD2Z(ctx->plan_z, owned, reinterpret_cast<cufftDoubleComplex *>(owned)));
     ctx->lib_calls++;
-    return fft_cols_y(ctx, owned, g.nx);
+    return 0;
+}
+
+static int fft_yz_own(genpk_ctx *ctx, int which)
+{
+    if (int rc = fft_z_rows(ctx, which)) return rc;
+    return fft_cols_y(ctx, ctx->grid[which] + ctx->g.owned_offset(), ctx->g.nx);
 }
 
 int fft_yz(genpk_ctx *ctx, int which)

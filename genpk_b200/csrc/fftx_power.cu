@@ -204,9 +204,15 @@ struct FftColsArgs {
     long long plane_stride;   // modes per plane: N * nc
     int groups;               // column groups per plane: ceil(nc / C)
     long long n_tiles;        // n_planes * groups
+    // SCATTER (multi-GPU transpose fused into the pass): row ky of local plane o is written to
+    // rank ky / ny, into its [dims][ny][nc] block at plane x0 + o, row ky % ny -- a peer store
+    // over NVLink (or a local store for the rank's own rows) instead of an in-place store.
+    double2 *peer[GENPK_MAX_PEERS];
+    int ny_shift;             // log2(ny)
+    int x0;                   // first global x plane of this rank
 };
 
-template <class PL>
+template <class PL, bool SCATTER>
 __global__ void __launch_bounds__(PL::THREADS, PL::TILE == 4096 ? 2 : 1) fft_cols_kernel(const __grid_constant__ FftColsArgs A)
 {
     constexpr int N = PL::N, C = PL::C, TILE_MODES = PL::TILE;
@@ -265,10 +271,20 @@ __global__ void __launch_bounds__(PL::THREADS, PL::TILE == 4096 ? 2 : 1) fft_col
                        [&](int i) { return b_ex2r[(i % R3) & 3] + PL::ex2_r_part(i); });
         PL::pass3(v);
         if (valid) {
-            double2 *dst = A.spec + (size_t)o * A.plane_stride + kz;
+            if (SCATTER) {
+                const int ny = 1 << A.ny_shift;
+                const size_t plane_off = (size_t)(A.x0 + o) * ny * A.nc + kz;
 #pragma unroll
-            for (int i = 0; i < EPT; i++)
-                dst[(size_t)(kb + PL::out_k_part(i)) * A.nc] = v[i];
+                for (int i = 0; i < EPT; i++) {
+                    const int ky = kb + PL::out_k_part(i);
+                    A.peer[ky >> A.ny_shift][plane_off + (size_t)(ky & (ny - 1)) * A.nc] = v[i];
+                }
+            } else {
+                double2 *dst = A.spec + (size_t)o * A.plane_stride + kz;
+#pragma unroll
+                for (int i = 0; i < EPT; i++)
+                    dst[(size_t)(kb + PL::out_k_part(i)) * A.nc] = v[i];
+            }
         }
     }
     cp_async_wait_all();
@@ -406,9 +422,9 @@ int fftx_power_raw(genpk_ctx *ctx, const double *spec_yz, int n_mid, int mid0, i
     return 1;
 }
 
-template <class PL> static int launch_cols(genpk_ctx *ctx, FftColsArgs &A, int n_planes)
+template <class PL, bool SCATTER> static int launch_cols(genpk_ctx *ctx, FftColsArgs &A, int n_planes)
 {
-    auto kern = fft_cols_kernel<PL>;
+    auto kern = fft_cols_kernel<PL, SCATTER>;
     const size_t smem = (size_t)PL::TILE * 24;                   // staging tile + half-size exchange buffer
     A.groups = (A.nc + PL::C - 1) / PL::C;
     A.n_tiles = (long long)n_planes * A.groups;
@@ -435,23 +451,52 @@ bool fft_cols_supported(const genpk_ctx *ctx)
            (size_t)8192 * 24 <= (size_t)ctx->smem_optin;
 }
 
+template <bool SCATTER> static int cols_dispatch(genpk_ctx *ctx, FftColsArgs &A, int n_planes)
+{
+    switch (ctx->g.dims) {
+    case 256: return launch_cols<Plan<4, 8, 8, 4096>, SCATTER>(ctx, A, n_planes);
+    case 512: return launch_cols<Plan<8, 8, 8, 4096>, SCATTER>(ctx, A, n_planes);
+    case 1024: return launch_cols<Plan<16, 8, 8, 8192>, SCATTER>(ctx, A, n_planes);
+    case 2048: return launch_cols<Plan<16, 16, 8, 8192>, SCATTER>(ctx, A, n_planes);
+    }
+    set_error("column FFT: unsupported grid side %d", ctx->g.dims);
+    return 1;
+}
+
 // In-place FFT along y of n_planes planes [dims][nc] starting at spec.
 int fft_cols_y(genpk_ctx *ctx, double *spec, int n_planes)
 {
     if (int rc = ensure_twiddles(ctx)) return rc;
-    FftColsArgs A;
+    FftColsArgs A = {};
     A.spec = reinterpret_cast<double2 *>(spec);
     A.tw = reinterpret_cast<const double2 *>(ctx->d_twiddle);
     A.nc = ctx->g.nc;
     A.plane_stride = (long long)ctx->g.dims * ctx->g.nc;
-    switch (ctx->g.dims) {
-    case 256: return launch_cols<Plan<4, 8, 8, 4096>>(ctx, A, n_planes);
-    case 512: return launch_cols<Plan<8, 8, 8, 4096>>(ctx, A, n_planes);
-    case 1024: return launch_cols<Plan<16, 8, 8, 8192>>(ctx, A, n_planes);
-    case 2048: return launch_cols<Plan<16, 16, 8, 8192>>(ctx, A, n_planes);
+    return cols_dispatch<false>(ctx, A, n_planes);
+}
+
+// The y pass of this rank's planes with the transpose fused in: results go straight to the
+// [dims][ny][nc] blocks of their owner ranks (peer[r], set by genpk_slab_set_peers).
+int fft_cols_y_scatter(genpk_ctx *ctx, double *spec, int n_planes)
+{
+    const SlabGeom &g = ctx->g;
+    const int ny = g.dims / g.nranks;
+    if (!ctx->peers_set || g.nranks > GENPK_MAX_PEERS || (ny & (ny - 1)) != 0) {
+        set_error("scatter y pass: peers not set, more than %d ranks, or dims/nranks not a power of two", GENPK_MAX_PEERS);
+        return 1;
     }
-    set_error("column FFT: unsupported grid side %d", ctx->g.dims);
-    return 1;
+    if (int rc = ensure_twiddles(ctx)) return rc;
+    FftColsArgs A = {};
+    A.spec = reinterpret_cast<double2 *>(spec);
+    A.tw = reinterpret_cast<const double2 *>(ctx->d_twiddle);
+    A.nc = g.nc;
+    A.plane_stride = (long long)g.dims * g.nc;
+    for (int r = 0; r < g.nranks; r++)
+        A.peer[r] = reinterpret_cast<double2 *>(ctx->peer_recv[r]);
+    A.ny_shift = 0;
+    while ((1 << A.ny_shift) < ny) A.ny_shift++;
+    A.x0 = g.x0;
+    return cols_dispatch<true>(ctx, A, n_planes);
 }
 
 }  // namespace genpk

@@ -44,6 +44,8 @@ class CudaStages:
         self._spec = [None, None]
         self._send = None
         self._sums = None
+        self.scatter_ready = False     # every rank's transposed block is known: the y pass stores into them
+        self._recv = None
 
     def close(self):
         self.ctx.close()
@@ -108,6 +110,37 @@ class CudaStages:
         self.ctx.slab_power_partial(spec_a.data_ptr(), spec_b.data_ptr() if spec_b is not None else 0, nrbins,
                                     self._sums.data_ptr())
         return self._sums
+
+    # -- transpose fused into the y pass ----------------------------------------------------
+    def recv_block(self) -> torch.Tensor:
+        if self._recv is None:
+            ptr, nbytes = self.ctx.slab_recv_buffer()
+            self._recv = torch.as_tensor(_DevMem(ptr, nbytes), device=self.device)
+        return self._recv
+
+    def enable_scatter(self, group=None) -> bool:
+        """Exchange the CUDA IPC handles of every rank's transposed block (one process per GPU,
+        same node) so that genpk_slab_fft_yz_scatter can store into them over NVLink."""
+        if self.scatter_ready:
+            return True
+        ok = torch.tensor([1 if self.ctx.slab_scatter_supported() else 0], dtype=torch.int32, device=self.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            return False
+        self.recv_block()
+        mine = torch.frombuffer(bytearray(self.ctx.ipc_export()), dtype=torch.uint8).to(self.device)
+        handles = [torch.empty_like(mine) for _ in range(self.nranks)]
+        dist.all_gather(handles, mine, group=group)
+        for r in range(self.nranks):
+            if r == self.rank:
+                self.ctx.slab_set_peer(r, None, self.ctx.slab_recv_buffer()[0])
+            else:
+                self.ctx.slab_set_peer(r, bytes(handles[r].cpu().numpy().tobytes()))
+        self.scatter_ready = True
+        return True
+
+    def fft_yz_scatter(self, which=0):
+        self.ctx.slab_fft_yz_scatter(which)
 
     def fused_xpass(self, nrbins: int) -> bool:
         return self.ctx.fused_xpass_supported(nrbins)
@@ -244,6 +277,12 @@ class SlabPipeline:
             self.stages.fft_x(spec)
         return spec
 
+    def _barrier(self, device):
+        """Stream-ordered rendezvous of all ranks (a 1-element all-reduce)."""
+        if getattr(self, "_flag", None) is None or self._flag.device != device:
+            self._flag = torch.zeros(1, dtype=torch.int32, device=device)
+        dist.all_reduce(self._flag, group=self.group)
+
     def _reduce_finalize(self, sums, nrbins, total_mass, total_mass2):
         with self._Timed(self, "allreduce_d2h"):
             if self.P > 1:
@@ -260,6 +299,19 @@ class SlabPipeline:
         nrbins = self.dims if nrbins is None else nrbins
         self.deposit(pos, mass, cmass, boxsize, 0, True, routed)
         fused = getattr(self.stages, "fused_xpass", None)
+        if fused is not None and fused(nrbins) and getattr(self.stages, "scatter_ready", False) and self.P > 1:
+            # the y pass stores its results straight into their owner's transposed block (peer
+            # stores over NVLink): no pack, no all-to-all.  Barriers: nobody still reads its block
+            # (the previous call's x pass) / every rank has finished storing.
+            with self._Timed(self, "ghost_exchange"):
+                self.exchange_ghost(0)
+            with self._Timed(self, "barriers"):
+                self._barrier(pos.device)
+            self.stages.fft_yz_scatter(0)
+            with self._Timed(self, "barriers"):
+                self._barrier(pos.device)
+            sums = self.stages.fftx_power_partial(self.stages.recv_block(), nrbins)
+            return self._reduce_finalize(sums, nrbins, total_mass, total_mass)
         if fused is not None and fused(nrbins):
             # the x transform and the binning of the transposed block share one kernel
             spec = self.spectrum(0, x_pass=False)

@@ -142,3 +142,64 @@ def test_own_y_pass_vs_cufft_2d(dims, P):
     a, b = outs
     scale = float(b.abs().max())
     assert float((a - b).abs().max()) <= 1e-12 * scale
+
+
+@pytest.mark.parametrize("dims,P", [(256, 2), (256, 8), (512, 4), (1024, 2)])
+def test_scatter_y_pass_emulated_on_one_gpu(dims, P):
+    """genpk_slab_fft_yz_scatter: the y pass stores its results straight into the owner ranks'
+    transposed blocks (peer pointers; here P slab contexts in one process on one GPU), then the
+    fused x pass bins each block.  Against fft_yz + pack + hand-made all-to-all + cuFFT x pass +
+    bin_power_kernel on the same random slabs."""
+    import torch
+    from genpk_b200.distributed import CudaStages, _DevMem
+    dev = torch.device("cuda", 0)
+    nrbins = dims
+    st = [CudaStages(dims, P, r, dev) for r in range(P)]
+    try:
+        grids = []
+        for r in range(P):
+            nd = st[r].ctx.grid_doubles()
+            g = torch.as_tensor(_DevMem(st[r].ctx.grid_ptr(), nd * 8), device=dev)
+            gen = torch.Generator(device=dev).manual_seed(1000 * dims + r)
+            g.copy_(torch.randn(nd, dtype=torch.float64, device=dev, generator=gen))
+            grids.append((g, g.clone()))
+        # (a) library path
+        nx = ny = dims // P
+        nc = dims // 2 + 1
+        blk = nx * ny * nc * 2
+        sends = []
+        for r in range(P):
+            st[r].ctx.set_option(api.OPT_OWN_YPASS, 0)
+            st[r].fft_yz()
+            sends.append(st[r].pack().clone())
+        want = torch.zeros(3 * nrbins, dtype=torch.float64, device=dev)
+        for s in range(P):
+            spec = st[s].spectrum_buffer()
+            for r in range(P):
+                spec[r * blk:(r + 1) * blk] = sends[r][s * blk:(s + 1) * blk]
+            st[s].fft_x(spec)
+            want += st[s].power_partial(spec, None, nrbins)
+        torch.cuda.synchronize()
+        # (b) scatter path on the same input
+        ptrs = [st[r].ctx.slab_recv_buffer()[0] for r in range(P)]
+        for r in range(P):
+            grids[r][0].copy_(grids[r][1])
+            st[r].ctx.set_option(api.OPT_OWN_YPASS, 1)
+            assert st[r].ctx.slab_scatter_supported()
+            for s in range(P):
+                st[r].ctx.slab_set_peer(s, None, ptrs[s])
+        for r in range(P):
+            st[r].fft_yz_scatter()
+        torch.cuda.synchronize()                                   # "barrier": every rank has stored
+        got = torch.zeros(3 * nrbins, dtype=torch.float64, device=dev)
+        for s in range(P):
+            got += st[s].fftx_power_partial(st[s].recv_block(), nrbins)
+        torch.cuda.synchronize()
+        w, g = want.cpu().numpy().reshape(3, nrbins), got.cpu().numpy().reshape(3, nrbins)
+        np.testing.assert_array_equal(g[1:], w[1:])
+        assert int(w[2].sum()) == dims ** 3 - 1
+        nz = w[2] > 0
+        np.testing.assert_allclose(g[0][nz], w[0][nz], rtol=1e-9, atol=0)
+    finally:
+        for s in st:
+            s.close()

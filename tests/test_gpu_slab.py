@@ -114,7 +114,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _nccl_worker(rank, world, port, dims, n, box, out_dir):
+def _nccl_worker(rank, world, port, dims, n, box, out_dir, scatter=False):
     import torch
     import torch.distributed as dist
     sys.path.insert(0, ROOT)
@@ -130,6 +130,10 @@ def _nccl_worker(rank, world, port, dims, n, box, out_dir):
         dev = torch.device("cuda", rank)
         stages = CudaStages(dims, world, rank, dev)
         pipe = SlabPipeline(dims, stages)
+        if scatter:
+            assert stages.enable_scatter(), "CUDA IPC exchange of the transposed blocks failed"
+            pipe.pk(torch.from_numpy(pos[lo:hi].reshape(-1).copy()).to(dev),        # twice: blocks are reused
+                    torch.from_numpy(masses[lo:hi].copy()).to(dev), 0.0, box, tm, dims)
         p, c, k = pipe.pk(torch.from_numpy(pos[lo:hi].reshape(-1).copy()).to(dev),
                           torch.from_numpy(masses[lo:hi].copy()).to(dev), 0.0, box, tm, dims)
         stages.check()
@@ -148,6 +152,26 @@ def test_slab_pipeline_over_nccl(tmp_path, port):
         pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
     dims, n, box = 128, 400000, 100.0
     mp.spawn(_nccl_worker, args=(world, _free_port(), dims, n, box, str(tmp_path)), nprocs=world, join=True)
+    got = np.load(tmp_path / "out.npz")
+    pos, masses = _particles(n, box, 99, True)
+    tm = float(masses.astype(np.float64).sum())
+    _, pr, cr, kr = port.pk(box, dims, pos, masses, 0.0, tm, dims)
+    assert np.array_equal(got["c"], cr)
+    nz = cr > 0
+    np.testing.assert_allclose(got["p"][nz], pr[nz], rtol=1e-5)
+    np.testing.assert_allclose(got["k"][nz], kr[nz], rtol=1e-5)
+
+
+def test_slab_pipeline_over_nccl_with_peer_stores(tmp_path, port):
+    """One process per GPU: the y pass of every rank stores into the other ranks' transposed
+    blocks through CUDA IPC mappings (NVLink), then the fused x pass; against the CPU oracle."""
+    import torch
+    import torch.multiprocessing as mp
+    world = min(torch.cuda.device_count(), 8)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
+    dims, n, box = 256, 400000, 100.0
+    mp.spawn(_nccl_worker, args=(world, _free_port(), dims, n, box, str(tmp_path), True), nprocs=world, join=True)
     got = np.load(tmp_path / "out.npz")
     pos, masses = _particles(n, box, 99, True)
     tm = float(masses.astype(np.float64).sum())
