@@ -10,7 +10,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgenpk_cuda.so")
+# GENPK_LIB: another build of the same library (kernel-variant measurements), never a fallback
+LIB_PATH = os.environ.get("GENPK_LIB") or os.path.join(_HERE, "libgenpk_cuda.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 c_f32p = C.c_void_p
