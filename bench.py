@@ -67,6 +67,8 @@ def parse_args():
     ap.add_argument("--fft-yz-batch", type=int, default=-1, help="x planes per 2-D cuFFT call (0 = all, -1 = library default)")
     ap.add_argument("--no-own-ypass", action="store_true", help="cuFFT's 2-D (y,z) plan instead of cuFFT z + own y pass")
     ap.add_argument("--no-scatter", action="store_true", help="multi-GPU: pack + all-to-all instead of the y pass storing into peers")
+    ap.add_argument("--check-mass", action="store_true",
+                    help="before timing: one deposit (+ ghost exchange), the grid must sum to the particle count")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
@@ -85,6 +87,16 @@ def measured_peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+def ncu_traffic(workload):
+    """DRAM bytes per launch from the committed ncu --set full captures (tools/ncu_traffic.py), or {}."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        d = json.load(open(p))
+        return d["kernels"] if d.get("workload") == workload else {}
+    except Exception:
+        return {}
 
 
 def algorithmic_bytes(n_particles, dims, nranks=1):
@@ -352,6 +364,30 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    if args.check_mass:
+        from genpk_b200.distributed import _DevMem
+        if world == 1:
+            ctx.grid_zero()
+            ctx.deposit_dev(dpos.data_ptr(), count, 0, 1.0, BOX)
+        else:
+            pipe.deposit(dpos, None, 1.0, BOX, 0, True, False)
+            pipe.exchange_ghost(0)
+        fd = 2 * (dims // 2 + 1)
+        owned = (dims // world) * dims * fd
+        off = ctx.owned_offset()
+        g = torch.as_tensor(_DevMem(ctx.grid_ptr() + 8 * off, 8 * owned), device=dev)
+        if args.fixed_point:
+            tot = g.view(torch.int64).view(-1, fd).sum(dim=1).to(torch.float64).sum() / 2.0 ** 40
+        else:
+            tot = g.view(-1, fd).sum(dim=1).sum()
+        tot = tot.reshape(1).clone()
+        if world > 1:
+            dist.all_reduce(tot)
+        rel = abs(float(tot.item()) / n_total - 1.0)
+        assert rel < 1e-9, f"deposited mass {float(tot.item())!r} != {n_total} particles (rel {rel:.3e})"
+        if rank == 0:
+            print(f"mass check: grid sums to {float(tot.item()):.6f} for {n_total} particles (rel {rel:.2e})", file=sys.stderr, flush=True)
+
     # ---- device-resident timing ------------------------------------------------------------
     for _ in range(max(args.warmup, 3)):
         out = step_device()
@@ -422,6 +458,15 @@ def run_ours(args):
         ach = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
         roof[name] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                       "traffic": None, "ms": ms, "algorithmic_bytes": nbytes}
+    # DRAM traffic of the stage's kernels from the committed ncu capture of this workload (single GPU only)
+    tr = ncu_traffic(args.workload) if world == 1 else {}
+    if "deposit_march_kernel" in tr and ctx.last_order().get("lattice"):
+        k = tr["deposit_march_kernel"]
+        roof["deposit"]["traffic"] = k["dram_read_bytes"] + k["dram_write_bytes"] + 8 * dims * dims * (2 * (dims // 2 + 1))
+        roof["deposit"]["traffic_note"] = "deposit_march_kernel (ncu) + the memset's writes (8 B/cell)"
+    bk = "fftx_power_kernel" if fused else "bin_power_kernel"
+    if bk in tr:
+        roof["binning"]["traffic"] = tr[bk]["dram_read_bytes"] + tr[bk]["dram_write_bytes"]
     dom = "deposit" if stage_ms["deposit_with_zero"] >= stage_ms["binning"] else "binning"
     roofline = dict(roof[dom])
     roofline["kernel"] = {"deposit": "deposit stage (grid zero + order probe + deposit_march_kernel | brick sort + "

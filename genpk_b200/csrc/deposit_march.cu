@@ -25,16 +25,16 @@
 // further) just flushes what it carried with its own red.add.  On a regular lattice
 // one red.add per particle leaves the SM, 32 lanes to 32 consecutive doubles.
 //
-// Particle rows are read straight into registers (three 4-byte streaming loads per lane
-// cover the row's 384 contiguous bytes; the second and third hit L1) three rows ahead of
-// their use, so no instruction is spent on staging buffers, waits or warp barriers.
+// Particle rows are staged through shared memory with cp.async (4 rows in flight per
+// warp, evict-first in L2) so the loads are fully coalesced and asynchronous.
 #include "deposit.cuh"
 
 namespace genpk {
 
 constexpr int MARCH_THREADS = 256;
 constexpr int MARCH_WARPS = MARCH_THREADS / 32;
-constexpr int MARCH_AHEAD = 3;           // particle rows in flight per warp (registers)
+constexpr int MARCH_STAGES = 4;          // particle rows in flight per warp
+constexpr int MARCH_ROW_FLOATS = 128;    // 96 position floats + 32 masses per staged row
 #ifndef GENPK_MARCH_MINB
 #define GENPK_MARCH_MINB 3               // resident CTAs per SM the register allocation must allow (3 -> 80 registers)
 #endif
@@ -49,6 +49,15 @@ struct MarchGeom {
     long long tasks_per_layer;   // nzs * yb_per_band
     long long n_tasks;           // nbands * nxb * tasks_per_layer
 };
+
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc, unsigned long long policy)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 4, %2;\n" ::"r"(d), "l"(gsrc), "l"(policy)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 // Out-of-box cell index -> [0, dims) (fieldize.cpp:70-75); kept out of line, it is rare.
 __device__ __noinline__ int wrap_cell(int f, int dims)
@@ -92,9 +101,13 @@ __global__ void __launch_bounds__(MARCH_THREADS, GENPK_MARCH_MINB) deposit_march
     constexpr key_t INVALID = ~(key_t)0;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // x-carry slots [ry+1][threads] (value, key)
+    // x-carry slots [ry+1][threads] (value, key), then the staging rows of each warp
     acc_t *const xc_val0 = reinterpret_cast<acc_t *>(smem_raw) + tid;
     key_t *const xc_key0 = reinterpret_cast<key_t *>(reinterpret_cast<acc_t *>(smem_raw) + (size_t)(g.ry + 1) * MARCH_THREADS) + tid;
+    float *const stage = reinterpret_cast<float *>(reinterpret_cast<key_t *>(reinterpret_cast<acc_t *>(smem_raw) +
+                                                                             (size_t)(g.ry + 1) * MARCH_THREADS) +
+                                                   (size_t)(g.ry + 1) * MARCH_THREADS) +
+                         (size_t)warp * MARCH_STAGES * MARCH_ROW_FLOATS;
 
     // ---- which part of the lattice this warp marches over ----
     const long long task = (long long)blockIdx.x * MARCH_WARPS + warp;
@@ -127,33 +140,47 @@ __global__ void __launch_bounds__(MARCH_THREADS, GENPK_MARCH_MINB) deposit_march
     const int dims = a.dims;
     const double units = a.units;
 
+    unsigned long long policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(policy));
+
     for (int s = 0; s <= ry_eff; s++)
         xc_key0[s * MARCH_THREADS] = INVALID;
 
-    // ---- register pipeline over the (plane, row) steps: MARCH_AHEAD rows in flight ----
-    // Lanes past the end of the arrays (the last row's 32-lane window, ragged tails) read the
-    // last particle instead; they are not live, so what they read is never used.
-    long long pl = p_first + lane;           // load cursor: this lane's particle
+    // ---- cp.async pipeline over the (plane, row) steps ----
+    long long pl = p_first;                  // load cursor: particle of lane 0
+    const float *lsrc = a.pos + 3 * p_first + lane;
+    const float *lmass = MASS ? a.mass + p_first + lane : nullptr;
     int l_r = 0;
-    const long long last = a.n - 1;
-    float lx[MARCH_AHEAD], ly[MARCH_AHEAD], lz[MARCH_AHEAD], lm[MARCH_AHEAD];
-    auto issue_load = [&](int q, int slot) {
+    // FULL still has to stop the last row's 32-lane window at the end of the arrays
+    const bool window_safe = FULL && ((x_end - 1) * g.n1 + y_end - 1) * g.n0 + 31LL * zs + 32 <= a.n;
+    auto issue_load = [&](int q) {
         if (q < nsteps) {
-            const long long p = pl < last ? pl : last;
-            const float *src = a.pos + 3 * p;
-            lx[slot] = __ldcs(src);
-            ly[slot] = __ldcs(src + 1);
-            lz[slot] = __ldcs(src + 2);
-            if (MASS)
-                lm[slot] = __ldcs(a.mass + p);
+            float *dst = stage + (q & (MARCH_STAGES - 1)) * MARCH_ROW_FLOATS + lane;
+            if (window_safe || pl + 32 <= a.n) {
+                cp_async4(dst, lsrc, policy);
+                cp_async4(dst + 32, lsrc + 32, policy);
+                cp_async4(dst + 64, lsrc + 64, policy);
+                if (MASS)
+                    cp_async4(dst + 96, lmass, policy);
+            } else {
+                const long long fmax = 3 * a.n, f = 3 * pl + lane;
+                if (f < fmax) cp_async4(dst, lsrc, policy);
+                if (f + 32 < fmax) cp_async4(dst + 32, lsrc + 32, policy);
+                if (f + 64 < fmax) cp_async4(dst + 64, lsrc + 64, policy);
+                if (MASS && pl + lane < a.n)
+                    cp_async4(dst + 96, lmass, policy);
+            }
             const long long inc = (++l_r == ry_eff) ? plane_inc : g.n0;
             if (l_r == ry_eff) l_r = 0;
             pl += inc;
+            lsrc += 3 * inc;
+            if (MASS) lmass += inc;
         }
+        cp_async_commit();
     };
 #pragma unroll
-    for (int q = 0; q < MARCH_AHEAD; q++)
-        issue_load(q, q);
+    for (int q = 0; q < MARCH_STAGES - 1; q++)
+        issue_load(q);
 
     // y-carry: the two high-y sums of the previous row
     bool yc_has = false;
@@ -182,22 +209,22 @@ __global__ void __launch_bounds__(MARCH_THREADS, GENPK_MARCH_MINB) deposit_march
     long long pc = p_first + lane;           // this lane's particle at the current step (only read when !FULL)
     acc_t *xv_p = xc_val0;
     key_t *xk_p = xc_key0;
+    const float *my_stage = stage + 3 * lane;
     const bool emit_rule_full = pair_in_row ? lane < 31 : owner_lane;
-    for (int q0 = 0; q0 < nsteps; q0 += MARCH_AHEAD) {
-#pragma unroll
-      for (int u = 0; u < MARCH_AHEAD; u++) {
-        const int q = q0 + u;
-        if (q >= nsteps)
-            break;
+    for (int q = 0; q < nsteps; q++) {
+        issue_load(q + MARCH_STAGES - 1);
+        cp_async_wait<MARCH_STAGES - 1>();
+        __syncwarp();
+        const int slot = (q & (MARCH_STAGES - 1)) * MARCH_ROW_FLOATS;
         const bool live = lane_in_row && (FULL || pc < a.n);
-        float px = lx[u], py = ly[u], pz = lz[u];
+        float px = my_stage[slot], py = my_stage[slot + 1], pz = my_stage[slot + 2];
         double m = a.cmass;
         if (MASS)
-            m = (double)lm[u];                                               // fieldize.cpp:63
-        issue_load(q + MARCH_AHEAD, u);                                      // the slot just consumed
+            m = (double)stage[slot + 96 + lane];                             // fieldize.cpp:63
+        __syncwarp();                                                        // slot may be refilled from here on
         bool ok = live && fabsf(px) < pos_limit && fabsf(py) < pos_limit && fabsf(pz) < pos_limit;
         if (!ok)
-            px = py = pz = 0.f;                                              // not this lane's particle / non-finite
+            px = py = pz = 0.f;                                              // stale / non-finite staging data
         int fx, fy, fz;
         double tx, dx, ty, dy, tz, dz;
         axis_fast(px, units, fx, tx, dx);
@@ -290,7 +317,6 @@ __global__ void __launch_bounds__(MARCH_THREADS, GENPK_MARCH_MINB) deposit_march
         } else {
             if (!FULL) pc += g.n0;
         }
-    }
     }
     // ---- what the last plane left behind ----
     for (int s = 0; s <= ry_eff; s++) {
@@ -488,7 +514,8 @@ template <bool FIXED, typename key_t, bool FULL, bool MASS, bool SLAB>
 static int launch_march_t(genpk_ctx *ctx, const DepositArgs &a, const MarchGeom &g)
 {
     auto kern = deposit_march_kernel<FIXED, key_t, FULL, MASS, SLAB>;
-    const size_t smem = (size_t)(g.ry + 1) * MARCH_THREADS * (sizeof(typename Acc<FIXED>::type) + sizeof(key_t));
+    const size_t smem = (size_t)(g.ry + 1) * MARCH_THREADS * (sizeof(typename Acc<FIXED>::type) + sizeof(key_t)) +
+                        (size_t)MARCH_WARPS * MARCH_STAGES * MARCH_ROW_FLOATS * sizeof(float);
     GENPK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long blocks = (g.n_tasks + MARCH_WARPS - 1) / MARCH_WARPS;
     if (blocks > 0x7fffffffLL) {
