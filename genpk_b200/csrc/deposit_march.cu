@@ -92,8 +92,7 @@ __device__ __forceinline__ void add_if(long long &lo, long long from, int take)
 
 // FULL: every lattice site the launch touches holds a particle (n == n0*n1*n2), so no
 // per-step bound checks on the particle index.  MASS: per-particle masses.
-// SLAB: the grid is an x-slab with ghost planes (multi-GPU contexts).
-template <bool FIXED, typename key_t, bool FULL, bool MASS, bool SLAB>
+template <bool FIXED, typename key_t, bool FULL, bool MASS>
 __global__ void __launch_bounds__(MARCH_THREADS, GENPK_MARCH_MINB) deposit_march_kernel(const __grid_constant__ DepositArgs a,
                                                                          const __grid_constant__ MarchGeom g)
 {
@@ -237,7 +236,7 @@ __global__ void __launch_bounds__(MARCH_THREADS, GENPK_MARCH_MINB) deposit_march
         }
         int xl = fx;
         int xstep = 1;                                                       // planes from the low-x to the high-x corner
-        if (SLAB) {                                                          // slab: the +1 neighbour may be a ghost plane
+        if (a.slab) {                                                        // slab: the +1 neighbour may be a ghost plane
             xl = slab_plane(fx, a.x0, a.ghost_lo, dims);
             ok = ok && xl >= 0 && xl <= a.xl_max;
         } else if (fx + 1 == dims) {
@@ -510,10 +509,10 @@ int probe_order(genpk_ctx *ctx, const float *pos, int64_t n, double units, Order
     return 0;
 }
 
-template <bool FIXED, typename key_t, bool FULL, bool MASS, bool SLAB>
+template <bool FIXED, typename key_t, bool FULL, bool MASS>
 static int launch_march_t(genpk_ctx *ctx, const DepositArgs &a, const MarchGeom &g)
 {
-    auto kern = deposit_march_kernel<FIXED, key_t, FULL, MASS, SLAB>;
+    auto kern = deposit_march_kernel<FIXED, key_t, FULL, MASS>;
     const size_t smem = (size_t)(g.ry + 1) * MARCH_THREADS * (sizeof(typename Acc<FIXED>::type) + sizeof(key_t)) +
                         (size_t)MARCH_WARPS * MARCH_STAGES * MARCH_ROW_FLOATS * sizeof(float);
     GENPK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -528,21 +527,13 @@ static int launch_march_t(genpk_ctx *ctx, const DepositArgs &a, const MarchGeom 
     return 0;
 }
 
-template <bool FIXED, typename key_t, bool SLAB>
-static int launch_march_s(genpk_ctx *ctx, const DepositArgs &a, const MarchGeom &g)
-{
-    const bool full = g.n0 * g.n1 * g.n2 == a.n;
-    if (a.mass)
-        return full ? launch_march_t<FIXED, key_t, true, true, SLAB>(ctx, a, g)
-                    : launch_march_t<FIXED, key_t, false, true, SLAB>(ctx, a, g);
-    return full ? launch_march_t<FIXED, key_t, true, false, SLAB>(ctx, a, g)
-                : launch_march_t<FIXED, key_t, false, false, SLAB>(ctx, a, g);
-}
-
 template <bool FIXED, typename key_t>
 static int launch_march_k(genpk_ctx *ctx, const DepositArgs &a, const MarchGeom &g)
 {
-    return a.slab ? launch_march_s<FIXED, key_t, true>(ctx, a, g) : launch_march_s<FIXED, key_t, false>(ctx, a, g);
+    const bool full = g.n0 * g.n1 * g.n2 == a.n;
+    if (a.mass)
+        return full ? launch_march_t<FIXED, key_t, true, true>(ctx, a, g) : launch_march_t<FIXED, key_t, false, true>(ctx, a, g);
+    return full ? launch_march_t<FIXED, key_t, true, false>(ctx, a, g) : launch_march_t<FIXED, key_t, false, false>(ctx, a, g);
 }
 
 // n0: particles per lattice row; n1: rows per plane (0 = unknown: the whole array is one plane).
