@@ -584,6 +584,10 @@ int genpk_slab_pack(genpk_ctx *ctx, int which, void *send_dev)
 int genpk_slab_fft_x(genpk_ctx *ctx, void *recv_dev)
 {
     if (!ctx || !recv_dev) { set_error("genpk_slab_fft_x: bad arguments"); return 1; }
+    if (recv_dev == ctx->d_recv) {
+        set_error("genpk_slab_fft_x: the library-owned transposed block has padded rows; use genpk_slab_fftx_power_partial");
+        return 1;
+    }
     return fft_x(ctx, recv_dev);
 }
 
@@ -609,7 +613,9 @@ int genpk_slab_fftx_power_partial(genpk_ctx *ctx, const void *spec_yz_dev, int n
     if (!ctx || !spec_yz_dev || !sums_dev || nrbins < 1) { set_error("genpk_slab_fftx_power_partial: bad arguments"); return 1; }
     const int ny = ctx->g.dims / ctx->g.nranks;
     stage_begin(ctx, ST_POWER);
-    if (int rc = fftx_power_raw(ctx, (const double *)spec_yz_dev, ny, ctx->g.rank * ny, nrbins, sums_dev)) return rc;
+    // the library-owned transposed block (filled by genpk_slab_fft_yz_scatter) has padded rows
+    const int pitch = spec_yz_dev == ctx->d_recv ? recv_row_pitch(ctx) : 0;
+    if (int rc = fftx_power_raw(ctx, (const double *)spec_yz_dev, ny, ctx->g.rank * ny, nrbins, sums_dev, pitch)) return rc;
     stage_end(ctx, ST_POWER);
     return 0;
 }
@@ -617,7 +623,7 @@ int genpk_slab_fftx_power_partial(genpk_ctx *ctx, const void *spec_yz_dev, int n
 void *genpk_slab_recv_buffer(genpk_ctx *ctx, size_t *bytes)
 {
     if (!ctx) { set_error("genpk_slab_recv_buffer: null context"); return nullptr; }
-    const size_t n = genpk_slab_spectrum_bytes(ctx);
+    const size_t n = (size_t)ctx->g.dims * (ctx->g.dims / ctx->g.nranks) * recv_row_pitch(ctx) * 2 * sizeof(double);
     if (!ctx->d_recv && cudaMalloc(&ctx->d_recv, n) != cudaSuccess) {
         set_error("genpk_slab_recv_buffer: cudaMalloc(%zu) failed: %s", n, cudaGetErrorString(cudaGetLastError()));
         return nullptr;

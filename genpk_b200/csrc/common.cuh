@@ -157,7 +157,8 @@ int power_raw(genpk_ctx *ctx, const double *spec_a, const double *spec_b, int n_
 int power_seed_sums(genpk_ctx *ctx, int n_outer, int outer0, int n_mid, int mid0, int nrbins, double *sums_dev);
 // fftx_power.cu
 bool fftx_supported(const genpk_ctx *ctx, int nrbins);
-int fftx_power_raw(genpk_ctx *ctx, const double *spec_yz, int n_mid, int mid0, int nrbins, double *sums_dev);
+int fftx_power_raw(genpk_ctx *ctx, const double *spec_yz, int n_mid, int mid0, int nrbins, double *sums_dev, int row_pitch = 0);
+int recv_row_pitch(const genpk_ctx *ctx);
 bool fft_cols_supported(const genpk_ctx *ctx);
 int fft_cols_y(genpk_ctx *ctx, double *spec, int n_planes);
 int fft_cols_y_scatter(genpk_ctx *ctx, double *spec, int n_planes);

@@ -32,7 +32,8 @@ struct FftxArgs {
     const double2 *spec;      // [dims][n_mid][nc]
     const double2 *tw;        // exp(-2 pi i t / dims), t < dims
     int dims, nc, n_mid, mid0;
-    long long x_stride;       // modes between consecutive x: n_mid * nc
+    int row_pitch;            // modes between consecutive mid rows (nc, or the padded pitch of a transposed block)
+    long long x_stride;       // modes between consecutive x: n_mid * row_pitch
     int groups;               // column groups per (x, mid) row: ceil(nc / C)
     long long n_tiles;        // n_mid * groups
     int nrbins;
@@ -135,7 +136,7 @@ __global__ void __launch_bounds__(PL::THREADS, PL::TILE == 4096 ? 2 : 1) fftx_po
             const long long m = tile / A.groups;
             const int kz = g * C + c;
             if (kz < A.nc) {
-                const double2 *src = A.spec + (size_t)m * A.nc + kz;
+                const double2 *src = A.spec + (size_t)m * A.row_pitch + kz;
 #pragma unroll
                 for (int i = 0; i < EPT; i++) {
                     const int n = PL::load_n(t, i);
@@ -209,6 +210,7 @@ struct FftColsArgs {
     // over NVLink (or a local store for the rank's own rows) instead of an in-place store.
     double2 *peer[GENPK_MAX_PEERS];
     int ny_shift;             // log2(ny)
+    int dst_pitch;            // modes between consecutive rows of a transposed block
     int x0;                   // first global x plane of this rank
 };
 
@@ -273,11 +275,11 @@ __global__ void __launch_bounds__(PL::THREADS, PL::TILE == 4096 ? 2 : 1) fft_col
         if (valid) {
             if (SCATTER) {
                 const int ny = 1 << A.ny_shift;
-                const size_t plane_off = (size_t)(A.x0 + o) * ny * A.nc + kz;
+                const size_t plane_off = (size_t)(A.x0 + o) * ny * A.dst_pitch + kz;
 #pragma unroll
                 for (int i = 0; i < EPT; i++) {
                     const int ky = kb + PL::out_k_part(i);
-                    A.peer[ky >> A.ny_shift][plane_off + (size_t)(ky & (ny - 1)) * A.nc] = v[i];
+                    A.peer[ky >> A.ny_shift][plane_off + (size_t)(ky & (ny - 1)) * A.dst_pitch] = v[i];
                 }
             } else {
                 double2 *dst = A.spec + (size_t)o * A.plane_stride + kz;
@@ -324,6 +326,11 @@ bool fftx_supported(const genpk_ctx *ctx, int nrbins)
         return false;
     return nrbins >= 1 && fftx_smem_bytes(ctx, nrbins) <= (size_t)ctx->smem_optin;
 }
+
+// Rows of the library-owned transposed block start on 128-byte boundaries (nc = dims/2+1 is odd:
+// with the natural pitch every other row would straddle sectors, and 128-byte peer stores
+// would split into two NVLink packets).
+int recv_row_pitch(const genpk_ctx *ctx) { return (ctx->g.nc + 7) / 8 * 8; }
 
 static int ensure_twiddles(genpk_ctx *ctx)
 {
@@ -375,7 +382,7 @@ template <class PL> static int launch_fftx(genpk_ctx *ctx, const FftxArgs &A, si
 // P sums of the block [dims][n_mid][nc] of a (y,z)-transformed spectrum whose first mid
 // row is global ky index mid0, with the x transform done on the fly.  sums_dev: 3*nrbins
 // doubles (P from this pass, K and N from the cached geometry pass).
-int fftx_power_raw(genpk_ctx *ctx, const double *spec_yz, int n_mid, int mid0, int nrbins, double *sums_dev)
+int fftx_power_raw(genpk_ctx *ctx, const double *spec_yz, int n_mid, int mid0, int nrbins, double *sums_dev, int row_pitch)
 {
     if (!fftx_supported(ctx, nrbins)) {
         set_error("fused x pass: unsupported grid side %d / nrbins %d", ctx->g.dims, nrbins);
@@ -391,7 +398,8 @@ int fftx_power_raw(genpk_ctx *ctx, const double *spec_yz, int n_mid, int mid0, i
     A.nc = ctx->g.nc;
     A.n_mid = n_mid;
     A.mid0 = mid0;
-    A.x_stride = (long long)n_mid * A.nc;
+    A.row_pitch = row_pitch > 0 ? row_pitch : A.nc;
+    A.x_stride = (long long)n_mid * A.row_pitch;
     A.nrbins = nrbins;
     A.iw1d = ctx->d_iw1d;
     A.thresh = ctx->d_thresh;
@@ -496,6 +504,7 @@ int fft_cols_y_scatter(genpk_ctx *ctx, double *spec, int n_planes)
     A.ny_shift = 0;
     while ((1 << A.ny_shift) < ny) A.ny_shift++;
     A.x0 = g.x0;
+    A.dst_pitch = recv_row_pitch(ctx);
     return cols_dispatch<true>(ctx, A, n_planes);
 }
 

@@ -263,14 +263,14 @@ int genpk_slab_power_partial(genpk_ctx *ctx, const void *spec_a_dev, const void 
 int genpk_slab_fftx_power_partial(genpk_ctx *ctx, const void *spec_yz_dev, int nrbins, double *sums_dev);
 
 /* ---- transpose fused into the y pass (peer stores over NVLink) -------------------------
- * Each rank owns one transposed block [dims][ny_local][dims/2+1] (genpk_slab_recv_buffer,
- * allocated by the library so that it can be shared).  Once every rank knows every block's
+ * Each rank owns one transposed block [dims][ny_local][pitch], pitch = dims/2+1 rounded up to 8 modes
+ * so that rows start on 128-byte boundaries (genpk_slab_recv_buffer, allocated by the library so that
+ * it can be shared; only genpk_slab_fft_yz_scatter writes it and genpk_slab_fftx_power_partial reads it).  Once every rank knows every block's
  * address -- genpk_ipc_export / genpk_ipc_open between processes, plain pointers inside one
  * process -- genpk_slab_fft_yz_scatter does the z pass, then the y pass whose results are
  * stored straight into their owner's block: no pack kernel, no all-to-all.  The caller
  * orders the ranks: nobody may still read its block when the scatter starts, and everybody
- * must have finished scattering before genpk_slab_fftx_power_partial / genpk_slab_fft_x
- * read a block (two barriers, e.g. 1-element all-reduces on the stream).
+ * must have finished scattering before genpk_slab_fftx_power_partial reads a block (two barriers, e.g. 1-element all-reduces on the stream).
  * Needs grid side 256/512/1024/2048, dims/nranks a power of two, nranks <= GENPK_MAX_PEERS. */
 #define GENPK_MAX_PEERS 16
 #define GENPK_IPC_HANDLE_BYTES 64
