@@ -130,10 +130,18 @@ __global__ void __launch_bounds__(PL::THREADS, PL::TILE == 4096 ? 2 : 1) fftx_po
     double *const hist = sP + (c & (A.hists - 1));                   // neighbouring kz columns: different histograms
 
     // a thread copies exactly the 16 staging slots it later reads: no barrier guards the staging buffer
-    auto issue = [&](long long tile) {
-        if (tile < A.n_tiles) {
-            const int g = (int)(tile % A.groups);
-            const long long m = tile / A.groups;
+    // tile -> (column group g, mid row m), advanced without divisions: tiles go up by gridDim.x
+    const int step_g = (int)(gridDim.x % (unsigned)A.groups), step_m = (int)(gridDim.x / (unsigned)A.groups);
+    auto advance = [&](int &g, int &m) {
+        g += step_g;
+        m += step_m;
+        if (g >= A.groups) {
+            g -= A.groups;
+            m++;
+        }
+    };
+    auto issue = [&](int g, int m) {
+        if (m < A.n_mid) {
             const int kz = g * C + c;
             if (kz < A.nc) {
                 const double2 *src = A.spec + (size_t)m * A.row_pitch + kz;
@@ -147,11 +155,11 @@ __global__ void __launch_bounds__(PL::THREADS, PL::TILE == 4096 ? 2 : 1) fftx_po
         cp_async_commit_group();
     };
 
-    long long tile = blockIdx.x;
-    issue(tile);
-    for (; tile < A.n_tiles; tile += gridDim.x) {
-        const int g = (int)(tile % A.groups);
-        const int m = (int)(tile / A.groups);
+    int g = (int)(blockIdx.x % (unsigned)A.groups), m = (int)(blockIdx.x / (unsigned)A.groups);
+    int g_next = g, m_next = m;
+    issue(g, m);
+    for (; m < A.n_mid; g = g_next, m = m_next) {
+        advance(g_next, m_next);
         const int kz = g * C + c;
         const bool valid = kz < A.nc;
         int kj = A.mid0 + m;
@@ -163,7 +171,7 @@ __global__ void __launch_bounds__(PL::THREADS, PL::TILE == 4096 ? 2 : 1) fftx_po
         for (int i = 0; i < EPT; i++)
             v[i] = valid ? stage[PL::load_n(t, i) * C + c] : make_double2(0.0, 0.0);
         PL::pass1(v, t, A.tw);
-        issue(tile + gridDim.x);                                     // the registers above are consumed: slots are free
+        issue(g_next, m_next);                                       // the registers above are consumed: slots are free
 
         __syncthreads();                                             // the previous tile's bin walk has left P
         exchange<N, C, false, PL::ONE_UNIT2>(E, v, w, c, [&](int i) { return t + PL::ex1_w_part(i); },
@@ -204,6 +212,7 @@ struct FftColsArgs {
     int nc;
     long long plane_stride;   // modes per plane: N * nc
     int groups;               // column groups per plane: ceil(nc / C)
+    int n_planes;
     long long n_tiles;        // n_planes * groups
     // SCATTER (multi-GPU transpose fused into the pass): row ky of local plane o is written to
     // rank ky / ny, into its [dims][ny][nc] block at plane x0 + o, row ky % ny -- a peer store
@@ -233,10 +242,18 @@ __global__ void __launch_bounds__(PL::THREADS, PL::TILE == 4096 ? 2 : 1) fft_col
     }
     const int kb = PL::out_k_base(t);
 
-    auto issue = [&](long long tile) {
-        if (tile < A.n_tiles) {
-            const int g = (int)(tile % A.groups);
-            const long long o = tile / A.groups;
+    // tile -> (column group g, plane o), advanced without divisions: tiles go up by gridDim.x
+    const int step_g = (int)(gridDim.x % (unsigned)A.groups), step_o = (int)(gridDim.x / (unsigned)A.groups);
+    auto advance = [&](int &g, int &o) {
+        g += step_g;
+        o += step_o;
+        if (g >= A.groups) {
+            g -= A.groups;
+            o++;
+        }
+    };
+    auto issue = [&](int g, int o) {
+        if (o < A.n_planes) {
             const int kz = g * C + c;
             if (kz < A.nc) {
                 const double2 *src = A.spec + (size_t)o * A.plane_stride + kz;
@@ -250,11 +267,11 @@ __global__ void __launch_bounds__(PL::THREADS, PL::TILE == 4096 ? 2 : 1) fft_col
         cp_async_commit_group();
     };
 
-    long long tile = blockIdx.x;
-    issue(tile);
-    for (; tile < A.n_tiles; tile += gridDim.x) {
-        const int g = (int)(tile % A.groups);
-        const long long o = tile / A.groups;
+    int g = (int)(blockIdx.x % (unsigned)A.groups), o = (int)(blockIdx.x / (unsigned)A.groups);
+    int g_next = g, o_next = o;
+    issue(g, o);
+    for (; o < A.n_planes; g = g_next, o = o_next) {
+        advance(g_next, o_next);
         const int kz = g * C + c;
         const bool valid = kz < A.nc;
         cd v[EPT], w[EPT];
@@ -263,7 +280,7 @@ __global__ void __launch_bounds__(PL::THREADS, PL::TILE == 4096 ? 2 : 1) fft_col
         for (int i = 0; i < EPT; i++)
             v[i] = valid ? stage[PL::load_n(t, i) * C + c] : make_double2(0.0, 0.0);
         PL::pass1(v, t, A.tw);
-        issue(tile + gridDim.x);                                     // another tile: never the rows written below
+        issue(g_next, o_next);                                       // another tile: never the rows written below
         __syncthreads();                                             // the previous tile's last exchange read is over
         exchange<N, C, false, PL::ONE_UNIT2>(E, v, w, c, [&](int i) { return t + PL::ex1_w_part(i); },
                        [&](int i) { return b_ex1r + PL::ex1_r_part(i); });
@@ -435,6 +452,7 @@ template <class PL, bool SCATTER> static int launch_cols(genpk_ctx *ctx, FftCols
     auto kern = fft_cols_kernel<PL, SCATTER>;
     const size_t smem = (size_t)PL::TILE * 24;                   // staging tile + half-size exchange buffer
     A.groups = (A.nc + PL::C - 1) / PL::C;
+    A.n_planes = n_planes;
     A.n_tiles = (long long)n_planes * A.groups;
     GENPK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;

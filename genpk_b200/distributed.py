@@ -127,17 +127,28 @@ class CudaStages:
         dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
         if int(ok.item()) == 0:
             return False
-        self.recv_block()
-        mine = torch.frombuffer(bytearray(self.ctx.ipc_export()), dtype=torch.uint8).to(self.device)
+        good = 1
+        try:
+            self.recv_block()
+            mine = torch.frombuffer(bytearray(self.ctx.ipc_export()), dtype=torch.uint8).to(self.device)
+        except Exception:                                   # no IPC export on this platform: every rank falls back
+            good = 0
+            mine = torch.zeros(self.ctx.IPC_HANDLE_BYTES, dtype=torch.uint8, device=self.device)
         handles = [torch.empty_like(mine) for _ in range(self.nranks)]
         dist.all_gather(handles, mine, group=group)
-        for r in range(self.nranks):
-            if r == self.rank:
-                self.ctx.slab_set_peer(r, None, self.ctx.slab_recv_buffer()[0])
-            else:
-                self.ctx.slab_set_peer(r, bytes(handles[r].cpu().numpy().tobytes()))
-        self.scatter_ready = True
-        return True
+        if good:
+            try:
+                for r in range(self.nranks):
+                    if r == self.rank:
+                        self.ctx.slab_set_peer(r, None, self.ctx.slab_recv_buffer()[0])
+                    else:
+                        self.ctx.slab_set_peer(r, bytes(handles[r].cpu().numpy().tobytes()))
+            except Exception:                               # a peer mapping failed (IPC namespace, no peer access)
+                good = 0
+        ok.fill_(good)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)   # all ranks or none: the paths must match
+        self.scatter_ready = bool(int(ok.item()))
+        return self.scatter_ready
 
     def fft_yz_scatter(self, which=0):
         self.ctx.slab_fft_yz_scatter(which)

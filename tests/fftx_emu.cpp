@@ -28,6 +28,15 @@ static int emu_tile(const double *tile_in, const double *twiddle, double *spec_o
             if (PL::ex2_r(t, i) != PL::ex2_r_base(t, (i % PL::R3) & 3) + PL::ex2_r_part(i)) return 13;
             if (PL::out_k(t, i) != PL::out_k_base(t) + PL::out_k_part(i)) return 14;
         }
+    // the kernel exchanges through a half-size buffer, lower half of the index space first: on the
+    // pass-2 side of a plan whose thread owns one radix-R2 unit, all 16 indices of a thread must
+    // share a half (exchange<..., W_UNI / R_UNI> in fftx_power.cu relies on it)
+    if (PL::ONE_UNIT2)
+        for (int t = 0; t < T; t++)
+            for (int i = 1; i < EPT; i++) {
+                if ((PL::ex1_r(t, i) >= N / 2) != (PL::ex1_r(t, 0) >= N / 2)) return 15;
+                if ((PL::ex2_w(t, i) >= N / 2) != (PL::ex2_w(t, 0) >= N / 2)) return 16;
+            }
     // fill + pass 1 + exchange-1 write
     for (int tid = 0; tid < PL::THREADS; tid++) {
         const int c = col(tid), t = thr(tid);

@@ -10,8 +10,15 @@ from oracle.oracle import Oracle, padded_shape
 
 
 class NumpyStages:
-    def __init__(self, dims, nranks, rank, ghost_planes=0):
+    def __init__(self, dims, nranks, rank, ghost_planes=0, fused=False, scatter=False):
+        """fused: offer the x pass + binning as one stage (CudaStages.fftx_power_partial);
+        scatter: also offer the y pass that delivers its rows to their owners (here an
+        all-to-all inside the stage stands in for the peer stores)."""
         self.dims, self.nranks, self.rank = dims, nranks, rank
+        if fused:
+            self.fused_xpass = lambda nrbins: True
+        self.scatter_ready = bool(scatter)
+        self._recv = None
         self.ghost_planes = ghost_planes if nranks > 1 else 0     # > 0: ghosts on both sides (wide slabs)
         self.glo = self.ghost_planes
         self.ghi = (self.ghost_planes or 1) if nranks > 1 else 1
@@ -108,6 +115,25 @@ class NumpyStages:
             sums[nrbins: 2 * nrbins] = k * c
             sums[2 * nrbins:] = c
         return torch.from_numpy(sums)
+
+    # -- the fused stages of CudaStages --------------------------------------------------
+    def fftx_power_partial(self, spec_yz, nrbins):
+        spec = spec_yz.clone()
+        self.fft_x(spec)
+        return self.power_partial(spec, None, nrbins)
+
+    def fft_yz_scatter(self, which=0):
+        import torch.distributed as dist
+        self.fft_yz(which)
+        send = self.pack(which)
+        self._recv = self.spectrum_buffer(which)
+        if self.nranks == 1:
+            self._recv.copy_(send)
+        else:
+            dist.all_to_all_single(self._recv, send)
+
+    def recv_block(self):
+        return self._recv
 
     def check(self):
         pass

@@ -75,7 +75,7 @@ def test_wide_ghost_slabs_skip_the_particle_exchange(tmp_path, port, world, dims
     np.testing.assert_allclose(got["p"][nz], pr[nz], rtol=1e-9)
 
 
-def _worker(rank, world, port, dims, n, box, var_mass, out_dir):
+def _worker(rank, world, port, dims, n, box, var_mass, out_dir, fused=False, scatter=False):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -86,7 +86,7 @@ def _worker(rank, world, port, dims, n, box, var_mass, out_dir):
         pos, masses = _particles(n, box, 123, var_mass)
         lo, hi = rank * n // world, (rank + 1) * n // world                 # rank-sharded, arbitrary order
         tm = float(masses.astype(np.float64).sum()) if var_mass else 0.5 * n
-        pipe = SlabPipeline(dims, NumpyStages(dims, world, rank))
+        pipe = SlabPipeline(dims, NumpyStages(dims, world, rank, 0, fused, scatter))
         p, c, k = pipe.pk(torch.from_numpy(pos[lo:hi].reshape(-1).copy()),
                           torch.from_numpy(masses[lo:hi].copy()) if var_mass else None, 0.5, box, tm, dims)
         if rank == 0:
@@ -102,6 +102,22 @@ def test_slab_pipeline_over_gloo(tmp_path, port, world, dims, var_mass):
     got = np.load(tmp_path / "out.npz")
     pos, masses = _particles(n, box, 123, var_mass)
     tm = float(masses.astype(np.float64).sum()) if var_mass else 0.5 * n
+    _, pr, cr, kr = port.pk(box, dims, pos, masses, 0.5, tm, dims)
+    assert np.array_equal(got["c"], cr)
+    nz = cr > 0
+    np.testing.assert_allclose(got["p"][nz], pr[nz], rtol=1e-9)
+    np.testing.assert_allclose(got["k"][nz], kr[nz], rtol=1e-12)
+
+
+@pytest.mark.parametrize("world,dims,scatter", [(2, 16, False), (2, 16, True), (4, 32, True)])
+def test_fused_and_scatter_branches_over_gloo(tmp_path, port, world, dims, scatter):
+    """SlabPipeline.pk's other two branches: x pass + binning as one stage after the all-to-all,
+    and the y pass that delivers its rows itself between two barriers (no transpose step)."""
+    n, box = 6000, 100.0
+    mp.spawn(_worker, args=(world, _free_port(), dims, n, box, True, str(tmp_path), True, scatter), nprocs=world, join=True)
+    got = np.load(tmp_path / "out.npz")
+    pos, masses = _particles(n, box, 123, True)
+    tm = float(masses.astype(np.float64).sum())
     _, pr, cr, kr = port.pk(box, dims, pos, masses, 0.5, tm, dims)
     assert np.array_equal(got["c"], cr)
     nz = cr > 0
