@@ -429,13 +429,16 @@ int main(int argc, char *argv[])
                     read_deposit(src, STARS_TYPE, box, sink, &total_mass);         // :228-230
             }
             printf("total_mass in type %d = %g\n", type, total_mass);             // :232
-            if (genpk_fft(ctx, 0)) {                                               // :233
-                fprintf(stderr, "FFT failed: %s\n", genpk_last_error());
+            // :233-238: fftw_execute + powerspectrum as one call (the last FFT pass and the binning share a
+            // kernel for grid sides 256/512/1024/2048; the library's 3-D plan + binning pass otherwise)
+            if (genpk_fft_power(ctx, 0, nrbins, power.data(), count.data(), keffs.data(), total_mass, total_mass) ||
+                genpk_synchronize(ctx)) {
+                fprintf(stderr, "FFT / powerspectrum failed: %s\n", genpk_last_error());
                 status = 1;
                 break;
             }
-            if (run_power(0, 0, total_mass, total_mass, outdir + "/PK-" + type_str(type) + "-" + base, &t))   // :234-238
-                continue;
+            stage_times(ctx, &t);
+            print_pk(outdir + "/PK-" + type_str(type) + "-" + base, nrbins, keffs.data(), power.data(), count.data());
             t.wall_ms = now_ms() - t0;
             timings.push_back(t);
         }
