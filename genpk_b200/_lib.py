@@ -37,6 +37,7 @@ SIGNATURES = {
     "genpk_synchronize": (C.c_int, [C.c_void_p]),
     "genpk_grid_zero": (C.c_int, [C.c_void_p, C.c_int]),
     "genpk_deposit": (C.c_int, [C.c_void_p, C.c_int, c_f32p, c_f32p, C.c_int64, C.c_double, C.c_double, C.c_int]),
+    "genpk_deposit_f64": (C.c_int, [C.c_void_p, C.c_int, c_f64p, c_f32p, C.c_int64, C.c_double, C.c_double, C.c_int]),
     "genpk_fft": (C.c_int, [C.c_void_p, C.c_int]),
     "genpk_power": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_f64p, c_i32p, c_f64p, C.c_double, C.c_double]),
     "genpk_power_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, c_f64p, c_i32p, c_f64p, C.c_double,

@@ -219,6 +219,22 @@ class Context:
         check(self.lib.genpk_deposit(self.h, which, positions.ctypes.data, mp, n, float(mass), float(boxsize), 0),
               "genpk_deposit")
 
+    def deposit_f64(self, positions, masses=None, mass=1.0, boxsize=1.0, which: int = 0):
+        """Host positions in double precision, narrowed on the GPU (read_fieldize_bigfile.cpp:93-94)."""
+        positions = np.ascontiguousarray(positions, dtype=np.float64)
+        n = positions.size // 3
+        mp = None
+        if masses is not None:
+            masses = _f32(masses)
+            assert masses.size >= n
+            mp = masses.ctypes.data
+        check(self.lib.genpk_deposit_f64(self.h, which, positions.ctypes.data, mp, n, float(mass), float(boxsize), 0),
+              "genpk_deposit_f64")
+
+    def deposit_f64_dev(self, pos_ptr: int, n: int, mass_ptr: int = 0, mass=1.0, boxsize=1.0, which: int = 0):
+        check(self.lib.genpk_deposit_f64(self.h, which, pos_ptr, mass_ptr or None, int(n), float(mass), float(boxsize), 1),
+              "genpk_deposit_f64")
+
     def deposit_dev(self, pos_ptr: int, n: int, mass_ptr: int = 0, mass=1.0, boxsize=1.0, which: int = 0):
         check(self.lib.genpk_deposit(self.h, which, pos_ptr, mass_ptr or None, int(n), float(mass), float(boxsize), 1),
               "genpk_deposit")

@@ -138,6 +138,7 @@ void genpk_destroy(genpk_ctx *ctx)
         if (ctx->grid[i]) cudaFree(ctx->grid[i]);
         if (ctx->d_stage_pos[i]) cudaFree(ctx->d_stage_pos[i]);
         if (ctx->d_stage_mass[i]) cudaFree(ctx->d_stage_mass[i]);
+        if (ctx->d_stage_pos64[i]) cudaFree(ctx->d_stage_pos64[i]);
         if (ctx->stage_free[i]) cudaEventDestroy(ctx->stage_free[i]);
     }
     if (ctx->d_iw1d) cudaFree(ctx->d_iw1d);
@@ -275,6 +276,97 @@ static int ensure_stage(genpk_ctx *ctx, int64_t cap, bool with_mass)
     return 0;
 }
 
+// positions[i] = (float)((double *)pos)[i]: the narrowing of read_fieldize_bigfile.cpp:93-94 (round to nearest)
+__global__ void narrow_f64_kernel(const double *src, float *dst, size_t n)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        dst[i] = __double2float_rn(src[i]);
+}
+
+static int ensure_stage64(genpk_ctx *ctx, int64_t cap)
+{
+    if (cap > ctx->stage64_cap) {
+        for (int i = 0; i < 2; i++) {
+            if (ctx->d_stage_pos64[i]) cudaFree(ctx->d_stage_pos64[i]);
+            ctx->d_stage_pos64[i] = nullptr;
+        }
+        ctx->stage64_cap = 0;
+        for (int i = 0; i < 2; i++)
+            GENPK_CUDA_OK(cudaMalloc(&ctx->d_stage_pos64[i], (size_t)cap * 3 * sizeof(double)));
+        ctx->stage64_cap = cap;
+    }
+    return 0;
+}
+
+// Chunk loop shared by genpk_deposit (float positions) and genpk_deposit_f64 (double positions,
+// narrowed on the GPU).  Host particles: chunks go up on the copy stream into two device staging
+// buffers while the previous chunk is being deposited (chunk loop of read_fieldize.cpp:51-93,
+// overlapped).  The deposit is planned once, on the first chunk (the only host synchronisation of
+// the loop); when that finds a lattice the following chunks end on lattice-plane (or row)
+// boundaries so every chunk marches from a row start.
+static int deposit_chunks(genpk_ctx *ctx, int which, const void *positions, bool f64, const float *masses, int64_t n,
+                          double mass, double boxsize, int on_device)
+{
+    const int64_t chunk = n < ((int64_t)1 << 23) ? n : ((int64_t)1 << 23);
+    if (int rc = ensure_stage(ctx, chunk, masses != nullptr && !on_device)) return rc;
+    if (f64 && !on_device)
+        if (int rc = ensure_stage64(ctx, chunk)) return rc;
+    const float *pos32 = reinterpret_cast<const float *>(positions);
+    const double *pos64 = reinterpret_cast<const double *>(positions);
+    int rc = 0, buf = 0;
+    DepositPlan plan;
+    bool planned = false;
+    int64_t unit = 1;
+    for (int64_t off = 0; off < n && !rc; buf ^= 1) {
+        int64_t m = (n - off) < chunk ? (n - off) : chunk;
+        if (planned && off + m < n && m > unit)
+            m = m / unit * unit;
+        const float *dmass = masses ? masses + off : nullptr;
+        if (!on_device) {
+            GENPK_CUDA_OK(cudaStreamWaitEvent(ctx->copy_stream, ctx->stage_free[buf], 0));
+            if (f64)
+                GENPK_CUDA_OK(cudaMemcpyAsync(ctx->d_stage_pos64[buf], pos64 + 3 * off, (size_t)m * 3 * sizeof(double),
+                                              cudaMemcpyHostToDevice, ctx->copy_stream));
+            else
+                GENPK_CUDA_OK(cudaMemcpyAsync(ctx->d_stage_pos[buf], pos32 + 3 * off, (size_t)m * 3 * sizeof(float),
+                                              cudaMemcpyHostToDevice, ctx->copy_stream));
+            if (masses) {
+                GENPK_CUDA_OK(cudaMemcpyAsync(ctx->d_stage_mass[buf], masses + off, (size_t)m * sizeof(float),
+                                              cudaMemcpyHostToDevice, ctx->copy_stream));
+                dmass = ctx->d_stage_mass[buf];
+            }
+            cudaEvent_t up;   // chunk uploaded
+            GENPK_CUDA_OK(cudaEventCreateWithFlags(&up, cudaEventDisableTiming));
+            GENPK_CUDA_OK(cudaEventRecord(up, ctx->copy_stream));
+            GENPK_CUDA_OK(cudaStreamWaitEvent(ctx->stream, up, 0));
+            GENPK_CUDA_OK(cudaEventDestroy(up));
+        }
+        if (f64) {
+            const double *src = on_device ? pos64 + 3 * off : ctx->d_stage_pos64[buf];
+            narrow_f64_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(src, ctx->d_stage_pos[buf], (size_t)m * 3);
+            ctx->launches++;
+            GENPK_CUDA_OK(cudaGetLastError());
+        }
+        const float *dpos = (f64 || !on_device) ? ctx->d_stage_pos[buf] : pos32 + 3 * off;
+        if (!planned) {
+            if ((rc = deposit_plan(ctx, dpos, m, boxsize, &plan))) break;
+            planned = true;
+            if (plan.mode == GENPK_DEPOSIT_MARCH && plan.n0 > 0) {
+                const int64_t plane = plan.n1 > 0 ? plan.n0 * plan.n1 : 0;
+                unit = (plane > 0 && plane <= chunk) ? plane : (plan.n0 <= chunk ? plan.n0 : 1);
+                if (off + m < n && m > unit)
+                    m = m / unit * unit;           // the tail of this chunk is handled again with the next one
+            }
+        }
+        rc = deposit_device(ctx, which, dpos, dmass, m, mass, boxsize, &plan);
+        if (!on_device || f64)
+            GENPK_CUDA_OK(cudaEventRecord(ctx->stage_free[buf], ctx->stream));
+        off += m;
+    }
+    return rc;
+}
+
 int genpk_deposit(genpk_ctx *ctx, int which, const float *positions, const float *masses, int64_t n, double mass,
                   double boxsize, int on_device)
 {
@@ -283,52 +375,22 @@ int genpk_deposit(genpk_ctx *ctx, int which, const float *positions, const float
     if (n == 0) return 0;
     stage_begin(ctx, ST_DEPOSIT);
     int rc = 0;
-    if (on_device) {
-        rc = deposit_device(ctx, which, positions, masses, n, mass, boxsize);
-    } else {
-        // Host particles: chunks go up on the copy stream into two device staging
-        // buffers while the previous chunk is being deposited (chunk loop of
-        // read_fieldize.cpp:51-93, overlapped).  The deposit is planned once, on the first
-        // chunk (the only host synchronisation of the loop); when that finds a lattice the
-        // following chunks end on lattice-plane (or row) boundaries so every chunk marches
-        // from a row start.
-        const int64_t chunk = n < ((int64_t)1 << 23) ? n : ((int64_t)1 << 23);
-        if ((rc = ensure_stage(ctx, chunk, masses != nullptr))) return rc;
-        int buf = 0;
-        DepositPlan plan;
-        bool planned = false;
-        int64_t unit = 1;
-        for (int64_t off = 0; off < n && !rc; buf ^= 1) {
-            int64_t m = (n - off) < chunk ? (n - off) : chunk;
-            if (planned && off + m < n && m > unit)
-                m = m / unit * unit;
-            GENPK_CUDA_OK(cudaStreamWaitEvent(ctx->copy_stream, ctx->stage_free[buf], 0));
-            GENPK_CUDA_OK(cudaMemcpyAsync(ctx->d_stage_pos[buf], positions + 3 * off, (size_t)m * 3 * sizeof(float),
-                                          cudaMemcpyHostToDevice, ctx->copy_stream));
-            if (masses)
-                GENPK_CUDA_OK(cudaMemcpyAsync(ctx->d_stage_mass[buf], masses + off, (size_t)m * sizeof(float),
-                                              cudaMemcpyHostToDevice, ctx->copy_stream));
-            cudaEvent_t up;   // chunk uploaded
-            GENPK_CUDA_OK(cudaEventCreateWithFlags(&up, cudaEventDisableTiming));
-            GENPK_CUDA_OK(cudaEventRecord(up, ctx->copy_stream));
-            GENPK_CUDA_OK(cudaStreamWaitEvent(ctx->stream, up, 0));
-            GENPK_CUDA_OK(cudaEventDestroy(up));
-            if (!planned) {
-                if ((rc = deposit_plan(ctx, ctx->d_stage_pos[buf], m, boxsize, &plan))) break;
-                planned = true;
-                if (plan.mode == GENPK_DEPOSIT_MARCH && plan.n0 > 0) {
-                    const int64_t plane = plan.n1 > 0 ? plan.n0 * plan.n1 : 0;
-                    unit = (plane > 0 && plane <= chunk) ? plane : (plan.n0 <= chunk ? plan.n0 : 1);
-                    if (off + m < n && m > unit)
-                        m = m / unit * unit;           // the tail of this upload goes up again with the next chunk
-                }
-            }
-            rc = deposit_device(ctx, which, ctx->d_stage_pos[buf], masses ? ctx->d_stage_mass[buf] : nullptr, m, mass,
-                                boxsize, &plan);
-            GENPK_CUDA_OK(cudaEventRecord(ctx->stage_free[buf], ctx->stream));
-            off += m;
-        }
-    }
+    if (on_device)
+        rc = deposit_device(ctx, which, positions, masses, n, mass, boxsize);      // one launch over the resident set
+    else
+        rc = deposit_chunks(ctx, which, positions, false, masses, n, mass, boxsize, 0);
+    stage_end(ctx, ST_DEPOSIT);
+    return rc;
+}
+
+int genpk_deposit_f64(genpk_ctx *ctx, int which, const double *positions, const float *masses, int64_t n, double mass,
+                      double boxsize, int on_device)
+{
+    if (!check_which(ctx, which, "genpk_deposit_f64")) return 1;
+    if (n < 0 || (n > 0 && !positions)) { set_error("genpk_deposit_f64: bad particle array"); return 1; }
+    if (n == 0) return 0;
+    stage_begin(ctx, ST_DEPOSIT);
+    const int rc = deposit_chunks(ctx, which, positions, true, masses, n, mass, boxsize, on_device);
     stage_end(ctx, ST_DEPOSIT);
     return rc;
 }

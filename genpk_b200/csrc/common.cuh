@@ -102,6 +102,8 @@ struct genpk_ctx {
     // deposit scratch
     float *d_stage_pos[2] = {nullptr, nullptr};
     float *d_stage_mass[2] = {nullptr, nullptr};
+    double *d_stage_pos64[2] = {nullptr, nullptr};   // double-precision positions before the narrowing kernel
+    int64_t stage64_cap = 0;
     float *h_stage_pos[2] = {nullptr, nullptr};
     float *h_stage_mass[2] = {nullptr, nullptr};
     cudaEvent_t stage_free[2] = {nullptr, nullptr};

@@ -155,6 +155,17 @@ struct Sink {
         }
         return 0;
     }
+    // double-precision positions go up as they are stored and are narrowed on the GPU
+    // (the dump mode keeps the host narrowing: it shows what the reference's reader hands over)
+    bool takes_f64() const { return dump_pos == nullptr; }
+    int put64(const double *pos, const float *masses, int64_t n, double mass, double box)
+    {
+        if (genpk_deposit_f64(ctx, which, pos, masses, n, mass, box, 0)) {
+            fprintf(stderr, "deposit failed: %s\n", genpk_last_error());
+            return 1;
+        }
+        return 0;
+    }
 };
 
 // read_fieldize() (read_fieldize.cpp:18-97) and read_fieldize_bigfile()
@@ -188,9 +199,13 @@ static int read_deposit(const Source &src, int type, double box, Sink &sink, dou
         // the reference holds the whole type in RAM and makes one fieldize() call; chunks give the
         // same sums (total_mass_this_file is accumulated in double over all particles, :110-112)
         double total_mass_this_file = 0;
+        const bool f64 = bp.dtype == "<f8" && sink.takes_f64();                     // stored doubles: narrowed on the GPU
+        std::vector<double> pos64;
+        if (f64)
+            pos64.resize(3 * (size_t)chunk);
         for (int64_t done = 0; done < npart_total; done += chunk) {
             const int64_t n = std::min(chunk, npart_total - done);
-            if (!src.big->read_f32(bp, done, n, pos.data())) {
+            if (!(f64 ? src.big->read_f64_raw(bp, done, n, pos64.data()) : src.big->read_f32(bp, done, n, pos.data()))) {
                 fprintf(stderr, "Failed to read from block: %s\n", src.big->error().c_str());
                 return 1;
             }
@@ -202,7 +217,8 @@ static int read_deposit(const Source &src, int type, double box, Sink &sink, dou
                 for (int64_t i = 0; i < n; i++)
                     total_mass_this_file += masses[i];
             }
-            if (sink.put(pos.data(), mass == 0 ? masses.data() : nullptr, n, mass, box))
+            if (f64 ? sink.put64(pos64.data(), mass == 0 ? masses.data() : nullptr, n, mass, box)
+                    : sink.put(pos.data(), mass == 0 ? masses.data() : nullptr, n, mass, box))
                 return 1;
         }
         *total_mass += total_mass_this_file;

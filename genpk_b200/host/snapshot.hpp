@@ -86,6 +86,9 @@ public:
     // rows [first, first+count) of a block converted to float32 (through double when the
     // stored type is f8, as read_fieldize_bigfile.cpp:82-95 does)
     bool read_f32(const BigBlockInfo &b, int64_t first, int64_t count, float *dst) const;
+    // rows [first, first+count) of a little-endian f8 block as stored (the GPU narrows them:
+    // genpk_deposit_f64); false for any other dtype
+    bool read_f64_raw(const BigBlockInfo &b, int64_t first, int64_t count, double *dst) const;
     const std::string &error() const { return error_; }
 
 private:

@@ -182,4 +182,42 @@ bool BigfileSnapshot::read_f32(const BigBlockInfo &b, int64_t first, int64_t cou
     return true;
 }
 
+bool BigfileSnapshot::read_f64_raw(const BigBlockInfo &b, int64_t first, int64_t count, double *dst) const
+{
+    if (b.dtype != "<f8") {
+        error_ = "block " + b.dir + " is not <f8";
+        return false;
+    }
+    const size_t rowbytes = (size_t)8 * b.nmemb;
+    int64_t file_first = 0, done = 0;
+    for (size_t f = 0; f < b.file_rows.size() && done < count; f++) {
+        const int64_t file_last = file_first + b.file_rows[f];
+        const int64_t lo = first + done;
+        if (lo < file_last) {
+            const int64_t n = (file_last - lo < count - done) ? file_last - lo : count - done;
+            char fname[16];
+            snprintf(fname, sizeof(fname), "%06X", (unsigned)f);
+            FILE *fd = fopen((b.dir + "/" + fname).c_str(), "rb");
+            if (!fd) {
+                error_ = "cannot open " + b.dir + "/" + fname;
+                return false;
+            }
+            const bool good = fseek(fd, (long)((lo - file_first) * (int64_t)rowbytes), SEEK_SET) == 0 &&
+                              fread(dst + (size_t)done * b.nmemb, rowbytes, (size_t)n, fd) == (size_t)n;
+            fclose(fd);
+            if (!good) {
+                error_ = "short read in " + b.dir + "/" + fname;
+                return false;
+            }
+            done += n;
+        }
+        file_first = file_last;
+    }
+    if (done != count) {
+        error_ = "block " + b.dir + " holds fewer rows than requested";
+        return false;
+    }
+    return true;
+}
+
 }  // namespace genpk_host

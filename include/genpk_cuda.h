@@ -130,6 +130,14 @@ int genpk_grid_zero(genpk_ctx *ctx, int which);
 int genpk_deposit(genpk_ctx *ctx, int which, const float *positions, const float *masses,
                   int64_t n, double mass, double boxsize, int on_device);
 
+/* The same deposit for double-precision positions (bigfile `Position` blocks of dtype f8,
+ * DOUBLE_PRECISION_SNAP Gadget files): narrowed to float on the GPU exactly as
+ * read_fieldize_bigfile.cpp:93-94 does on the host (`positions[i] = ((double *)pos)[i]`, round
+ * to nearest), then deposited; identical grids to narrowing on the host and calling
+ * genpk_deposit.  Masses stay float (read_fieldize_bigfile.cpp:98-118). */
+int genpk_deposit_f64(genpk_ctx *ctx, int which, const double *positions, const float *masses,
+                      int64_t n, double mass, double boxsize, int on_device);
+
 /* fftw_execute() of gen-pk.cpp:233 on grid `which`, in place (cuFFT D2Z).  In
  * fixed-point mode the int64 grid is converted to double first. */
 int genpk_fft(genpk_ctx *ctx, int which);

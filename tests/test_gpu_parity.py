@@ -392,3 +392,31 @@ def test_full_size_properties():
     assert 0.9 < np.median(shot) < 1.1
     np.testing.assert_allclose(results["sorted"], results["direct"], rtol=1e-9, atol=1e-20)
     np.testing.assert_allclose(results["fixed"], results["direct"], rtol=1e-7, atol=1e-20)
+
+
+@pytest.mark.parametrize("var_mass", [False, True])
+def test_double_precision_positions_are_narrowed_like_the_reference(var_mass):
+    """genpk_deposit_f64: f8 positions narrowed on the GPU as read_fieldize_bigfile.cpp:93-94 narrows
+    them on the host ((float) of each double, round to nearest): the fixed-point grid must be
+    bit-identical to narrowing with numpy and calling genpk_deposit; host and device-resident input."""
+    import torch
+    dims, box, n = 96, 250.0, 300000
+    rng = np.random.default_rng(11)
+    pos64 = (rng.random((n, 3)) * 1.1 - 0.05) * box                    # full double mantissas, some outside the box
+    masses = (10.0 ** rng.uniform(-1, 1, n)).astype(np.float32) if var_mass else None
+    with gp.Context(dims, flags=api.FLAG_FIXED_POINT) as ctx:
+        ctx.grid_zero()
+        ctx.deposit(pos64.astype(np.float32), masses, 0.5, box)
+        want = ctx.grid_download_fixed()
+        ctx.grid_zero()
+        ctx.deposit_f64(pos64, masses, 0.5, box)
+        got = ctx.grid_download_fixed()
+        dpos = torch.from_numpy(pos64.reshape(-1).copy()).cuda()
+        dm = torch.from_numpy(masses).cuda() if var_mass else None
+        ctx.grid_zero()
+        ctx.deposit_f64_dev(dpos.data_ptr(), n, dm.data_ptr() if var_mass else 0, 0.5, box)
+        got_dev = ctx.grid_download_fixed()
+        ctx.synchronize()
+    assert want.any()
+    assert np.array_equal(got, want)
+    assert np.array_equal(got_dev, want)
