@@ -50,6 +50,26 @@ def test_no_cuda_device_fails_loudly(built):
         gp.fieldize(10.0, 4, field, 1, np.zeros(3, np.float32), None, 1.0, 1)
 
 
+def test_null_handles_are_errors_not_crashes(built):
+    """Every handle entry point of the fused / peer-store path refuses a null context with an
+    error code and a message (no GPU needed: nothing is launched)."""
+    import ctypes as C
+    lib = gp.load()
+    buf = C.create_string_buffer(64)
+    out = (C.c_double * 4)()
+    cnt = (C.c_int * 4)()
+    assert lib.genpk_fft_power(None, 0, 4, out, cnt, out, 1.0, 1.0) != 0
+    assert lib.genpk_deposit_f64(None, 0, out, None, 1, 1.0, 1.0, 0) != 0
+    assert lib.genpk_slab_fft_yz_scatter(None, 0) != 0
+    assert lib.genpk_slab_fftx_power_partial(None, out, 4, out) != 0
+    assert lib.genpk_ipc_export(None, buf) != 0
+    assert lib.genpk_slab_set_peer(None, 0, buf, None) != 0
+    assert not lib.genpk_slab_recv_buffer(None, None)
+    assert lib.genpk_fused_xpass_supported(None, 4) == 0
+    assert lib.genpk_slab_scatter_supported(None) == 0
+    assert gp.last_error() if hasattr(gp, "last_error") else True
+
+
 def test_product_never_imports_oracle():
     pkg = os.path.join(ROOT, "genpk_b200")
     for dirpath, _, files in os.walk(pkg):
