@@ -54,9 +54,16 @@ def _direct_bins(spec, n, kj, kz0, nc, thresh, iw, nrbins):
     return p
 
 
+@pytest.mark.parametrize("plan,nrbins", [(256, 1), (256, 37), (512, 2 * 512 + 3), (1024, 100)])
+def test_tile_bins_for_other_bin_counts(emu, plan, nrbins):
+    """nrbins is independent of the grid side in the C ABI (gen-pk uses nrbins = dims): one bin,
+    few bins (long runs), more bins than |k| values (many empty bins)."""
+    test_tile_fft_and_bins(emu, plan, -7, 16, nrbins)
+
+
 @pytest.mark.parametrize("plan", [256, 512, 1024, 2048, -1024])      # -1024: the 8192-mode tile of the 1024 plan
 @pytest.mark.parametrize("kj,kz0", [(0, 0), (-3, 8), (5, None)])
-def test_tile_fft_and_bins(emu, plan, kj, kz0):
+def test_tile_fft_and_bins(emu, plan, kj, kz0, nrbins=None):
     ncols = emu.fftx_emu_columns(plan)
     n = abs(plan)
     assert ncols * n in (4096, 8192)
@@ -67,9 +74,9 @@ def test_tile_fft_and_bins(emu, plan, kj, kz0):
     tile = rng.standard_normal((n, ncols)) + 1j * rng.standard_normal((n, ncols))
     tile *= np.exp(rng.uniform(-6, 6, (n, 1)))                   # a wide dynamic range
     tw = np.exp(-2j * np.pi * np.arange(n) / n)
-    nrbins = n
+    nrbins = n if nrbins is None else nrbins
     thresh, iw = _tables(n, nrbins)
-    half_bpu = np.float32(0.5 * (nrbins - 1) / np.log(np.sqrt(3.0) * n / 2.0))
+    half_bpu = np.float32(0.5 * (nrbins - 1) / np.log(np.sqrt(3.0) * n / 2.0)) if nrbins > 1 else np.float32(0)
     spec = np.zeros((n, ncols), dtype=np.complex128)
     mod2 = np.zeros((n, ncols))
     sp = np.zeros(nrbins)
