@@ -52,6 +52,17 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
 __device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
+// The staged tile has been read into registers: wait for those shared-memory loads to
+// complete (an empty asm that consumes the registers) so that the slots may be refilled.
+__device__ __forceinline__ void loads_landed(const fftx::cd *v)
+{
+#pragma unroll
+    for (int i = 0; i < fftx::EPT; i += 4)
+        asm volatile("" ::"d"(v[i].x), "d"(v[i].y), "d"(v[i + 1].x), "d"(v[i + 1].y), "d"(v[i + 2].x), "d"(v[i + 2].y),
+                     "d"(v[i + 3].x), "d"(v[i + 3].y)
+                     : "memory");
+}
+
 // One exchange through the half-size buffer E ([N/2][C] complex): the lower half of the index
 // space first, then the upper half.  WI(i) / RI(i): element index of register i on the writing /
 // reading side.  Which half an index falls in is a compile-time property of i (the predicates
@@ -170,8 +181,9 @@ __global__ void __launch_bounds__(PL::THREADS, PL::TILE == 4096 ? 2 : 1) fftx_po
 #pragma unroll
         for (int i = 0; i < EPT; i++)
             v[i] = valid ? stage[PL::load_n(t, i) * C + c] : make_double2(0.0, 0.0);
+        loads_landed(v);
+        issue(g_next, m_next);                                       // the slots are free: the next tile has the whole tile time to arrive
         PL::pass1(v, t, A.tw);
-        issue(g_next, m_next);                                       // the registers above are consumed: slots are free
 
         __syncthreads();                                             // the previous tile's bin walk has left P
         exchange<N, C, false, PL::ONE_UNIT2>(E, v, w, c, [&](int i) { return t + PL::ex1_w_part(i); },
@@ -279,8 +291,9 @@ __global__ void __launch_bounds__(PL::THREADS, PL::TILE == 4096 ? 2 : 1) fft_col
 #pragma unroll
         for (int i = 0; i < EPT; i++)
             v[i] = valid ? stage[PL::load_n(t, i) * C + c] : make_double2(0.0, 0.0);
+        loads_landed(v);
+        issue(g_next, o_next);                                       // slots free; another tile: never the rows written below
         PL::pass1(v, t, A.tw);
-        issue(g_next, o_next);                                       // another tile: never the rows written below
         __syncthreads();                                             // the previous tile's last exchange read is over
         exchange<N, C, false, PL::ONE_UNIT2>(E, v, w, c, [&](int i) { return t + PL::ex1_w_part(i); },
                        [&](int i) { return b_ex1r + PL::ex1_r_part(i); });
