@@ -53,7 +53,13 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("GENPK_WORKLOAD", "c3"), choices=sorted(WORKLOADS))
     ap.add_argument("--fixed-point", action="store_true", help="deterministic int64 accumulation mode")
-    ap.add_argument("--deposit", default="auto", choices=["auto", "direct", "sorted", "march"])
+    ap.add_argument("--deposit", default="auto", choices=["auto", "direct", "sorted", "march", "sweep"])
+    ap.add_argument("--no-sweep", action="store_true", help="lattice input: the march kernel instead of the sweep kernel")
+    ap.add_argument("--no-zero-ahead", action="store_true", help="memset the grid instead of clearing it ahead of the sweep's front")
+    ap.add_argument("--za-window", type=int, default=0, help="zero ahead: planes kept clear past the expected plane (0 = from the probe)")
+    ap.add_argument("--za-slack", type=int, default=-1)
+    ap.add_argument("--sweep-ry", type=int, default=0)
+    ap.add_argument("--no-self-check", action="store_true", help="skip the comparison with the committed reference fixtures")
     ap.add_argument("--power", default="cached", choices=["cached", "fused"],
                     help="binning pass: geometry sums cached in the context, or recomputed every call")
     ap.add_argument("--lattice-hint", action="store_true", help="pass the lattice extents instead of probing them")
@@ -217,8 +223,59 @@ def time_cpu_path(kind, wl, reps=1, want="reference"):
         cur = dict(deposit=t1 - t0, fft=t2 - t1, binning=t3 - t2, total=t3 - t0)
         if best is None or cur["total"] < best["total"]:
             best = cur
-    threads = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
+    threads = int(os.environ.get("OMP_NUM_THREADS", cpu_threads()))
     return dict(kind=backend, n=n, n_side=n_side, dims=dims, cores=threads, **best)
+
+
+def check_against_fixtures(workload, dims, power, cnt, keffs):
+    """The run's own P(k) next to the committed reference fixtures: mode counts must equal the golden table
+    (tests/golden/mode_counts.npz, from the reference's bin rule) and, for the configs that have a full-size
+    fixture made from the reference's object code (tests/golden/fullsize_pk.npz), P(k) and k_eff must agree
+    to 1e-5 relative.  A mismatch fails the run."""
+    out = {}
+    gold = os.path.join(ROOT, "tests", "golden")
+    try:
+        mc = np.load(os.path.join(gold, "mode_counts.npz"))
+        key = f"count{dims}"
+        if key in mc.files:
+            assert np.array_equal(cnt.astype(np.int64), mc[key]), "mode counts differ from the golden table"
+            out["counts"] = f"bit-exact vs tests/golden/mode_counts.npz:{key}"
+    except OSError:
+        pass
+    try:
+        fs = np.load(os.path.join(gold, "fullsize_pk.npz"))
+        if f"{workload}_power" in fs.files:
+            pr, cr, kr = fs[f"{workload}_power"], fs[f"{workload}_count"], fs[f"{workload}_keffs"]
+            assert np.array_equal(cnt.astype(np.int64), cr.astype(np.int64)), "mode counts differ from the reference fixture"
+            nz = cr > 0
+            dp = float(np.max(np.abs(power[nz] / pr[nz] - 1.0)))
+            dk = float(np.max(np.abs(keffs[nz] / kr[nz] - 1.0)))
+            assert dp <= 1e-5 and dk <= 1e-5, f"P(k) differs from the reference fixture: max rel {dp:.3e} (k_eff {dk:.3e})"
+            out["pk"] = {"fixture": f"tests/golden/fullsize_pk.npz:{workload} (reference objects at full size)",
+                         "max_rel_power": dp, "max_rel_keff": dk, "tolerance": 1e-5}
+    except OSError:
+        pass
+    return out or None
+
+
+def cpu_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def use_all_host_threads():
+    """torch.distributed.run exports OMP_NUM_THREADS=1 to its workers; the CPU arm is the reference's OpenMP code on
+    ALL host cores.  Must run before the oracle's shared objects (libgomp) are loaded."""
+    n = cpu_threads()
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    try:
+        import ctypes
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(n)
+    except OSError:
+        pass
+    return n
 
 
 def cpu_model():
@@ -239,6 +296,7 @@ def run_reference(args):
     if rank != 0:
         return
     wl = WORKLOADS[args.workload]
+    use_all_host_threads()
     times = []
     for i in range(args.warmup + args.steps):
         t = time_cpu_path(wl["kind"], wl, reps=1)
@@ -292,7 +350,7 @@ def run_ours(args):
     kind = {"uniform": api.SYNTH_UNIFORM_RANDOM, "clustered": api.SYNTH_CLUSTERED}[wl["kind"]]
     flags = api.FLAG_FIXED_POINT if args.fixed_point else 0
     mode = {"auto": api.DEPOSIT_AUTO, "direct": api.DEPOSIT_DIRECT, "sorted": api.DEPOSIT_SORTED,
-            "march": api.DEPOSIT_MARCH}[args.deposit]
+            "march": api.DEPOSIT_MARCH, "sweep": api.DEPOSIT_SWEEP}[args.deposit]
 
     # this rank's shard: a contiguous index range of the set (an x-slab of the lattice for the
     # lattice-ordered kinds, an arbitrary subset for the random kind)
@@ -347,6 +405,16 @@ def run_ours(args):
     fused = ctx.fused_xpass_supported(nrbins)
     if args.lattice_hint and wl["kind"] != "uniform":
         ctx.set_lattice_hint(n_side, n_side)
+    if args.no_sweep:
+        ctx.set_option(api.OPT_SWEEP, 0)
+    if args.no_zero_ahead:
+        ctx.set_option(api.OPT_ZERO_AHEAD, 0)
+    if args.za_window:
+        ctx.set_option(api.OPT_ZA_WINDOW, args.za_window)
+    if args.za_slack >= 0:
+        ctx.set_option(api.OPT_ZA_SLACK, args.za_slack)
+    if args.sweep_ry:
+        ctx.set_option(api.OPT_SWEEP_RY, args.sweep_ry)
     if args.march_ry:
         ctx.set_option(api.OPT_MARCH_RY, args.march_ry)
     if args.march_rx:
@@ -423,6 +491,7 @@ def run_ours(args):
             stage_ms[k] = v / args.steps                     # exchange steps of rank 0 (device time)
     power, cnt, keffs = out
     assert int(cnt.astype(np.int64).sum()) == dims ** 3 - 1, "mode counts do not sum to dims^3-1"
+    self_check = None if args.no_self_check else check_against_fixtures(args.workload, dims, power, cnt, keffs)
 
     # ---- end to end from pinned host memory ---------------------------------------------------
     e2e = None
@@ -451,8 +520,10 @@ def run_ours(args):
     peak, peak_src = measured_peaks()
     dep_bytes, bin_bytes = algorithmic_bytes(n_total, dims, world)
     roof = {}
-    # the deposit's algorithmic bytes include writing the grid once, so its time includes zeroing it
-    stage_ms["deposit_with_zero"] = stage_ms["deposit"] + stage_ms["zero"]
+    # the deposit's algorithmic bytes include writing the grid once, so its time includes zeroing it:
+    # genpk_grid_zero is lazy -- the grid is cleared inside the deposit stage, by the sweep kernel itself
+    # (zero ahead) or by a memset (stage_ms["zero"], a part of stage_ms["deposit"])
+    stage_ms["deposit_with_zero"] = stage_ms["deposit"]
     for name, nbytes in (("deposit", dep_bytes), ("binning", bin_bytes)):
         ms = stage_ms["deposit_with_zero"] if name == "deposit" else stage_ms[name]
         ach = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
@@ -481,7 +552,8 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl["label"], "particles": n_total, "grid": dims, "nrbins": nrbins, "box": BOX,
                    "accumulation": "int64 fixed-point" if args.fixed_point else "fp64 red.add",
-                   "deposit_mode": args.deposit, "order_probe": ctx.last_order(), "binning_mode": args.power,
+                   "deposit_mode": args.deposit, "order_probe": ctx.last_order(), "sweep": ctx.last_sweep(),
+                   "binning_mode": args.power,
                    "x_pass": "fused with binning (fftx_power_kernel)" if fused else "cuFFT", "parallelism": (f"x-slab x{world}, {ghost} ghost planes, particles {pipe.placement}, transpose "
                                    + ("fused into the y pass (peer stores)" if stages.scatter_ready else "pack + all-to-all")
                                    if world > 1
@@ -494,9 +566,10 @@ def run_ours(args):
         if stage_ms["binning"] else None,
         "roofline": roofline, "roofline_all": roof,
         "gpu_launches": int(launches), "cufft_execs_per_step": 1 if (world == 1 or fused) else 2,
-        "e2e": e2e, "clocks": clocks,
+        "e2e": e2e, "clocks": clocks, "self_check": self_check,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        use_all_host_threads()
         t = time_cpu_path(wl["kind"], wl, reps=2)
         line["cpu_baseline"] = {
             "value": t["n"] / t["total"] / 1e6, "unit": UNIT, "cores": t["cores"], "kind": t["kind"],

@@ -56,6 +56,7 @@ SIGNATURES = {
     "genpk_stage_reset": (C.c_int, [C.c_void_p]),
     "genpk_launch_count": (C.c_int64, [C.c_void_p]),
     "genpk_last_order": (C.c_int, [C.c_void_p, c_i64p]),
+    "genpk_last_sweep": (C.c_int, [C.c_void_p, c_i64p]),
     # 3. slab stages
     "genpk_create_slab": (C.c_void_p, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint]),
     "genpk_create_slab_wide": (C.c_void_p, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint, C.c_int]),

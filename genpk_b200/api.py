@@ -21,8 +21,9 @@ OPT_LATTICE_N0, OPT_LATTICE_N1, OPT_MARCH_RY, OPT_MARCH_RX = 4, 5, 6, 7
 OPT_FUSED_XPASS = 8
 OPT_FFT_YZ_BATCH = 9
 OPT_OWN_YPASS = 10
+OPT_SWEEP, OPT_SWEEP_RY, OPT_ZERO_AHEAD, OPT_ZA_WINDOW, OPT_ZA_SLACK, OPT_ZA_DEFERRED = 11, 12, 13, 14, 15, 16
 POWER_CACHED, POWER_FUSED = 0, 1
-DEPOSIT_AUTO, DEPOSIT_DIRECT, DEPOSIT_SORTED, DEPOSIT_TILED, DEPOSIT_MARCH = 0, 1, 2, 3, 4
+DEPOSIT_AUTO, DEPOSIT_DIRECT, DEPOSIT_SORTED, DEPOSIT_TILED, DEPOSIT_MARCH, DEPOSIT_SWEEP = 0, 1, 2, 3, 4, 5
 STAGE_DEPOSIT, STAGE_FFT, STAGE_POWER, STAGE_SORT, STAGE_ZERO = 0, 1, 2, 3, 4
 SYNTH_UNIFORM_RANDOM, SYNTH_LATTICE, SYNTH_CLUSTERED = 0, 1, 2
 FIELD_DIMS = 3072          # gen-pk.cpp:63
@@ -177,6 +178,13 @@ class Context:
         check(self.lib.genpk_last_order(self.h, out.ctypes.data), "genpk_last_order")
         keys = ("coherent", "lattice", "n0", "n1", "score_z", "score_y", "score_x")
         return {k: int(v) for k, v in zip(keys, out)}
+
+    def last_sweep(self) -> dict:
+        """The last lattice-sweep deposit: rows per column, columns (= warps), whether it cleared the grid
+        ahead of its own front (zero ahead), and the window in planes (diagnostics)."""
+        out = np.zeros(4, np.int64)
+        check(self.lib.genpk_last_sweep(self.h, out.ctypes.data), "genpk_last_sweep")
+        return {k: int(v) for k, v in zip(("ry", "columns", "zero_ahead", "window"), out)}
 
     def set_power_mode(self, mode: int):
         self.set_option(OPT_POWER, mode)

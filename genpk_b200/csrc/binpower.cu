@@ -277,13 +277,10 @@ __global__ void __launch_bounds__(POWER_THREADS) bin_power_kernel(PowerArgs A)
     }
 }
 
-int ensure_tables(genpk_ctx *ctx, int nrbins)
+// Frees the device side of the bin tables and forgets the cached geometry: the next
+// ensure_tables rebuilds everything (also the state a failed rebuild leaves behind).
+static void drop_tables(genpk_ctx *ctx)
 {
-    const unsigned rule = (ctx->flags & GENPK_FLAG_BINRULE_SOURCE) ? 1u : 0u;
-    if (ctx->tables.nrbins == nrbins && ctx->tables.dims == ctx->g.dims && ctx->d_thresh)
-        return 0;
-    if (int rc = build_bin_tables(ctx->g.dims, nrbins, rule, &ctx->tables))
-        return rc;
     if (ctx->d_thresh) cudaFree(ctx->d_thresh);
     if (ctx->d_iw1d) cudaFree(ctx->d_iw1d);
     if (ctx->d_sums) cudaFree(ctx->d_sums);
@@ -291,17 +288,43 @@ int ensure_tables(genpk_ctx *ctx, int nrbins)
     if (ctx->h_sums) cudaFreeHost(ctx->h_sums);
     ctx->d_thresh = nullptr; ctx->d_iw1d = nullptr; ctx->d_sums = nullptr; ctx->h_sums = nullptr; ctx->d_geom = nullptr;
     ctx->geom_valid = false;
-    GENPK_CUDA_OK(cudaMalloc(&ctx->d_thresh, ctx->tables.thresh.size() * sizeof(uint32_t)));
-    GENPK_CUDA_OK(cudaMalloc(&ctx->d_iw1d, ctx->tables.iw1d.size() * sizeof(float)));
+    ctx->sums_cap = 0;
+    ctx->tables.nrbins = 0;
+    ctx->tables.dims = 0;
+}
+
+static int upload_tables(genpk_ctx *ctx, const BinTables &t, int nrbins)
+{
+    GENPK_CUDA_OK(cudaMalloc(&ctx->d_thresh, t.thresh.size() * sizeof(uint32_t)));
+    GENPK_CUDA_OK(cudaMalloc(&ctx->d_iw1d, t.iw1d.size() * sizeof(float)));
     GENPK_CUDA_OK(cudaMalloc(&ctx->d_sums, (size_t)3 * nrbins * sizeof(double)));
     GENPK_CUDA_OK(cudaMalloc(&ctx->d_geom, (size_t)3 * nrbins * sizeof(double)));
     GENPK_CUDA_OK(cudaMallocHost(&ctx->h_sums, (size_t)3 * nrbins * sizeof(double)));
-    ctx->sums_cap = nrbins;
-    GENPK_CUDA_OK(cudaMemcpyAsync(ctx->d_thresh, ctx->tables.thresh.data(), ctx->tables.thresh.size() * sizeof(uint32_t),
-                                  cudaMemcpyHostToDevice, ctx->stream));
-    GENPK_CUDA_OK(cudaMemcpyAsync(ctx->d_iw1d, ctx->tables.iw1d.data(), ctx->tables.iw1d.size() * sizeof(float),
-                                  cudaMemcpyHostToDevice, ctx->stream));
+    GENPK_CUDA_OK(cudaMemcpyAsync(ctx->d_thresh, t.thresh.data(), t.thresh.size() * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                                  ctx->stream));
+    GENPK_CUDA_OK(cudaMemcpyAsync(ctx->d_iw1d, t.iw1d.data(), t.iw1d.size() * sizeof(float), cudaMemcpyHostToDevice,
+                                  ctx->stream));
     GENPK_CUDA_OK(cudaStreamSynchronize(ctx->stream));     // the host vectors may be rebuilt later
+    return 0;
+}
+
+int ensure_tables(genpk_ctx *ctx, int nrbins)
+{
+    const unsigned rule = (ctx->flags & GENPK_FLAG_BINRULE_SOURCE) ? 1u : 0u;
+    if (ctx->tables.nrbins == nrbins && ctx->tables.dims == ctx->g.dims && ctx->tables.rule == rule && ctx->d_thresh)
+        return 0;
+    // built aside and committed only once every allocation and upload has succeeded: a failure
+    // leaves no half-updated cache behind (the next call starts from scratch)
+    BinTables fresh;
+    if (int rc = build_bin_tables(ctx->g.dims, nrbins, rule, &fresh))
+        return rc;
+    drop_tables(ctx);
+    if (int rc = upload_tables(ctx, fresh, nrbins)) {
+        drop_tables(ctx);
+        return rc;
+    }
+    ctx->tables = fresh;
+    ctx->sums_cap = nrbins;
     return 0;
 }
 

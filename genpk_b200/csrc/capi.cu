@@ -151,6 +151,8 @@ void genpk_destroy(genpk_ctx *ctx)
     if (ctx->d_brick_counts) cudaFree(ctx->d_brick_counts);
     if (ctx->d_errors) cudaFree(ctx->d_errors);
     if (ctx->d_order) cudaFree(ctx->d_order);
+    if (ctx->d_za_zdone) cudaFree(ctx->d_za_zdone);
+    if (ctx->d_za_def) cudaFree(ctx->d_za_def);
     if (ctx->d_twiddle) cudaFree(ctx->d_twiddle);
     for (int r = 0; r < GENPK_MAX_PEERS; r++)
         if (ctx->peer_opened[r] && ctx->peer_recv[r]) cudaIpcCloseMemHandle(ctx->peer_recv[r]);
@@ -176,7 +178,7 @@ int genpk_set_option(genpk_ctx *ctx, int option, int64_t value)
     if (!ctx) { set_error("genpk_set_option: null context"); return 1; }
     switch (option) {
     case GENPK_OPT_DEPOSIT:
-        if (value < GENPK_DEPOSIT_AUTO || value > GENPK_DEPOSIT_MARCH) break;
+        if (value < GENPK_DEPOSIT_AUTO || value > GENPK_DEPOSIT_SWEEP) break;
         ctx->deposit_mode = (int)value;
         return 0;
     case GENPK_OPT_SCALE_BITS:
@@ -215,6 +217,30 @@ int genpk_set_option(genpk_ctx *ctx, int option, int64_t value)
         if (value < 0 || value > 2) break;
         ctx->fused_xpass = (int)value;
         return 0;
+    case GENPK_OPT_SWEEP:
+        if (value != 0 && value != 1) break;
+        ctx->sweep = (int)value;
+        return 0;
+    case GENPK_OPT_SWEEP_RY:
+        if (value < 0 || value > 64) break;
+        ctx->sweep_ry = (int)value;
+        return 0;
+    case GENPK_OPT_ZERO_AHEAD:
+        if (value != 0 && value != 1) break;
+        ctx->zero_ahead = (int)value;
+        return 0;
+    case GENPK_OPT_ZA_WINDOW:
+        if (value < 0 || value > 4096) break;
+        ctx->za_window = (int)value;
+        return 0;
+    case GENPK_OPT_ZA_SLACK:
+        if (value < 0 || value > 64) break;
+        ctx->za_slack = (int)value;
+        return 0;
+    case GENPK_OPT_ZA_DEFERRED:
+        if (value < 1 || value > (1 << 20)) break;
+        ctx->za_def_per_col = (int)value;
+        return 0;
     }
     set_error("genpk_set_option: bad option %d / value %lld", option, (long long)value);
     return 1;
@@ -249,10 +275,15 @@ int genpk_take_rejected(genpk_ctx *ctx, uint64_t *rejected)
 int genpk_grid_zero(genpk_ctx *ctx, int which)
 {
     if (!check_which(ctx, which, "genpk_grid_zero")) return 1;
-    stage_begin(ctx, ST_ZERO);
-    GENPK_CUDA_OK(cudaMemsetAsync(ctx->grid[which], 0, ctx->g.grid_doubles() * sizeof(double), ctx->stream));
-    stage_end(ctx, ST_ZERO);
-    ctx->grid_is_fixed[which] = false;
+    // Lazy: the memset runs when the grid is next read or deposited into -- unless that next use is
+    // a lattice sweep, which clears the grid ahead of its own front instead (deposit_sweep.cu) and
+    // saves one write and one read of the whole grid.
+    ctx->zero_pending[which] = true;
+    if (!ctx->zero_ahead)
+        if (int rc = materialize_zero(ctx, which)) return rc;
+    // an all-zero grid is valid in either representation: take it from the context's mode, so a
+    // slab rank that deposits nothing still adds its neighbours' int64 ghost planes as integers
+    ctx->grid_is_fixed[which] = ctx->fixed;
     return 0;
 }
 
@@ -309,6 +340,10 @@ static int deposit_chunks(genpk_ctx *ctx, int which, const void *positions, bool
                           double mass, double boxsize, int on_device)
 {
     const int64_t chunk = n < ((int64_t)1 << 23) ? n : ((int64_t)1 << 23);
+    // a pending genpk_grid_zero: chunks are partial sweeps, so the grid is cleared by a memset here
+    // (it overlaps the first upload); one-call device-resident deposits clear it ahead of their front
+    if (n > chunk || !on_device)
+        if (int rc = materialize_zero(ctx, which)) return rc;
     if (int rc = ensure_stage(ctx, chunk, masses != nullptr && !on_device)) return rc;
     if (f64 && !on_device)
         if (int rc = ensure_stage64(ctx, chunk)) return rc;
@@ -363,6 +398,11 @@ static int deposit_chunks(genpk_ctx *ctx, int which, const void *positions, bool
         if (!on_device || f64)
             GENPK_CUDA_OK(cudaEventRecord(ctx->stage_free[buf], ctx->stream));
         off += m;
+    }
+    if (!on_device) {
+        // the uploads read the caller's buffers asynchronously: they are over when this call returns
+        // (the deposits of the last chunks may still be running on the context's stream)
+        GENPK_CUDA_OK(cudaStreamSynchronize(ctx->copy_stream));
     }
     return rc;
 }
@@ -446,6 +486,8 @@ int genpk_power(genpk_ctx *ctx, int a, int b, int nrbins, double *power, int *co
                 double total_mass2)
 {
     if (!check_which(ctx, a, "genpk_power") || !check_which(ctx, b, "genpk_power")) return 1;
+    if (int rc = materialize_zero(ctx, a)) return rc;
+    if (int rc = materialize_zero(ctx, b)) return rc;
     return power_on(ctx, ctx->grid[a], ctx->grid[b], nrbins, power, count, keffs, total_mass, total_mass2);
 }
 
@@ -499,12 +541,15 @@ size_t genpk_grid_owned_offset(const genpk_ctx *ctx) { return ctx ? ctx->g.owned
 
 void *genpk_grid_device_ptr(genpk_ctx *ctx, int which)
 {
-    return check_which(ctx, which, "genpk_grid_device_ptr") ? ctx->grid[which] : nullptr;
+    if (!check_which(ctx, which, "genpk_grid_device_ptr")) return nullptr;
+    if (materialize_zero(ctx, which)) return nullptr;          // the caller is about to look at the grid
+    return ctx->grid[which];
 }
 
 int genpk_grid_download(genpk_ctx *ctx, int which, double *host)
 {
     if (!check_which(ctx, which, "genpk_grid_download")) return 1;
+    if (int rc = materialize_zero(ctx, which)) return rc;
     const size_t n = ctx->g.grid_doubles();
     GENPK_CUDA_OK(cudaMemcpyAsync(host, ctx->grid[which], n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     GENPK_CUDA_OK(cudaStreamSynchronize(ctx->stream));
@@ -522,6 +567,7 @@ int genpk_grid_download(genpk_ctx *ctx, int which, double *host)
 int genpk_grid_download_fixed(genpk_ctx *ctx, int which, int64_t *host)
 {
     if (!check_which(ctx, which, "genpk_grid_download_fixed")) return 1;
+    if (int rc = materialize_zero(ctx, which)) return rc;
     if (!ctx->grid_is_fixed[which] && ctx->fixed) {
         // an untouched (zeroed) grid is valid fixed-point data too
     } else if (!ctx->grid_is_fixed[which]) {
@@ -537,6 +583,7 @@ int genpk_grid_download_fixed(genpk_ctx *ctx, int which, int64_t *host)
 int genpk_grid_upload(genpk_ctx *ctx, int which, const double *host)
 {
     if (!check_which(ctx, which, "genpk_grid_upload")) return 1;
+    ctx->zero_pending[which] = false;                            // overwritten as a whole
     GENPK_CUDA_OK(cudaMemcpyAsync(ctx->grid[which], host, ctx->g.grid_doubles() * sizeof(double), cudaMemcpyHostToDevice,
                                   ctx->stream));
     GENPK_CUDA_OK(cudaStreamSynchronize(ctx->stream));
@@ -588,6 +635,13 @@ int genpk_last_order(const genpk_ctx *ctx, int64_t out[7])
     return 0;
 }
 
+int genpk_last_sweep(const genpk_ctx *ctx, int64_t out[4])
+{
+    if (!ctx || !out) { set_error("genpk_last_sweep: bad arguments"); return 1; }
+    for (int i = 0; i < 4; i++) out[i] = ctx->last_sweep[i];
+    return 0;
+}
+
 /* ---------------- slab stages ---------------- */
 
 int genpk_route_particles(genpk_ctx *ctx, const float *pos_dev, const float *mass_dev, int64_t n, double boxsize,
@@ -603,6 +657,7 @@ int genpk_route_particles(genpk_ctx *ctx, const float *pos_dev, const float *mas
 void *genpk_ghost_side_ptr(genpk_ctx *ctx, int which, int side, size_t *bytes)
 {
     if (!check_which(ctx, which, "genpk_ghost_side_ptr")) return nullptr;
+    if (materialize_zero(ctx, which)) return nullptr;
     const SlabGeom &g = ctx->g;
     const int planes = side ? g.ghost_hi : g.ghost_lo;
     if (side < 0 || side > 1 || planes == 0) {
@@ -619,6 +674,7 @@ int genpk_ghost_side_accumulate(genpk_ctx *ctx, int which, int side, const void 
 {
     if (!check_which(ctx, which, "genpk_ghost_side_accumulate")) return 1;
     if (side < 0 || side > 1 || !recv_planes_dev) { set_error("genpk_ghost_side_accumulate: bad arguments"); return 1; }
+    if (int rc = materialize_zero(ctx, which)) return rc;
     return ghost_accumulate(ctx, which, side, recv_planes_dev);
 }
 
@@ -640,6 +696,7 @@ int genpk_slab_fft_yz(genpk_ctx *ctx, int which)
 int genpk_slab_pack(genpk_ctx *ctx, int which, void *send_dev)
 {
     if (!check_which(ctx, which, "genpk_slab_pack")) return 1;
+    if (int rc = materialize_zero(ctx, which)) return rc;
     return slab_pack(ctx, which, send_dev);
 }
 

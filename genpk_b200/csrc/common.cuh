@@ -104,8 +104,6 @@ struct genpk_ctx {
     float *d_stage_mass[2] = {nullptr, nullptr};
     double *d_stage_pos64[2] = {nullptr, nullptr};   // double-precision positions before the narrowing kernel
     int64_t stage64_cap = 0;
-    float *h_stage_pos[2] = {nullptr, nullptr};
-    float *h_stage_mass[2] = {nullptr, nullptr};
     cudaEvent_t stage_free[2] = {nullptr, nullptr};
     cudaStream_t copy_stream = nullptr;
     int64_t stage_cap = 0;            // particles per staging buffer
@@ -118,6 +116,19 @@ struct genpk_ctx {
     void *d_order = nullptr;                  // OrderInfo written by the order probe
     long long lattice_n0 = 0, lattice_n1 = 0; // caller's hint: particles per lattice row, rows per plane
     int march_ry = 8, march_rx = 8;           // rows / planes one warp marches over
+    // lattice sweep (deposit_sweep.cu)
+    int sweep = 1;                            // AUTO picks the sweep kernel for lattice input (0: the march kernel)
+    int sweep_ry = 0;                         // rows per column (0: as few as keep every column resident)
+    int zero_ahead = 1;                       // genpk_grid_zero is lazy; a sweep that follows clears the grid ahead of its front
+    int za_window = 0;                        // planes ahead of the expected plane kept clear (0: from the order probe)
+    int za_slack = 2;                         // lattice planes between clearing a plane and first needing it
+    int za_def_per_col = 4096;                // deferred-particle list entries per column
+    unsigned *d_za_zdone = nullptr;
+    int za_zdone_cap = 0;
+    unsigned *d_za_def = nullptr;
+    size_t za_def_cap = 0;
+    bool zero_pending[2] = {false, false};    // genpk_grid_zero has been asked for but not yet carried out
+    long long last_sweep[4] = {0, 0, 0, 0};   // rows per column, columns, zero ahead used, window (diagnostics)
 
     // fused x pass (fftx_power.cu)
     int fused_xpass = 1;                      // 0: always cuFFT's x pass + bin_power_kernel
@@ -144,14 +155,18 @@ namespace genpk {
 
 // deposit.cu
 struct DepositPlan {
-    int mode = 0;                 // GENPK_DEPOSIT_DIRECT / SORTED / MARCH
-    long long n0 = 0, n1 = 0;     // lattice row length / rows per plane (MARCH)
+    int mode = 0;                 // GENPK_DEPOSIT_DIRECT / SORTED / MARCH / SWEEP
+    long long n0 = 0, n1 = 0;     // lattice row length / rows per plane (MARCH, SWEEP)
+    bool have_dx = false;         // the order probe measured where lattice planes sit along x
+    int dx_mean = 0, dx_dev = 0;
 };
 int deposit_plan(genpk_ctx *ctx, const float *pos, int64_t n, double boxsize, DepositPlan *plan);
 // plan == nullptr: planned here (one order probe, one small D2H)
 int deposit_device(genpk_ctx *ctx, int which, const float *pos, const float *masses, int64_t n,
                    double mass, double boxsize, const DepositPlan *plan = nullptr);
 int fixed_to_double(genpk_ctx *ctx, int which);
+// carries out a pending genpk_grid_zero (every reader of the grid calls this first)
+int materialize_zero(genpk_ctx *ctx, int which);
 // binpower.cu
 int ensure_tables(genpk_ctx *ctx, int nrbins);
 int power_raw(genpk_ctx *ctx, const double *spec_a, const double *spec_b, int n_outer, int outer0,

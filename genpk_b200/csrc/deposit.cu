@@ -382,6 +382,27 @@ int deposit_device(genpk_ctx *ctx, int which, const float *pos, const float *mas
             return rc;
         plan = &local;
     }
+    if (plan->mode == GENPK_DEPOSIT_SWEEP) {
+        OrderInfo info = {};
+        info.dx_valid = plan->have_dx ? 1 : 0;
+        info.dx_mean = plan->dx_mean;
+        info.dx_dev = plan->dx_dev;
+        // a pending genpk_grid_zero: the sweep clears the grid ahead of its own front when it can
+        if (ctx->zero_pending[which] && ctx->zero_ahead) {
+            bool possible = true;
+            if (int rc = launch_sweep(ctx, a, plan->n0, plan->n1, true, &info, &possible))
+                return rc;
+            if (possible) {
+                ctx->zero_pending[which] = false;
+                return 0;
+            }
+        }
+        if (int rc = materialize_zero(ctx, which))
+            return rc;
+        return launch_sweep(ctx, a, plan->n0, plan->n1, false, &info, nullptr);
+    }
+    if (int rc = materialize_zero(ctx, which))
+        return rc;
     if (plan->mode == GENPK_DEPOSIT_MARCH)
         return launch_march(ctx, a, plan->n0, plan->n1);
     if (plan->mode == GENPK_DEPOSIT_SORTED) {
@@ -414,7 +435,9 @@ int deposit_plan(genpk_ctx *ctx, const float *pos, int64_t n, double boxsize, De
     long long n0 = ctx->lattice_n0, n1 = ctx->lattice_n1;
     if (mode == GENPK_DEPOSIT_AUTO && n < (1 << 16))
         mode = GENPK_DEPOSIT_DIRECT;
-    if (mode == GENPK_DEPOSIT_AUTO || (mode == GENPK_DEPOSIT_MARCH && n0 <= 0)) {
+    plan->have_dx = false;
+    const bool lattice_mode = mode == GENPK_DEPOSIT_MARCH || mode == GENPK_DEPOSIT_SWEEP;
+    if (mode == GENPK_DEPOSIT_AUTO || (lattice_mode && n0 <= 0) || (mode == GENPK_DEPOSIT_SWEEP && ctx->zero_ahead)) {
         OrderInfo info;
         if (int rc = probe_order(ctx, pos, n, g.dims / boxsize, &info))
             return rc;
@@ -425,10 +448,17 @@ int deposit_plan(genpk_ctx *ctx, const float *pos, int64_t n, double boxsize, De
         ctx->last_order[4] = info.score_z;
         ctx->last_order[5] = info.score_y;
         ctx->last_order[6] = info.score_x;
-        n0 = info.lattice ? info.n0 : 0;
-        n1 = info.lattice ? info.n1 : 0;
+        if (!(lattice_mode && n0 > 0)) {                  // (a caller's hint stands; the probe only adds the x offsets then)
+            n0 = info.lattice ? info.n0 : 0;
+            n1 = info.lattice ? info.n1 : 0;
+        }
+        if (info.lattice && info.dx_valid && info.n0 == n0 && (info.n1 == n1 || n1 == 0)) {
+            plan->have_dx = true;
+            plan->dx_mean = info.dx_mean;
+            plan->dx_dev = info.dx_dev;
+        }
         if (mode == GENPK_DEPOSIT_AUTO)
-            mode = info.lattice ? GENPK_DEPOSIT_MARCH
+            mode = info.lattice ? (ctx->sweep ? GENPK_DEPOSIT_SWEEP : GENPK_DEPOSIT_MARCH)
                                 : ((info.coherent || fits_l2) ? GENPK_DEPOSIT_DIRECT : GENPK_DEPOSIT_SORTED);
     }
     plan->mode = mode;
@@ -437,8 +467,21 @@ int deposit_plan(genpk_ctx *ctx, const float *pos, int64_t n, double boxsize, De
     return 0;
 }
 
+int materialize_zero(genpk_ctx *ctx, int which)
+{
+    if (!ctx->zero_pending[which])
+        return 0;
+    ctx->zero_pending[which] = false;
+    stage_begin(ctx, ST_ZERO);
+    GENPK_CUDA_OK(cudaMemsetAsync(ctx->grid[which], 0, ctx->g.grid_doubles() * sizeof(double), ctx->stream));
+    stage_end(ctx, ST_ZERO);
+    return 0;
+}
+
 int fixed_to_double(genpk_ctx *ctx, int which)
 {
+    if (int rc = materialize_zero(ctx, which))
+        return rc;
     if (!ctx->grid_is_fixed[which])
         return 0;
     const size_t n = ctx->g.grid_doubles();

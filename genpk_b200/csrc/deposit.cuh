@@ -27,9 +27,17 @@ struct OrderInfo {
     int lattice;          // 1: lattice order with row length n0 (and n1 rows per plane when > 0)
     long long n0, n1;
     int score_z, score_y, score_x, samples;   // per mille of exact one-cell hand-overs, diagnostics
+    // lattice only: where the particles of lattice plane x sit along x, in (local) grid planes, relative to
+    // floor((x + 1/2) * planes_per_lattice_plane): rounded mean and largest deviation from it over the samples
+    int dx_valid, dx_mean, dx_dev;
 };
 int probe_order(genpk_ctx *ctx, const float *pos, int64_t n, double units, OrderInfo *info);
 int launch_march(genpk_ctx *ctx, const DepositArgs &a, long long n0, long long n1);
+// deposit_sweep.cu.  za: the grid has NOT been cleared, the launch clears it ahead of its own front.
+// Returns with *za_possible false (and nothing launched) when za was asked for but this lattice cannot
+// be swept in one resident wave; the caller then clears the grid and calls again with za = false.
+int launch_sweep(genpk_ctx *ctx, const DepositArgs &a, long long n0, long long n1, bool za, const OrderInfo *info,
+                 bool *za_possible);
 
 struct AxisCell {
     int lo, hi;
@@ -88,5 +96,68 @@ template <> struct Acc<true> {
         atomicAdd(reinterpret_cast<unsigned long long *>(grid) + idx, (unsigned long long)v);   // REDG.E.ADD.64
     }
 };
+
+// One particle, eight reductions: the arithmetic of deposit_direct_kernel (fieldize.cpp:63-92) for the
+// stragglers of the sweep kernel.  Rejected (non-finite, outside the slab) particles are skipped.
+template <bool FIXED>
+__device__ __forceinline__ void deposit_single(const DepositArgs &a, float px, float py, float pz, double m)
+{
+    const AxisCell cx = axis_cell(px, a.units, a.dims);
+    const AxisCell cy = axis_cell(py, a.units, a.dims);
+    const AxisCell cz = axis_cell(pz, a.units, a.dims);
+    if (!(cx.ok && cy.ok && cz.ok))
+        return;
+    int xl = cx.lo, xh = cx.hi;
+    if (a.slab) {
+        xl = slab_plane(cx.lo, a.x0, a.ghost_lo, a.dims);
+        if (xl < 0 || xl > a.xl_max)
+            return;
+        xh = xl + 1;
+    }
+    const double mx0 = __dmul_rn(m, cx.wl), mx1 = __dmul_rn(m, cx.wh);
+    const double w00 = __dmul_rn(mx0, cy.wl), w10 = __dmul_rn(mx1, cy.wl);
+    const double w01 = __dmul_rn(mx0, cy.wh), w11 = __dmul_rn(mx1, cy.wh);
+    const size_t bx0 = a.plane * (size_t)xl, bx1 = a.plane * (size_t)xh;
+    const size_t by0 = (size_t)a.fd * cy.lo, by1 = (size_t)a.fd * cy.hi;
+    Acc<FIXED>::red(a.grid, bx0 + by0 + cz.lo, Acc<FIXED>::make(__dmul_rn(w00, cz.wl), a.scale));
+    Acc<FIXED>::red(a.grid, bx1 + by0 + cz.lo, Acc<FIXED>::make(__dmul_rn(w10, cz.wl), a.scale));
+    Acc<FIXED>::red(a.grid, bx0 + by1 + cz.lo, Acc<FIXED>::make(__dmul_rn(w01, cz.wl), a.scale));
+    Acc<FIXED>::red(a.grid, bx1 + by1 + cz.lo, Acc<FIXED>::make(__dmul_rn(w11, cz.wl), a.scale));
+    Acc<FIXED>::red(a.grid, bx0 + by0 + cz.hi, Acc<FIXED>::make(__dmul_rn(w00, cz.wh), a.scale));
+    Acc<FIXED>::red(a.grid, bx1 + by0 + cz.hi, Acc<FIXED>::make(__dmul_rn(w10, cz.wh), a.scale));
+    Acc<FIXED>::red(a.grid, bx0 + by1 + cz.hi, Acc<FIXED>::make(__dmul_rn(w01, cz.wh), a.scale));
+    Acc<FIXED>::red(a.grid, bx1 + by1 + cz.hi, Acc<FIXED>::make(__dmul_rn(w11, cz.wh), a.scale));
+}
+
+// Out-of-box cell index -> [0, dims) (fieldize.cpp:70-75); kept out of line, it is rare.
+static __device__ __noinline__ int wrap_cell(int f, int dims)
+{
+    f %= dims;
+    return f < 0 ? f + dims : f;
+}
+
+// Same arithmetic as axis_cell (x = p*units, f = floor(x), d = x - f, t = 1 - d) with the
+// floor taken by a round-down add of 1.5*2^52: the low word of the sum is floor(x) as an
+// int and sum - magic is floor(x) as a double, both exact for |x| < 2^31.  Two additions
+// instead of three 64-bit conversions, which run at a fraction of the FP64 add rate.
+__device__ __forceinline__ void axis_fast(float p, double units, int &f, double &wl, double &wh)
+{
+    const double magic = 6755399441055744.0;
+    const double x = __dmul_rn((double)p, units);           // fieldize.cpp:66
+    const double t = __dadd_rd(x, magic);
+    f = __double2loint(t);                                  // :67
+    wh = __dsub_rn(x, __dsub_rn(t, magic));                 // :68  dx
+    wl = __dsub_rn(1.0, wh);                                // :69  tx
+}
+
+// lo += from when take (one predicated add instead of add + two selects)
+__device__ __forceinline__ void add_if(double &lo, double from, int take)
+{
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p add.rn.f64 %0, %0, %1;\n\t}" : "+d"(lo) : "d"(from), "r"(take));
+}
+__device__ __forceinline__ void add_if(long long &lo, long long from, int take)
+{
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p add.s64 %0, %0, %1;\n\t}" : "+l"(lo) : "l"(from), "r"(take));
+}
 
 }  // namespace genpk

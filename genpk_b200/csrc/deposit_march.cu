@@ -59,37 +59,6 @@ __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc, unsi
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-// Out-of-box cell index -> [0, dims) (fieldize.cpp:70-75); kept out of line, it is rare.
-__device__ __noinline__ int wrap_cell(int f, int dims)
-{
-    f %= dims;
-    return f < 0 ? f + dims : f;
-}
-
-// Same arithmetic as axis_cell (x = p*units, f = floor(x), d = x - f, t = 1 - d) with the
-// floor taken by a round-down add of 1.5*2^52: the low word of the sum is floor(x) as an
-// int and sum - magic is floor(x) as a double, both exact for |x| < 2^31.  Two additions
-// instead of three 64-bit conversions, which run at a fraction of the FP64 add rate.
-__device__ __forceinline__ void axis_fast(float p, double units, int &f, double &wl, double &wh)
-{
-    const double magic = 6755399441055744.0;
-    const double x = __dmul_rn((double)p, units);           // fieldize.cpp:66
-    const double t = __dadd_rd(x, magic);
-    f = __double2loint(t);                                  // :67
-    wh = __dsub_rn(x, __dsub_rn(t, magic));                 // :68  dx
-    wl = __dsub_rn(1.0, wh);                                // :69  tx
-}
-
-// lo += from when take (one predicated add instead of add + two selects)
-__device__ __forceinline__ void add_if(double &lo, double from, int take)
-{
-    asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p add.rn.f64 %0, %0, %1;\n\t}" : "+d"(lo) : "d"(from), "r"(take));
-}
-__device__ __forceinline__ void add_if(long long &lo, long long from, int take)
-{
-    asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p add.s64 %0, %0, %1;\n\t}" : "+l"(lo) : "l"(from), "r"(take));
-}
-
 // FULL: every lattice site the launch touches holds a particle (n == n0*n1*n2), so no
 // per-step bound checks on the particle index.  MASS: per-particle masses.
 template <bool FIXED, typename key_t, bool FULL, bool MASS>
@@ -342,6 +311,9 @@ struct ProbeArgs {
     int dims;
     long long cand_n0[PROBE_CANDS], cand_n1[PROBE_CANDS];   // 0 = unused
     OrderInfo *out;
+    // where lattice plane x sits along x (for the sweep kernel's zero-ahead window)
+    int slab, x0, ghost_lo, n_local_planes;                 // slab geometry (slab = 0: the whole periodic grid)
+    int nx;                                                 // grid planes this context owns
 };
 
 __device__ __forceinline__ void probe_cells(const float *pos, long long p, double units, int dims, int c[3])
@@ -368,6 +340,9 @@ __global__ void __launch_bounds__(1024) order_probe_kernel(ProbeArgs A)
     __shared__ long long s_jmin, s_jmax;
     __shared__ int s_jcount;
     __shared__ long long s_det_n0;
+    __shared__ long long s_lat_n0, s_lat_n1;
+    __shared__ int s_dref, s_dmin, s_dmax, s_dcount;
+    __shared__ long long s_dsum;
     const int tid = threadIdx.x;
     if (tid == 0) {
         s_near = s_tried = s_z = 0;
@@ -463,7 +438,70 @@ __global__ void __launch_bounds__(1024) order_probe_kernel(ProbeArgs A)
                 o.n1 = o.score_x >= 400 ? n1 : 0;
             }
         }
+        o.dx_valid = o.dx_mean = o.dx_dev = 0;
         *A.out = o;
+        s_lat_n0 = o.lattice ? o.n0 : 0;
+        s_lat_n1 = o.lattice ? (o.n1 > 0 ? o.n1 : (n + o.n0 - 1) / o.n0) : 0;
+        s_dref = 0x7fffffff;
+        s_dmin = 0x7fffffff;
+        s_dmax = -0x7fffffff;
+        s_dcount = 0;
+        s_dsum = 0;
+    }
+    __syncthreads();
+    // (3) lattice: offset along x between a particle's (local) grid plane and the plane its lattice
+    // plane is expected at, floor((x_lat + 1/2) * nx / n2): mean and extremes over the samples
+    if (s_lat_n0 == 0)
+        return;
+    const long long per_plane = s_lat_n0 * s_lat_n1;
+    const long long n2 = (n + per_plane - 1) / per_plane;
+    const double planes_per = (double)A.nx / (double)n2;
+    auto offset_of = [&](long long i, int &d) {
+        const AxisCell cx = axis_cell(A.pos[3 * i], A.units, A.dims);
+        if (!cx.ok)
+            return false;
+        int xl = cx.lo;
+        if (A.slab) {
+            xl = slab_plane(cx.lo, A.x0, A.ghost_lo, A.dims);
+            if (xl < 0 || xl >= A.n_local_planes)
+                return false;
+        }
+        d = xl - (int)floor(((double)(i / per_plane) + 0.5) * planes_per);
+        return true;
+    };
+    if (tid == 0) {
+        int d;
+        for (int s = 0; s < 64; s++)
+            if (offset_of(sample_at(s), d)) {
+                s_dref = d;
+                break;
+            }
+    }
+    __syncthreads();
+    if (s_dref == 0x7fffffff)
+        return;
+    for (int s = tid; s < samples && n > 1; s += blockDim.x) {
+        int d;
+        if (!offset_of(sample_at(s), d))
+            continue;
+        d -= s_dref;
+        if (!A.slab) {                                      // periodic: the image nearest to the reference offset
+            if (d > A.dims / 2) d -= A.dims;
+            if (d < -A.dims / 2) d += A.dims;
+        }
+        atomicMin(&s_dmin, d);
+        atomicMax(&s_dmax, d);
+        atomicAdd(&s_dcount, 1);
+        atomicAdd((unsigned long long *)&s_dsum, (unsigned long long)(long long)d);
+    }
+    __syncthreads();
+    if (tid == 0 && s_dcount > 0) {
+        const double mean = (double)s_dsum / (double)s_dcount;
+        const int m = (int)floor(mean + 0.5);
+        A.out->dx_valid = 1;
+        A.out->dx_mean = s_dref + m;
+        const int up = s_dmax - m, down = m - s_dmin;
+        A.out->dx_dev = up > down ? up : down;
     }
 }
 
@@ -501,6 +539,11 @@ int probe_order(genpk_ctx *ctx, const float *pos, int64_t n, double units, Order
         if (long long k = exact_cbrt((long long)n * ctx->g.nranks))      // an x-slab of a cubic lattice
             A.cand_n0[c++] = k;
     A.out = reinterpret_cast<OrderInfo *>(ctx->d_order);
+    A.slab = ctx->g.nranks > 1 ? 1 : 0;
+    A.x0 = ctx->g.x0;
+    A.ghost_lo = ctx->g.ghost_lo;
+    A.n_local_planes = ctx->g.ghost_lo + ctx->g.nx + ctx->g.ghost_hi;
+    A.nx = ctx->g.nx;
     order_probe_kernel<<<1, 1024, 0, ctx->stream>>>(A);
     ctx->launches++;
     GENPK_CUDA_OK(cudaGetLastError());

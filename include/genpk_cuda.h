@@ -50,6 +50,9 @@ extern "C" {
 #define GENPK_DEPOSIT_TILED      3     /* reserved (alias of AUTO)                              */
 #define GENPK_DEPOSIT_MARCH      4     /* lattice-ordered input: neighbour contributions merged in
                                           registers along z, y and x before one red.add per particle */
+#define GENPK_DEPOSIT_SWEEP      5     /* lattice-ordered input: persistent warps sweep the lattice along x; merges in
+                                          registers (y), shared memory (x) and one shuffle (z); clears the grid ahead
+                                          of its own front when it follows genpk_grid_zero (AUTO's choice for lattices) */
 #define GENPK_OPT_SCALE_BITS     2     /* fixed-point mode: q = llrint(w * 2^bits), default 40 */
 /* Lattice hint for GENPK_DEPOSIT_MARCH / AUTO: particle p sits near lattice site
  * (ix,iy,iz) with p = (ix*N1 + iy)*N0 + iz.  0 = let the order probe find it.  Only
@@ -58,6 +61,15 @@ extern "C" {
 #define GENPK_OPT_LATTICE_N1     5
 #define GENPK_OPT_MARCH_RY       6     /* lattice rows one warp marches over (default 8)   */
 #define GENPK_OPT_MARCH_RX       7     /* lattice planes one warp marches over (default 8) */
+#define GENPK_OPT_SWEEP         11     /* 1 (default): AUTO uses the sweep kernel for lattice input; 0: the march kernel */
+#define GENPK_OPT_SWEEP_RY      12     /* lattice rows per sweep column (0 = as few as keep all columns resident) */
+#define GENPK_OPT_ZERO_AHEAD    13     /* 1 (default): genpk_grid_zero is carried out lazily, and by the sweep kernel itself
+                                          (first-touch zeroing ahead of its front) when a lattice deposit follows; 0: memset */
+#define GENPK_OPT_ZA_WINDOW     14     /* zero ahead: grid planes past a lattice plane's expected position that are kept
+                                          clear (0 = from the displacements the order probe saw).  Performance only:
+                                          particles displaced further are deposited by a clean-up pass */
+#define GENPK_OPT_ZA_SLACK      15     /* zero ahead: lattice planes between clearing a grid plane and first needing it */
+#define GENPK_OPT_ZA_DEFERRED   16     /* zero ahead: clean-up list entries per sweep column (default 4096) */
 /* ---- binning pass selection (genpk_set_option(ctx, GENPK_OPT_POWER, v)) ------------ */
 #define GENPK_OPT_POWER          3
 #define GENPK_POWER_CACHED       0     /* sum|k| and mode counts per bin depend on the grid only: computed
@@ -119,14 +131,19 @@ int genpk_set_stream(genpk_ctx *ctx, void *cuda_stream);
 int genpk_set_option(genpk_ctx *ctx, int option, int64_t value);
 int genpk_synchronize(genpk_ctx *ctx);
 
-/* memset(field,0,...) of gen-pk.cpp:208 for grid `which` (0 or 1). */
+/* memset(field,0,...) of gen-pk.cpp:208 for grid `which` (0 or 1).  Carried out lazily (see
+ * GENPK_OPT_ZERO_AHEAD): observable behaviour is that of an immediate memset. */
 int genpk_grid_zero(genpk_ctx *ctx, int which);
 
 /* fieldize() into the resident grid `which`; additive across calls until the
  * next genpk_grid_zero (chunk loop read_fieldize.cpp:51-93; stars into baryons
- * gen-pk.cpp:228-230).  positions/masses are host pointers when on_device==0
- * (copied through an internal pinned double buffer) or device pointers when
- * on_device!=0.  masses may be NULL (constant `mass`). */
+ * gen-pk.cpp:228-230).  positions/masses are host pointers when on_device==0 or device
+ * pointers when on_device!=0.  Host arrays go up in chunks of 2^23 particles straight from
+ * the caller's memory on a copy stream, double-buffered on the device so that chunk k+1
+ * uploads while chunk k is deposited (pin the arrays -- cudaHostAlloc / cudaHostRegister --
+ * to get the overlap; pageable memory is staged by the driver); every upload has completed
+ * when the call returns, so the arrays may be reused at once.  masses may be NULL (constant
+ * `mass`). */
 int genpk_deposit(genpk_ctx *ctx, int which, const float *positions, const float *masses,
                   int64_t n, double mass, double boxsize, int on_device);
 
@@ -199,6 +216,9 @@ int64_t genpk_launch_count(const genpk_ctx *ctx);
 /* Verdict of the last order probe of this context: {coherent, lattice, n0, n1,
  * score_z, score_y, score_x} (scores per mille; diagnostics for the bench line). */
 int genpk_last_order(const genpk_ctx *ctx, int64_t out[7]);
+/* The last sweep deposit of this context: {rows per column, columns (= warps), zero ahead used (0/1),
+ * zero-ahead window in planes}. */
+int genpk_last_sweep(const genpk_ctx *ctx, int64_t out[4]);
 
 /* ================= 3. slab stages for the multi-GPU pipeline ======================== */
 /* Rank `rank` of `nranks` owns x-planes [rank*dims/nranks, (rank+1)*dims/nranks)

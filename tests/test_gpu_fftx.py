@@ -17,11 +17,15 @@ def _particles(n, box, seed, var_mass=False):
     return pos, masses
 
 
-def test_fused_vs_oracle_256(port):
+def test_fused_vs_oracle_256(ref, port):
+    """The fused path against the reference's own object code (oracle/_ref) and the C restatement."""
     dims, box, n = 256, 500.0, 300000
     pos, masses = _particles(n, box, 5, True)
     tm = float(masses.astype(np.float64).sum())
-    _, pr, cr, kr = port.pk(box, dims, pos, masses, 1.0, tm, dims)
+    _, pr, cr, kr = ref.pk(box, dims, pos, masses, 1.0, tm, dims)
+    _, pp, cp, kp = port.pk(box, dims, pos, masses, 1.0, tm, dims)
+    assert np.array_equal(cp, cr)
+    np.testing.assert_allclose(pp[cr > 0], pr[cr > 0], rtol=1e-9, atol=0)
     with gp.Context(dims) as ctx:
         assert ctx.fused_xpass_supported(dims)
         launches0 = ctx.launch_count()

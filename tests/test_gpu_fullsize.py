@@ -1,0 +1,204 @@
+"""Parity on the BASELINE configs at their FULL sizes, through the default product path
+(order probe -> lattice-march deposit -> cuFFT z pass -> own y pass -> fused x pass + binning).
+
+C2 (256^3 uniform-random particles -> 512^3) and C3 (1024^3 Zel'dovich-displaced particles
+-> 1024^3, the benchmarked config) are put next to the reference's own object code
+(oracle/_ref: fieldize.cpp, powerspectrum.c compiled unmodified; FFT = pocketfft stand-in):
+mode counts bit-exact (and equal to the committed golden table), the density grid within
+relative 1e-6, P(k) and k_eff within relative 1e-5 (north_star tolerances).  The particles are
+generated on the device and copied to the host, so both sides see the same float32 bits.
+
+When the reference objects are not on the box the same assertions run against the committed
+fixture tests/golden/fullsize_pk.npz, which tests/golden/make_golden_fullsize.py produced
+from the reference objects on a B200 box.
+"""
+import json
+import os
+import time
+
+import numpy as np
+import pytest
+
+import genpk_b200 as gp
+from genpk_b200 import api
+from oracle.oracle import padded_shape
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+BOX = 1000.0
+
+
+def _mem_available_gb():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable"):
+                return int(line.split()[1]) / 2 ** 20
+    except OSError:
+        pass
+    return 0.0
+
+
+def _synth(kind, n_side, dims):
+    import torch
+    n = n_side ** 3
+    dpos = torch.empty(3 * n, dtype=torch.float32, device="cuda")
+    api.synth_particles_dev(kind, 42, n_side, 0, n, BOX, dims, dpos.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    return dpos
+
+
+def _grid_close(ours, ref, rtol=1e-6):
+    """|ours - ref| <= rtol*|ref| + rtol*mean(ref), evaluated plane by plane (8.6 GB arrays)."""
+    mean = float(ref[0].mean())                                               # the field is statistically uniform
+    worst = 0.0
+    for x in range(ref.shape[0]):
+        a, b = ours[x], ref[x]
+        err = np.abs(a - b) - rtol * np.abs(b)
+        worst = max(worst, float(err.max()))
+    assert worst <= rtol * mean, f"density grid differs from the reference: excess {worst:.3e} (floor {rtol * mean:.3e})"
+
+
+def _ours(dpos, n, dims, keep_grid, flags=0):
+    with gp.Context(dims, 0, flags) as ctx:
+        launches0 = ctx.launch_count()
+        ctx.grid_zero()
+        ctx.deposit_dev(dpos.data_ptr(), n, 0, 1.0, BOX)
+        grid = ctx.grid_download().reshape(padded_shape(dims)) if keep_grid else None
+        assert ctx.fused_xpass_supported(dims), "the default path must be the fused one at this size"
+        p, c, k = ctx.fft_power(dims, float(n), float(n))
+        ctx.synchronize()
+        order = ctx.last_order()
+        assert ctx.launch_count() - launches0 >= 3
+    return grid, p, c, k, order
+
+
+def _golden_full(name):
+    path = os.path.join(GOLD, "fullsize_pk.npz")
+    if not os.path.exists(path):
+        return None
+    g = np.load(path)
+    if f"{name}_power" not in g.files:
+        return None
+    return {k: g[f"{name}_{k}"] for k in ("power", "count", "keffs")}
+
+
+def _check_pk(p, c, k, pr, cr, kr, label):
+    assert np.array_equal(c.astype(np.int64), np.asarray(cr, np.int64)), f"{label}: mode counts differ"
+    nz = np.asarray(cr) > 0
+    np.testing.assert_allclose(p[nz], pr[nz], rtol=1e-5, atol=0, err_msg=f"{label}: P(k)")
+    np.testing.assert_allclose(k[nz], kr[nz], rtol=1e-5, atol=0, err_msg=f"{label}: k_eff")
+
+
+def test_c2_full_vs_reference(ref):
+    """BASELINE configs[1] at full size: P(k), k_eff, counts and the grid against the reference objects."""
+    n_side, dims = 256, 512
+    n = n_side ** 3
+    gold = np.load(os.path.join(GOLD, "mode_counts.npz"))
+    dpos = _synth(api.SYNTH_UNIFORM_RANDOM, n_side, dims)
+    grid, p, c, k, order = _ours(dpos, n, dims, True)
+    pos = dpos.cpu().numpy()
+    field, pr, cr, kr = ref.pk(BOX, dims, pos, None, 1.0, float(n), dims)
+    assert np.array_equal(c.astype(np.int64), gold["count512"])
+    _check_pk(p, c, k, pr, cr, kr, "C2 vs reference objects")
+    _grid_close(grid, field)
+
+
+def test_c2_full_vs_golden():
+    n_side, dims = 256, 512
+    g = _golden_full("c2")
+    if g is None:
+        pytest.skip("tests/golden/fullsize_pk.npz has no C2 entry")
+    dpos = _synth(api.SYNTH_UNIFORM_RANDOM, n_side, dims)
+    _, p, c, k, _ = _ours(dpos, n_side ** 3, dims, False)
+    _check_pk(p, c, k, g["power"], g["count"], g["keffs"], "C2 vs committed reference fixture")
+
+
+def test_c3_full_vs_golden():
+    """The benchmarked config against the committed fixture (made from the reference objects on a
+    B200 box by tests/golden/make_golden_fullsize.py): no CPU run, seconds."""
+    n_side = dims = 1024
+    g = _golden_full("c3")
+    if g is None:
+        pytest.skip("tests/golden/fullsize_pk.npz has no C3 entry")
+    gold = np.load(os.path.join(GOLD, "mode_counts.npz"))
+    dpos = _synth(api.SYNTH_CLUSTERED, n_side, dims)
+    _, p, c, k, order = _ours(dpos, n_side ** 3, dims, False)
+    assert order["lattice"] == 1, "C3 must take the lattice-march deposit"
+    assert np.array_equal(c.astype(np.int64), gold["count1024"])
+    _check_pk(p, c, k, g["power"], g["count"], g["keffs"], "C3 vs committed reference fixture")
+    # fixed-point accumulation: same spectrum (the grid differs by < 2^-40 per contribution)
+    _, pf, cf, kf, _ = _ours(dpos, n_side ** 3, dims, False, api.FLAG_FIXED_POINT)
+    _check_pk(pf, cf, kf, g["power"], g["count"], g["keffs"], "C3 fixed point vs committed reference fixture")
+
+
+def test_c3_full_vs_reference(ref):
+    """BASELINE configs[2] -- the benchmarked config -- at full size against the reference's object
+    code: 1024^3 device-generated particles copied to the host (12.9 GB), fieldize + powerspectrum
+    from oracle/_ref (about 30 GB of host memory and a minute or two of CPU time)."""
+    if _mem_available_gb() < 60:
+        pytest.skip("needs about 60 GB of free host memory")
+    n_side = dims = 1024
+    n = n_side ** 3
+    gold = np.load(os.path.join(GOLD, "mode_counts.npz"))
+    dpos = _synth(api.SYNTH_CLUSTERED, n_side, dims)
+    grid, p, c, k, order = _ours(dpos, n, dims, True)
+    assert order["lattice"] == 1, "C3 must take the lattice-march deposit"
+    assert np.array_equal(c.astype(np.int64), gold["count1024"])
+    pos = dpos.cpu().numpy()
+    del dpos
+    from oracle.oracle import rfftn_padded
+    t0 = time.perf_counter()
+    field = np.zeros(padded_shape(dims), np.float64)
+    ref.fieldize(BOX, dims, field, pos, None, 1.0, 1)
+    t1 = time.perf_counter()
+    del pos
+    _grid_close(grid, field)
+    assert abs(float(grid[:, :, :dims].sum()) / n - 1.0) < 1e-9
+    del grid
+    t2 = time.perf_counter()
+    spec = rfftn_padded(field, dims)
+    t3 = time.perf_counter()
+    del field
+    rc, pr, cr, kr = ref.powerspectrum(dims, spec, None, dims, float(n), float(n))
+    t4 = time.perf_counter()
+    assert rc == 0
+    _check_pk(p, c, k, pr, cr, kr, "C3 vs reference objects")
+    # the reference's own timings at the full benchmarked size, for the record (profiles/)
+    out = os.path.join(os.path.dirname(GOLD), "..", "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "c3_cpu_full_size.json"), "w") as f:
+            json.dump({"config": "1024^3 clustered -> 1024^3, reference objects (oracle/_ref), FFT = pocketfft stand-in",
+                       "threads": len(os.sched_getaffinity(0)), "deposit_s": t1 - t0, "fft_s": t3 - t2,
+                       "binning_s": t4 - t3, "total_s": (t1 - t0) + (t3 - t2) + (t4 - t3),
+                       "mparticles_per_s": n / ((t1 - t0) + (t3 - t2) + (t4 - t3)) / 1e6}, f)
+    except OSError:
+        pass
+
+
+def test_c5_slab_block_counts_golden():
+    """count2048 / ksum2048 of the golden table against the geometry pass of the fused slab path:
+    the eight ky blocks of a 2048^3 spectrum, binned block by block as the 8-GPU pipeline does."""
+    import torch
+    dims, P = 2048, 8
+    gold = np.load(os.path.join(GOLD, "mode_counts.npz"))
+    dev = torch.device("cuda", 0)
+    tot = np.zeros((3, dims))
+    for rank in range(P):
+        ctx = api.Context(dims, 0, 0, P, rank)
+        try:
+            ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+            nd = ctx.slab_spectrum_bytes() // 8
+            spec = torch.zeros(nd, dtype=torch.float64, device=dev)
+            sums = torch.zeros(3 * dims, dtype=torch.float64, device=dev)
+            ctx.slab_fftx_power_partial(spec.data_ptr(), dims, sums.data_ptr())
+            torch.cuda.synchronize()
+            tot += sums.cpu().numpy().reshape(3, dims)
+            del spec
+        finally:
+            ctx.close()
+    assert np.array_equal(tot[2].astype(np.int64), gold["count2048"])
+    assert int(tot[2].sum()) == dims ** 3 - 1
+    nz = gold["count2048"] > 0
+    np.testing.assert_allclose(tot[1][nz], gold["ksum2048"][nz], rtol=1e-12)
+    assert not tot[0].any()
