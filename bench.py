@@ -59,6 +59,8 @@ def parse_args():
     ap.add_argument("--za-window", type=int, default=0, help="zero ahead: planes kept clear past the expected plane (0 = from the probe)")
     ap.add_argument("--za-slack", type=int, default=-1)
     ap.add_argument("--sweep-ry", type=int, default=0)
+    ap.add_argument("--sweep-couple", type=int, default=-1, help="planes a sweep warp may lead the slowest one by (0 = uncoupled)")
+    ap.add_argument("--za-zero-ctas", type=int, default=0)
     ap.add_argument("--no-self-check", action="store_true", help="skip the comparison with the committed reference fixtures")
     ap.add_argument("--power", default="cached", choices=["cached", "fused"],
                     help="binning pass: geometry sums cached in the context, or recomputed every call")
@@ -415,6 +417,10 @@ def run_ours(args):
         ctx.set_option(api.OPT_ZA_SLACK, args.za_slack)
     if args.sweep_ry:
         ctx.set_option(api.OPT_SWEEP_RY, args.sweep_ry)
+    if args.sweep_couple >= 0:
+        ctx.set_option(api.OPT_SWEEP_COUPLE, args.sweep_couple)
+    if args.za_zero_ctas:
+        ctx.set_option(api.OPT_ZA_ZERO_CTAS, args.za_zero_ctas)
     if args.march_ry:
         ctx.set_option(api.OPT_MARCH_RY, args.march_ry)
     if args.march_rx:

@@ -67,6 +67,11 @@ SIGNATURES = {
     "genpk_route_particles": (C.c_int, [C.c_void_p, c_f32p, c_f32p, C.c_int64, C.c_double, c_f32p, c_f32p, c_i64p]),
     "genpk_ghost_ptr": (C.c_void_p, [C.c_void_p, C.c_int, C.POINTER(C.c_size_t)]),
     "genpk_ghost_accumulate": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "genpk_ipc_export_grid": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "genpk_slab_set_grid_peer": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "genpk_ghost_pull_ready": (C.c_int, [C.c_void_p, C.c_int]),
+    "genpk_ghost_pull": (C.c_int, [C.c_void_p, C.c_int]),
+    "genpk_rejected_to": (C.c_int, [C.c_void_p, C.c_void_p]),
     "genpk_slab_fft_yz": (C.c_int, [C.c_void_p, C.c_int]),
     "genpk_slab_pack": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "genpk_slab_fft_x": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -87,8 +87,12 @@ static genpk_ctx *create_common(int dims, int device, int nranks, int rank, unsi
     g.fd = 2 * g.nc;
     const int ngrids = (flags & GENPK_FLAG_TWO_FIELDS) ? 2 : 1;
     bool ok = true;
-    for (int i = 0; i < ngrids && ok; i++)
-        ok = cudaMalloc(&ctx->grid[i], g.grid_doubles() * sizeof(double)) == cudaSuccess;
+    for (int i = 0; i < ngrids && ok; i++) {
+        ok = cudaMalloc(&ctx->grid[i], g.grid_doubles() * sizeof(double) + GRID_TAIL_BYTES) == cudaSuccess;
+        // touched-plane range: "every plane" until a deposit that tracks it says otherwise
+        const int full[2] = {0, g.ghost_lo + g.nx + g.ghost_hi - 1};
+        ok = ok && cudaMemcpy(ctx->grid[i] + g.grid_doubles(), full, sizeof(full), cudaMemcpyHostToDevice) == cudaSuccess;
+    }
     ok = ok && cudaMalloc(&ctx->d_errors, sizeof(unsigned long long)) == cudaSuccess;
     ok = ok && cudaMemset(ctx->d_errors, 0, sizeof(unsigned long long)) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
@@ -156,6 +160,13 @@ void genpk_destroy(genpk_ctx *ctx)
     if (ctx->d_twiddle) cudaFree(ctx->d_twiddle);
     for (int r = 0; r < GENPK_MAX_PEERS; r++)
         if (ctx->peer_opened[r] && ctx->peer_recv[r]) cudaIpcCloseMemHandle(ctx->peer_recv[r]);
+    for (int w = 0; w < 2; w++)
+        for (int side = 0; side < 2; side++)
+            if (ctx->grid_peer_opened[w][side] && ctx->grid_peer[w][side]) {
+                // the same allocation may be mapped for both sides (two ranks): close it once
+                if (side == 1 && ctx->grid_peer[w][0] == ctx->grid_peer[w][1] && ctx->grid_peer_opened[w][0]) continue;
+                cudaIpcCloseMemHandle(ctx->grid_peer[w][side]);
+            }
     if (ctx->d_recv) cudaFree(ctx->d_recv);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (int i = 0; i < ST_COUNT; i++)
@@ -237,6 +248,14 @@ int genpk_set_option(genpk_ctx *ctx, int option, int64_t value)
         if (value < 0 || value > 64) break;
         ctx->za_slack = (int)value;
         return 0;
+    case GENPK_OPT_ZA_ZERO_CTAS:
+        if (value < 0 || value > 1024) break;
+        ctx->za_zero_ctas = (int)value;
+        return 0;
+    case GENPK_OPT_SWEEP_COUPLE:
+        if (value < 0 || value > 4096) break;
+        ctx->sweep_couple = (int)value;
+        return 0;
     case GENPK_OPT_ZA_DEFERRED:
         if (value < 1 || value > (1 << 20)) break;
         ctx->za_def_per_col = (int)value;
@@ -257,6 +276,21 @@ int genpk_synchronize(genpk_ctx *ctx)
         set_error("%llu particles rejected (non-finite position, or outside this rank's x-slab)", bad);
         return 3;
     }
+    return 0;
+}
+
+__global__ void rejected_to_kernel(unsigned long long *errors, double *dst)
+{
+    *dst = (double)*errors;
+    *errors = 0ull;
+}
+
+int genpk_rejected_to(genpk_ctx *ctx, double *dst_dev)
+{
+    if (!ctx || !dst_dev) { set_error("genpk_rejected_to: bad arguments"); return 1; }
+    rejected_to_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d_errors, dst_dev);
+    ctx->launches++;
+    GENPK_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
@@ -413,14 +447,10 @@ int genpk_deposit(genpk_ctx *ctx, int which, const float *positions, const float
     if (!check_which(ctx, which, "genpk_deposit")) return 1;
     if (n < 0 || (n > 0 && !positions)) { set_error("genpk_deposit: bad particle array"); return 1; }
     if (n == 0) return 0;
-    stage_begin(ctx, ST_DEPOSIT);
-    int rc = 0;
+    StageScope scope(ctx, ST_DEPOSIT);
     if (on_device)
-        rc = deposit_device(ctx, which, positions, masses, n, mass, boxsize);      // one launch over the resident set
-    else
-        rc = deposit_chunks(ctx, which, positions, false, masses, n, mass, boxsize, 0);
-    stage_end(ctx, ST_DEPOSIT);
-    return rc;
+        return deposit_device(ctx, which, positions, masses, n, mass, boxsize);        // one launch over the resident set
+    return deposit_chunks(ctx, which, positions, false, masses, n, mass, boxsize, 0);
 }
 
 int genpk_deposit_f64(genpk_ctx *ctx, int which, const double *positions, const float *masses, int64_t n, double mass,
@@ -429,10 +459,8 @@ int genpk_deposit_f64(genpk_ctx *ctx, int which, const double *positions, const 
     if (!check_which(ctx, which, "genpk_deposit_f64")) return 1;
     if (n < 0 || (n > 0 && !positions)) { set_error("genpk_deposit_f64: bad particle array"); return 1; }
     if (n == 0) return 0;
-    stage_begin(ctx, ST_DEPOSIT);
-    const int rc = deposit_chunks(ctx, which, positions, true, masses, n, mass, boxsize, on_device);
-    stage_end(ctx, ST_DEPOSIT);
-    return rc;
+    StageScope scope(ctx, ST_DEPOSIT);
+    return deposit_chunks(ctx, which, positions, true, masses, n, mass, boxsize, on_device);
 }
 
 int genpk_fft(genpk_ctx *ctx, int which)
@@ -442,10 +470,11 @@ int genpk_fft(genpk_ctx *ctx, int which)
         set_error("genpk_fft: slab contexts use genpk_slab_fft_yz / genpk_slab_pack / genpk_slab_fft_x");
         return 1;
     }
-    stage_begin(ctx, ST_FFT);
-    if (int rc = fixed_to_double(ctx, which)) return rc;
-    if (int rc = fft_3d(ctx, which)) return rc;
-    stage_end(ctx, ST_FFT);
+    {
+        StageScope scope(ctx, ST_FFT);
+        if (int rc = fixed_to_double(ctx, which)) return rc;
+        if (int rc = fft_3d(ctx, which)) return rc;
+    }
     return 0;
 }
 
@@ -473,9 +502,10 @@ static int power_on(genpk_ctx *ctx, const double *spec_a, const double *spec_b, 
     if (nrbins < 1 || !power || !count || !keffs) { set_error("genpk_power: bad arguments"); return 1; }
     if (ctx->g.nranks != 1) { set_error("genpk_power: slab contexts use genpk_slab_power_partial"); return 1; }
     if (int rc = ensure_tables(ctx, nrbins)) return rc;
-    stage_begin(ctx, ST_POWER);
-    if (int rc = power_raw(ctx, spec_a, spec_b, ctx->g.dims, 0, ctx->g.dims, 0, nrbins, ctx->d_sums)) return rc;
-    stage_end(ctx, ST_POWER);
+    {
+        StageScope scope(ctx, ST_POWER);
+        if (int rc = power_raw(ctx, spec_a, spec_b, ctx->g.dims, 0, ctx->g.dims, 0, nrbins, ctx->d_sums)) return rc;
+    }
     GENPK_CUDA_OK(cudaMemcpyAsync(ctx->h_sums, ctx->d_sums, (size_t)3 * nrbins * sizeof(double), cudaMemcpyDeviceToHost,
                                   ctx->stream));
     GENPK_CUDA_OK(cudaStreamSynchronize(ctx->stream));
@@ -511,13 +541,15 @@ int genpk_fft_power(genpk_ctx *ctx, int which, int nrbins, double *power, int *c
         return genpk_power(ctx, which, which, nrbins, power, count, keffs, total_mass, total_mass2);
     }
     if (int rc = ensure_tables(ctx, nrbins)) return rc;
-    stage_begin(ctx, ST_FFT);
-    if (int rc = fixed_to_double(ctx, which)) return rc;
-    if (int rc = fft_yz(ctx, which)) return rc;
-    stage_end(ctx, ST_FFT);
-    stage_begin(ctx, ST_POWER);
-    if (int rc = fftx_power_raw(ctx, ctx->grid[which], ctx->g.dims, 0, nrbins, ctx->d_sums)) return rc;
-    stage_end(ctx, ST_POWER);
+    {
+        StageScope scope(ctx, ST_FFT);
+        if (int rc = fixed_to_double(ctx, which)) return rc;
+        if (int rc = fft_yz(ctx, which)) return rc;
+    }
+    {
+        StageScope scope(ctx, ST_POWER);
+        if (int rc = fftx_power_raw(ctx, ctx->grid[which], ctx->g.dims, 0, nrbins, ctx->d_sums)) return rc;
+    }
     GENPK_CUDA_OK(cudaMemcpyAsync(ctx->h_sums, ctx->d_sums, (size_t)3 * nrbins * sizeof(double), cudaMemcpyDeviceToHost,
                                   ctx->stream));
     GENPK_CUDA_OK(cudaStreamSynchronize(ctx->stream));
@@ -683,13 +715,71 @@ int genpk_ghost_accumulate(genpk_ctx *ctx, int which, const void *recv_plane_dev
     return genpk_ghost_side_accumulate(ctx, which, 0, recv_plane_dev);
 }
 
+/* ---- ghost exchange by peer loads ---- */
+
+int genpk_ipc_export_grid(genpk_ctx *ctx, int which, void *handle_out)
+{
+    if (!check_which(ctx, which, "genpk_ipc_export_grid")) return 1;
+    if (!handle_out) { set_error("genpk_ipc_export_grid: null handle"); return 1; }
+    cudaIpcMemHandle_t h;
+    GENPK_CUDA_OK(cudaIpcGetMemHandle(&h, ctx->grid[which]));
+    memcpy(handle_out, &h, sizeof(h));
+    return 0;
+}
+
+int genpk_slab_set_grid_peer(genpk_ctx *ctx, int which, int side, const void *ipc_handle, void *same_process_ptr)
+{
+    if (!check_which(ctx, which, "genpk_slab_set_grid_peer")) return 1;
+    if (side < 0 || side > 1 || (!ipc_handle && !same_process_ptr)) { set_error("genpk_slab_set_grid_peer: bad arguments"); return 1; }
+    if (ctx->grid_peer_opened[which][side] && ctx->grid_peer[which][side] &&
+        !(ctx->grid_peer[which][side ^ 1] == ctx->grid_peer[which][side] && ctx->grid_peer_opened[which][side ^ 1]))
+        cudaIpcCloseMemHandle(ctx->grid_peer[which][side]);
+    ctx->grid_peer[which][side] = nullptr;
+    ctx->grid_peer_opened[which][side] = false;
+    if (same_process_ptr) {
+        ctx->grid_peer[which][side] = same_process_ptr;
+        return 0;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle, sizeof(h));
+    // two ranks: both neighbours are the same peer, and a handle can be opened only once per process
+    if (ctx->grid_peer_opened[which][side ^ 1] && ctx->grid_peer[which][side ^ 1] &&
+        memcmp(&h, ctx->grid_peer_handle[which][side ^ 1], sizeof(h)) == 0) {
+        ctx->grid_peer[which][side] = ctx->grid_peer[which][side ^ 1];
+        ctx->grid_peer_opened[which][side] = true;
+        memcpy(ctx->grid_peer_handle[which][side], &h, sizeof(h));
+        return 0;
+    }
+    void *p = nullptr;
+    GENPK_CUDA_OK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->grid_peer[which][side] = p;
+    ctx->grid_peer_opened[which][side] = true;
+    memcpy(ctx->grid_peer_handle[which][side], &h, sizeof(h));
+    return 0;
+}
+
+int genpk_ghost_pull_ready(const genpk_ctx *ctx, int which)
+{
+    if (!ctx || which < 0 || which > 1 || ctx->g.nranks < 2) return 0;
+    return ctx->grid_peer[which][0] && (ctx->g.ghost_lo == 0 || ctx->grid_peer[which][1]) ? 1 : 0;
+}
+
+int genpk_ghost_pull(genpk_ctx *ctx, int which)
+{
+    if (!check_which(ctx, which, "genpk_ghost_pull")) return 1;
+    if (!genpk_ghost_pull_ready(ctx, which)) { set_error("genpk_ghost_pull: the neighbours' grids are not mapped"); return 1; }
+    if (int rc = materialize_zero(ctx, which)) return rc;
+    return ghost_pull(ctx, which);
+}
+
 int genpk_slab_fft_yz(genpk_ctx *ctx, int which)
 {
     if (!check_which(ctx, which, "genpk_slab_fft_yz")) return 1;
-    stage_begin(ctx, ST_FFT);
-    if (int rc = fixed_to_double(ctx, which)) return rc;
-    if (int rc = fft_yz(ctx, which)) return rc;
-    stage_end(ctx, ST_FFT);
+    {
+        StageScope scope(ctx, ST_FFT);
+        if (int rc = fixed_to_double(ctx, which)) return rc;
+        if (int rc = fft_yz(ctx, which)) return rc;
+    }
     return 0;
 }
 
@@ -719,11 +809,12 @@ int genpk_slab_power_partial(genpk_ctx *ctx, const void *spec_a_dev, const void 
 {
     if (!ctx || !spec_a_dev || !sums_dev || nrbins < 1) { set_error("genpk_slab_power_partial: bad arguments"); return 1; }
     const int ny = ctx->g.dims / ctx->g.nranks;
-    stage_begin(ctx, ST_POWER);
-    if (int rc = power_raw(ctx, (const double *)spec_a_dev, (const double *)(spec_b_dev ? spec_b_dev : spec_a_dev),
-                           ctx->g.dims, 0, ny, ctx->g.rank * ny, nrbins, sums_dev))
-        return rc;
-    stage_end(ctx, ST_POWER);
+    {
+        StageScope scope(ctx, ST_POWER);
+        if (int rc = power_raw(ctx, (const double *)spec_a_dev, (const double *)(spec_b_dev ? spec_b_dev : spec_a_dev),
+                               ctx->g.dims, 0, ny, ctx->g.rank * ny, nrbins, sums_dev))
+            return rc;
+    }
     return 0;
 }
 
@@ -731,11 +822,12 @@ int genpk_slab_fftx_power_partial(genpk_ctx *ctx, const void *spec_yz_dev, int n
 {
     if (!ctx || !spec_yz_dev || !sums_dev || nrbins < 1) { set_error("genpk_slab_fftx_power_partial: bad arguments"); return 1; }
     const int ny = ctx->g.dims / ctx->g.nranks;
-    stage_begin(ctx, ST_POWER);
-    // the library-owned transposed block (filled by genpk_slab_fft_yz_scatter) has padded rows
-    const int pitch = spec_yz_dev == ctx->d_recv ? recv_row_pitch(ctx) : 0;
-    if (int rc = fftx_power_raw(ctx, (const double *)spec_yz_dev, ny, ctx->g.rank * ny, nrbins, sums_dev, pitch)) return rc;
-    stage_end(ctx, ST_POWER);
+    {
+        StageScope scope(ctx, ST_POWER);
+        // the library-owned transposed block (filled by genpk_slab_fft_yz_scatter) has padded rows
+        const int pitch = spec_yz_dev == ctx->d_recv ? recv_row_pitch(ctx) : 0;
+        if (int rc = fftx_power_raw(ctx, (const double *)spec_yz_dev, ny, ctx->g.rank * ny, nrbins, sums_dev, pitch)) return rc;
+    }
     return 0;
 }
 
@@ -802,11 +894,12 @@ int genpk_slab_fft_yz_scatter(genpk_ctx *ctx, int which)
 {
     if (!check_which(ctx, which, "genpk_slab_fft_yz_scatter")) return 1;
     if (!genpk_slab_scatter_supported(ctx)) { set_error("genpk_slab_fft_yz_scatter: unsupported geometry"); return 1; }
-    stage_begin(ctx, ST_FFT);
-    if (int rc = fixed_to_double(ctx, which)) return rc;
-    if (int rc = fft_z_rows(ctx, which)) return rc;
-    if (int rc = fft_cols_y_scatter(ctx, ctx->grid[which] + ctx->g.owned_offset(), ctx->g.nx)) return rc;
-    stage_end(ctx, ST_FFT);
+    {
+        StageScope scope(ctx, ST_FFT);
+        if (int rc = fixed_to_double(ctx, which)) return rc;
+        if (int rc = fft_z_rows(ctx, which)) return rc;
+        if (int rc = fft_cols_y_scatter(ctx, ctx->grid[which] + ctx->g.owned_offset(), ctx->g.nx)) return rc;
+    }
     return 0;
 }
 

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cufft.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdint.h>
 #include <stddef.h>
 #include <string>
@@ -61,6 +62,7 @@ struct SlabGeom {
     size_t owned_offset() const { return plane() * (size_t)ghost_lo; }    // first owned plane inside the allocation
 };
 
+constexpr size_t GRID_TAIL_BYTES = 256;
 enum Stage { ST_DEPOSIT = 0, ST_FFT = 1, ST_POWER = 2, ST_SORT = 3, ST_ZERO = 4, ST_COUNT = 5 };
 
 }  // namespace genpk
@@ -76,8 +78,14 @@ struct genpk_ctx {
     int scale_bits = 40;
     int deposit_mode = GENPK_DEPOSIT_AUTO;
 
+    // each grid allocation ends with GRID_TAIL_BYTES of bookkeeping that travels with its IPC handle:
+    // int32 {lowest, highest} local x plane written since the grid was cleared (slab contexts)
     double *grid[2] = {nullptr, nullptr};
     bool grid_is_fixed[2] = {false, false};   // grid currently holds int64 fixed-point sums
+    // ghost exchange by peer loads: the ring neighbours' grid allocations ([which][0]: rank-1, [1]: rank+1)
+    void *grid_peer[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    bool grid_peer_opened[2][2] = {{false, false}, {false, false}};
+    unsigned char grid_peer_handle[2][2][64] = {};
 
     // cuFFT
     cufftHandle plan3d = 0, plan_yz = 0, plan_x = 0, plan_z = 0;
@@ -122,7 +130,9 @@ struct genpk_ctx {
     int zero_ahead = 1;                       // genpk_grid_zero is lazy; a sweep that follows clears the grid ahead of its front
     int za_window = 0;                        // planes ahead of the expected plane kept clear (0: from the order probe)
     int za_slack = 2;                         // lattice planes between clearing a plane and first needing it
-    int za_def_per_col = 4096;                // deferred-particle list entries per column
+    int za_def_per_col = 4096;                // deferred-particle list entries per list
+    int za_zero_ctas = 0;                     // CTAs that only clear planes (0: a third of the SM count)
+    int sweep_couple = 6;                     // a warp starts lattice plane x once every warp has started x - couple (0: uncoupled)
     unsigned *d_za_zdone = nullptr;
     int za_zdone_cap = 0;
     unsigned *d_za_def = nullptr;
@@ -189,16 +199,41 @@ void fft_release(genpk_ctx *ctx);
 int route_particles(genpk_ctx *ctx, const float *pos, const float *mass, int64_t n, double boxsize,
                     float *spos, float *smass, int64_t *counts);
 int ghost_accumulate(genpk_ctx *ctx, int which, int side, const void *recv);
+int ghost_pull(genpk_ctx *ctx, int which);
+int touched_set(genpk_ctx *ctx, int which, int lo, int hi);      // stream-ordered write of the touched-plane range
+inline int *touched_ptr(genpk_ctx *ctx, int which)
+{
+    return reinterpret_cast<int *>(ctx->grid[which] + ctx->g.grid_doubles());
+}
 int slab_pack(genpk_ctx *ctx, int which, void *send);
 
+// A stage = one CUDA-event pair on the context's stream (summed on request) and one NVTX range on the
+// calling thread (genpk:deposit, genpk:fft, ... in a timeline; header-only NVTX, a no-op without a tool).
+inline const char *stage_name(int st)
+{
+    static const char *const names[ST_COUNT] = {"genpk:deposit", "genpk:fft", "genpk:power", "genpk:sort", "genpk:zero"};
+    return st >= 0 && st < ST_COUNT ? names[st] : "genpk:?";
+}
 inline void stage_begin(genpk_ctx *ctx, int st)
 {
+    nvtxRangePushA(stage_name(st));
     cudaEventRecord(ctx->ev_begin[st][ctx->ev_count[st] % genpk_ctx::EV_SLOTS], ctx->stream);
 }
 inline void stage_end(genpk_ctx *ctx, int st)
 {
     cudaEventRecord(ctx->ev_end[st][ctx->ev_count[st] % genpk_ctx::EV_SLOTS], ctx->stream);
     ctx->ev_count[st]++;
+    nvtxRangePop();
 }
+
+// scope form: the range and the event pair close on every return path
+struct StageScope {
+    genpk_ctx *ctx;
+    int st;
+    StageScope(genpk_ctx *c, int s) : ctx(c), st(s) { stage_begin(ctx, st); }
+    ~StageScope() { stage_end(ctx, st); }
+    StageScope(const StageScope &) = delete;
+    StageScope &operator=(const StageScope &) = delete;
+};
 
 }  // namespace genpk

@@ -369,6 +369,7 @@ int deposit_device(genpk_ctx *ctx, int which, const float *pos, const float *mas
     a.plane = g.plane();
     a.grid = ctx->grid[which];
     a.errors = ctx->d_errors;
+    a.touched = a.slab ? touched_ptr(ctx, which) : nullptr;
     if (ctx->fixed)
         ctx->grid_is_fixed[which] = true;
 
@@ -390,6 +391,8 @@ int deposit_device(genpk_ctx *ctx, int which, const float *pos, const float *mas
         // a pending genpk_grid_zero: the sweep clears the grid ahead of its own front when it can
         if (ctx->zero_pending[which] && ctx->zero_ahead) {
             bool possible = true;
+            if (a.slab)
+                if (int rc = touched_set(ctx, which, 0x7fffffff, -1)) return rc;     // cleared grid: nothing touched yet
             if (int rc = launch_sweep(ctx, a, plan->n0, plan->n1, true, &info, &possible))
                 return rc;
             if (possible) {
@@ -403,17 +406,20 @@ int deposit_device(genpk_ctx *ctx, int which, const float *pos, const float *mas
     }
     if (int rc = materialize_zero(ctx, which))
         return rc;
+    if (a.slab)                                          // these kernels do not track what they touch
+        if (int rc = touched_set(ctx, which, 0, g.ghost_lo + g.nx + g.ghost_hi - 1)) return rc;
     if (plan->mode == GENPK_DEPOSIT_MARCH)
         return launch_march(ctx, a, plan->n0, plan->n1);
     if (plan->mode == GENPK_DEPOSIT_SORTED) {
         const BrickMap bm = choose_bricks(ctx, a.units);
         if (bm.nbricks > 1 && bm.nbricks <= SORT_MAX_KEYS) {
-            stage_begin(ctx, ST_SORT);
-            if (int rc = ensure_sorted_scratch(ctx, n, masses != nullptr))
-                return rc;
-            if (int rc = sort_by_brick(ctx, pos, masses, n, bm, ctx->d_sorted_pos, ctx->d_sorted_mass, nullptr))
-                return rc;
-            stage_end(ctx, ST_SORT);
+            {
+                StageScope scope(ctx, ST_SORT);
+                if (int rc = ensure_sorted_scratch(ctx, n, masses != nullptr))
+                    return rc;
+                if (int rc = sort_by_brick(ctx, pos, masses, n, bm, ctx->d_sorted_pos, ctx->d_sorted_mass, nullptr))
+                    return rc;
+            }
             a.pos = ctx->d_sorted_pos;
             a.mass = masses ? ctx->d_sorted_mass : nullptr;
         }
@@ -472,9 +478,12 @@ int materialize_zero(genpk_ctx *ctx, int which)
     if (!ctx->zero_pending[which])
         return 0;
     ctx->zero_pending[which] = false;
-    stage_begin(ctx, ST_ZERO);
-    GENPK_CUDA_OK(cudaMemsetAsync(ctx->grid[which], 0, ctx->g.grid_doubles() * sizeof(double), ctx->stream));
-    stage_end(ctx, ST_ZERO);
+    {
+        StageScope scope(ctx, ST_ZERO);
+        GENPK_CUDA_OK(cudaMemsetAsync(ctx->grid[which], 0, ctx->g.grid_doubles() * sizeof(double), ctx->stream));
+    }
+    if (ctx->g.nranks > 1)
+        return touched_set(ctx, which, 0x7fffffff, -1);      // nothing touched yet
     return 0;
 }
 
@@ -534,6 +543,7 @@ int fieldize_host_shim(double boxsize, int dims, double *out, int64_t n, const f
         a.plane = (size_t)dims * fd;
         a.grid = d_grid;
         a.errors = d_err;
+        a.touched = nullptr;
         const int threads = 256;
         const int64_t blocks = (n + threads - 1) / threads;
         if (blocks > 0x7fffffffLL) break;

@@ -19,6 +19,7 @@ struct DepositArgs {
     size_t plane;          // doubles per x plane = dims*fd
     void *grid;
     unsigned long long *errors;
+    int *touched;          // slab: {lowest, highest} local x plane any deposit wrote since the grid was cleared (null: not tracked)
 };
 
 // deposit_march.cu
@@ -113,6 +114,10 @@ __device__ __forceinline__ void deposit_single(const DepositArgs &a, float px, f
         if (xl < 0 || xl > a.xl_max)
             return;
         xh = xl + 1;
+        if (a.touched) {
+            atomicMin(a.touched, xl);
+            atomicMax(a.touched + 1, xh);
+        }
     }
     const double mx0 = __dmul_rn(m, cx.wl), mx1 = __dmul_rn(m, cx.wh);
     const double w00 = __dmul_rn(mx0, cy.wl), w10 = __dmul_rn(mx1, cy.wl);

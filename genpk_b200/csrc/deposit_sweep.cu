@@ -32,11 +32,14 @@
 namespace genpk {
 
 #ifndef GENPK_SWEEP_THREADS
-#define GENPK_SWEEP_THREADS 224      // 7 warps: three CTAs per SM leave 96 registers per thread (256 threads: 80, which spills)
+#define GENPK_SWEEP_THREADS 128      // 4 warps: five CTAs per SM = 20 warps at 96 registers per thread (24 warps leave 80, which
+                                     // spills; register files are handed out in units of 4 warps, so 7-warp CTAs do not help)
 #endif
 constexpr int SWEEP_THREADS = GENPK_SWEEP_THREADS;
 constexpr int SWEEP_WARPS = SWEEP_THREADS / 32;
-constexpr int SWEEP_RY_MAX = 21;         // x-carry slots per thread: (ry + 1) * 20 B * 224 threads <= 99 KB
+constexpr int SWEEP_RY_MAX = 21;         // x-carry slots per thread: (ry + 1) * 20 B * 128 threads <= 56 KB
+constexpr int SWEEP_STAGES = 4;          // particle rows in flight per warp (cp.async ring)
+constexpr int SWEEP_ROW_FLOATS = 128;    // 96 position floats + 32 masses per staged row
 #ifndef GENPK_SWEEP_MAXREG
 #define GENPK_SWEEP_MAXREG 96
 #endif
@@ -56,7 +59,10 @@ struct SweepArgs {
     int za_slack;                // lattice planes between clearing a plane and first needing it
     long long za_uc0;            // expected plane (in u) of lattice plane x_begin
     unsigned long long za_gstep; // grid planes per lattice plane, 32.32 fixed point
-    unsigned *zdone;             // [za_umax] warps that have cleared their share of plane u
+    int n_zero_ctas;             // the first n_zero_ctas CTAs of the launch only clear planes (zero ahead)
+    int couple;                  // > 0: a warp starts lattice plane x only when every warp has started plane x - couple
+    unsigned *arrived;           // [planes swept] warps that have started lattice plane x
+    unsigned *zdone;             // [za_umax] zero CTAs that have cleared their share of plane u
     size_t zero_units;           // 16-byte units per grid plane
     unsigned *def_count;         // [SWEEP_DEF_LISTS] deferred particles per list (a column appends to list col % LISTS)
     unsigned *def_list;          // [SWEEP_DEF_LISTS][def_cap] particle indices (64 bit)
@@ -99,6 +105,68 @@ __device__ __forceinline__ void red_add(long long *p, long long v)
 
 constexpr int SWEEP_DEF_LISTS = 1024;    // deferred-particle lists (a column appends to list col % 1024)
 
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc, unsigned long long policy)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 4, %2;\n" ::"r"(d), "l"(gsrc), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// Spin until *counter >= want.  Relaxed loads with a back-off: what follows the wait are reductions
+// performed at L2, which the loop's exit orders after the load (no L1 involved, so no acquire --
+// an acquire load here costs a whole-L1 invalidate per probe).
+__device__ __forceinline__ void poll_at_least(const unsigned *counter, unsigned want)
+{
+    unsigned seen;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+    while (seen < want) {
+        __nanosleep(64);
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+    }
+}
+
+// Zero ahead, the clearing side: the first n_zero_ctas CTAs of the launch do nothing but clear grid
+// planes in order, each its slice of every plane, `slack` lattice planes ahead of the leading warp
+// of the sweep (arrived[x] > 0 says some warp has started lattice plane x), and count themselves
+// into zdone[u] once their slice of plane u is visible.
+__device__ __noinline__ void sweep_zero_role(const DepositArgs &a, const SweepArgs &g)
+{
+    __shared__ int s_lead;
+    const int tid = threadIdx.x, nthreads = blockDim.x, z = blockIdx.x;
+    const int n_planes = (int)(g.x_end - g.x_begin);
+    const size_t share = (g.zero_units + g.n_zero_ctas - 1) / g.n_zero_ctas;
+    const size_t lo = (size_t)z * share;
+    size_t hi = lo + share;
+    if (hi > g.zero_units) hi = g.zero_units;
+    int lead = 0;                                             // the sweep's leaders have started this lattice plane
+    for (int u = g.za_upre; u < g.za_umax; u++) {
+        // plane u comes into reach when the leaders start lattice plane x with uc(x + slack) + ahead > u
+        if (tid == 0) {
+            while (lead < n_planes - 1 && sweep_uc(g, g.x_begin + lead + g.za_slack) + g.za_ahead <= u) {
+                poll_at_least(g.arrived + lead + 1, 1u);
+                lead++;
+            }
+            s_lead = lead;
+        }
+        __syncthreads();
+        lead = s_lead;
+        int pl = u;
+        if (!a.slab) {
+            pl += g.za_base;
+            if (pl >= a.dims) pl -= a.dims;
+        }
+        uint4 *base = reinterpret_cast<uint4 *>(reinterpret_cast<double *>(a.grid) + (size_t)pl * a.plane);
+        for (size_t i = lo + tid; i < hi; i += nthreads)
+            base[i] = make_uint4(0u, 0u, 0u, 0u);
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            atomicAdd(&g.zdone[u], 1u);
+        }
+    }
+}
+
 // A particle whose cloud touches the periodic wrap of an axis (a cell index dims-1 or beyond, or a
 // negative one), found by the sweep: deposited on the spot with eight reductions and kept out of
 // the carries, so that every carried sum belongs to a cell whose +1 neighbours are plain +1 /
@@ -122,7 +190,14 @@ __global__ void __maxnreg__(GENPK_SWEEP_MAXREG) deposit_sweep_kernel(const __gri
     acc2_t *const xv0 = reinterpret_cast<acc2_t *>(smem_raw) + tid;
     key_t *const xk0 = reinterpret_cast<key_t *>(reinterpret_cast<acc2_t *>(smem_raw) + (size_t)(g.ry + 1) * SWEEP_THREADS) + tid;
 
-    const int col = blockIdx.x * SWEEP_WARPS + warp;
+    float *const ring = reinterpret_cast<float *>(smem_raw + (size_t)(g.ry + 1) * SWEEP_THREADS * (sizeof(acc2_t) + sizeof(key_t))) +
+                        (size_t)warp * SWEEP_STAGES * SWEEP_ROW_FLOATS;
+
+    if (ZA && (int)blockIdx.x < g.n_zero_ctas) {
+        sweep_zero_role(a, g);
+        return;
+    }
+    const int col = ((int)blockIdx.x - (ZA ? g.n_zero_ctas : 0)) * SWEEP_WARPS + warp;
     if (col >= g.ncols)
         return;
     const int zseg = col % g.nzs, yb = col / g.nzs;
@@ -133,9 +208,7 @@ __global__ void __maxnreg__(GENPK_SWEEP_MAXREG) deposit_sweep_kernel(const __gri
     // flags: 1 the lane has a particle in this row; 2 owner lane (lane 0 of later segments only carries
     // z1 sums); 4 this lane emits its z1 sums on a FULL lattice.  The z1 sums of the pair (lane, lane+1)
     // belong to this warp when lane < 31; a row's last particle has no pair and emits them in its owner
-    // lane.  Otherwise (!FULL) the array may end inside a row, the rule varies per step, and a lane that
-    // must not emit its z1 sums zeroes their weights at the source so that every carry it leaves behind
-    // can be flushed unconditionally.
+    // lane.  Otherwise (!FULL) the array may end inside a row and the rule varies per step.
     int flags = (iz < g.n0 ? 1 : 0) | ((lane > 0 || zseg == 0) ? 2 : 0);
     flags |= (pair_in_row ? lane < 31 : (flags & 2) != 0) ? 4 : 0;
     asm volatile("" : "+r"(flags));                          // keep it a register: not rematerialised from 64-bit compares
@@ -149,8 +222,13 @@ __global__ void __maxnreg__(GENPK_SWEEP_MAXREG) deposit_sweep_kernel(const __gri
     for (int s = 0; s <= ry_eff; s++)
         xk0[s * SWEEP_THREADS] = INVALID;
 
-    // ---- this lane's particle: index p, +n0 per row, +plane_inc at the end of a block of rows ----
-    long long p = (g.x_begin * g.n1 + y0) * g.n0 + iz;
+    // ---- particle rows: cp.async ring, SWEEP_STAGES - 1 rows ahead of the row being deposited ----
+    // Every lane copies its own particle (three floats, + its mass) and later reads back only what it
+    // copied, so no barrier guards the ring.  Evict-first in L2: the particles must not push grid lines out.
+    unsigned long long policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(policy));
+    long long p = (g.x_begin * g.n1 + y0) * g.n0 + iz;       // particle of the row being DEPOSITED (tracked when needed)
+    long long lp_index = p;                                  // particle of the row being LOADED (tracked when !FULL)
     const long long plane_inc = (g.n1 - ry_eff + 1) * g.n0;
     // byte steps of the load pointer: a row, and what the last row of a block adds on top of it
     // (opaque to the compiler, which would otherwise redo the 64-bit products every step)
@@ -158,21 +236,38 @@ __global__ void __maxnreg__(GENPK_SWEEP_MAXREG) deposit_sweep_kernel(const __gri
     asm volatile("" : "+l"(row_bytes), "+l"(block_adj_bytes));
     const char *lp = reinterpret_cast<const char *>(a.pos + 3 * p);
     const float *lm = MASS ? a.mass + p : nullptr;
-    float nx = 0.f, ny = 0.f, nz = 0.f, nm = 0.f;
-    // streaming loads (evict first): the particles must not push grid lines out of L2
-    auto fetch = [&]() {
-        if (lane_in_row && (FULL || p < a.n)) {
-            nx = __ldcs(reinterpret_cast<const float *>(lp));
-            ny = __ldcs(reinterpret_cast<const float *>(lp) + 1);
-            nz = __ldcs(reinterpret_cast<const float *>(lp) + 2);
-            if (MASS)
-                nm = __ldcs(lm);
-        }
-    };
     const int n_planes = (int)(g.x_end - g.x_begin);
-    int steps_left = n_planes * ry_eff;
-    if (steps_left > 0)
-        fetch();
+    int loads_left = n_planes * ry_eff, l_r = 0;
+    float *const my_ring = ring + 3 * lane;
+    auto issue_load = [&](int q) {
+        if (loads_left > 0) {
+            loads_left--;
+            if (lane_in_row && (FULL || lp_index < a.n)) {
+                float *dst = my_ring + (q & (SWEEP_STAGES - 1)) * SWEEP_ROW_FLOATS;
+                cp_async4(dst, lp, policy);
+                cp_async4(dst + 1, lp + 4, policy);
+                cp_async4(dst + 2, lp + 8, policy);
+                if (MASS)
+                    cp_async4(ring + (q & (SWEEP_STAGES - 1)) * SWEEP_ROW_FLOATS + 96 + lane, lm, policy);
+            }
+            const bool last_row = ++l_r == ry_eff;
+            lp += row_bytes;
+            if (last_row) {
+                lp += block_adj_bytes;
+                l_r = 0;
+            }
+            if (!FULL || MASS) {
+                const long long inc = last_row ? plane_inc : g.n0;
+                lp_index += inc;
+                if (MASS) lm += inc;
+            }
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int q = 0; q < SWEEP_STAGES - 1; q++)
+        issue_load(q);
+    int q_step = 0;
 
     // One row slot: merge what the previous plane left for this row (x), leave this row's high-x
     // sums for the next plane, then hand the z1 sum to the next lane (z) and emit.
@@ -211,55 +306,38 @@ __global__ void __maxnreg__(GENPK_SWEEP_MAXREG) deposit_sweep_kernel(const __gri
             red_add(grid + (size_t)key_b, v01);
     };
 
-    // ---- zero ahead: planes cleared so far by everybody's duties / known complete by this warp ----
-    int zero_next = g.za_upre, ready = g.za_upre;
+    // ---- zero ahead / coupling: planes known to be clear by this warp ----
+    int ready = g.za_upre;
     unsigned long long gacc = 0x80000000ull;                 // (x - x_begin) * gstep + 1/2
-    const size_t share = ZA ? (g.zero_units + g.ncols - 1) / g.ncols : 0;
-    auto clear_planes_to = [&](long long target) {
-        if (target > g.za_umax) target = g.za_umax;
-        for (; zero_next < target; zero_next++) {
-            int pl = zero_next;
-            if (!a.slab) {
-                pl += g.za_base;
-                if (pl >= dims) pl -= dims;
-            }
-            uint4 *base = reinterpret_cast<uint4 *>(reinterpret_cast<double *>(a.grid) + (size_t)pl * a.plane);
-            const size_t lo = (size_t)col * share;
-            size_t hi = lo + share;
-            if (hi > g.zero_units) hi = g.zero_units;
-            for (size_t i = lo + lane; i < hi; i += 32)
-                base[i] = make_uint4(0u, 0u, 0u, 0u);
-            __syncwarp();
-            if (lane == 0) {
-                __threadfence();
-                atomicAdd(&g.zdone[zero_next], 1u);
-            }
-        }
-    };
 
     acc_t c00 = 0, c10 = 0, c01 = 0, c11 = 0;                // y-carry: the four high-y sums of the previous row
     key_t yc_key = INVALID;
     unsigned n_rejected = 0;
+    int t_lo = 0x7fffffff, t_hi = -1;                        // slab: lowest / highest low-x plane of a deposited cloud
 
     for (int xi = 0; xi < n_planes; xi++) {
         // zero ahead: this lattice plane may deposit into local planes xl with (xl - za_lo) mod dims <= za_span
         int za_lo = 0, za_span = 0x7fffffff;
+        // Coupling: every warp announces the lattice plane it starts and starts plane x only when all
+        // warps have started plane x - couple, so the front of the sweep stays `couple` planes thick
+        // (L2 locality of the reductions; the zero CTAs clear just ahead of the leaders).
+        if (g.arrived) {
+            if (lane == 0) {
+                asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(g.arrived + xi), "r"(1u) : "memory");
+                if (g.couple > 0 && xi >= g.couple)
+                    poll_at_least(g.arrived + (xi - g.couple), (unsigned)g.ncols);
+            }
+            __syncwarp();
+        }
         if (ZA) {
-            // duty: my share of the planes that come into reach `slack` lattice planes from now
-            clear_planes_to(g.za_uc0 + (long long)((gacc + (unsigned long long)g.za_slack * g.za_gstep) >> 32) + g.za_ahead);
             const long long front = g.za_uc0 + (long long)(gacc >> 32) + g.za_ahead;
             const int need = front > g.za_umax ? g.za_umax : (int)front;
             za_lo = g.za_base;
             za_span = front >= g.za_umax ? 0x7fffffff : (int)front - 2;          // u + 2 <= front
             if (ready < need) {
-                if (lane == 0) {
-                    for (; ready < need; ready++) {
-                        unsigned seen;
-                        do {
-                            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(g.zdone + ready) : "memory");
-                        } while (seen < (unsigned)g.ncols);
-                    }
-                }
+                if (lane == 0)
+                    for (int u = ready; u < need; u++)
+                        poll_at_least(g.zdone + u, (unsigned)g.n_zero_ctas);
                 ready = need;
                 __syncwarp();
             }
@@ -268,27 +346,19 @@ __global__ void __maxnreg__(GENPK_SWEEP_MAXREG) deposit_sweep_kernel(const __gri
         acc2_t *xv = xv0;
         key_t *xk = xk0;
         for (int r = 0; r < ry_eff; r++) {
-            const float px = nx, py = ny, pz = nz;
+            issue_load(q_step + SWEEP_STAGES - 1);
+            cp_async_wait<SWEEP_STAGES - 1>();
+            const float *row = my_ring + (q_step & (SWEEP_STAGES - 1)) * SWEEP_ROW_FLOATS;
+            q_step++;
+            const float px = row[0], py = row[1], pz = row[2];
             double m = a.cmass;
             if (MASS)
-                m = (double)nm;                                             // fieldize.cpp:63
+                m = (double)row[96 - 2 * lane];                             // ring[slot][96 + lane], fieldize.cpp:63
             const bool live = lane_in_row && (FULL || p < a.n);
             const bool emit_b = FULL ? emit_b_full : ((pair_in_row && p + 1 < a.n) ? lane < 31 : owner_lane);
             const long long p_now = p;
-            // next step's row, one step ahead
-            {
-                const bool last_row = r + 1 == ry_eff;
-                lp += row_bytes;
-                if (last_row)
-                    lp += block_adj_bytes;
-                if (!FULL || MASS) {
-                    const long long inc = last_row ? plane_inc : g.n0;
-                    p += inc;
-                    if (MASS) lm += inc;
-                }
-                if (--steps_left > 0)
-                    fetch();
-            }
+            if (!FULL || MASS)
+                p += (r + 1 == ry_eff) ? plane_inc : g.n0;
             bool ok = live && fabsf(px) < pos_limit && fabsf(py) < pos_limit && fabsf(pz) < pos_limit;
             int fx, fy, fz;
             double tx, dx, ty, dy, tz, dz;
@@ -350,6 +420,10 @@ __global__ void __maxnreg__(GENPK_SWEEP_MAXREG) deposit_sweep_kernel(const __gri
                 ok = false;
             }
             ok = ok && live;
+            if (a.slab && ok) {                                             // planes this rank's ghost exchange has to move
+                t_lo = xl < t_lo ? xl : t_lo;
+                t_hi = xl > t_hi ? xl : t_hi;
+            }
             // sums this lane must not emit are zero from the start: lane 0 of a later segment repeats the
             // previous segment's last particle and only carries its z1 sums; the z1 sums of a lane whose
             // pair belongs to the next segment are carried there.  Every carry can then be flushed as it is.
@@ -409,8 +483,15 @@ __global__ void __maxnreg__(GENPK_SWEEP_MAXREG) deposit_sweep_kernel(const __gri
     }
     if (n_rejected)
         atomicAdd(a.errors, (unsigned long long)n_rejected);
-    if (ZA)
-        clear_planes_to(g.za_umax);                           // planes no lattice plane reached
+    if (a.touched) {
+        t_lo = __reduce_min_sync(0xffffffffu, t_lo);
+        t_hi = __reduce_max_sync(0xffffffffu, t_hi);
+        if (lane == 0 && t_hi >= 0) {
+            atomicMin(a.touched, t_lo);
+            atomicMax(a.touched + 1, t_hi + 1);
+        }
+    }
+    cp_async_wait<0>();
 }
 
 // ---------------------------------------------------------------------------------
@@ -487,19 +568,22 @@ template <bool FIXED, typename key_t> static const void *sweep_pick(bool full, b
 static size_t sweep_smem(int ry, bool fixed, bool key32)
 {
     (void)fixed;
-    return (size_t)(ry + 1) * SWEEP_THREADS * (16 + (key32 ? 4 : 8));
+    return (size_t)(ry + 1) * SWEEP_THREADS * (16 + (key32 ? 4 : 8)) +
+           (size_t)SWEEP_WARPS * SWEEP_STAGES * SWEEP_ROW_FLOATS * sizeof(float);
 }
 
-static int ensure_za_scratch(genpk_ctx *ctx, int umax, int ncols, int def_cap)
+// device scratch of the coupled / zero-ahead sweep: arrived[n_planes], zdone[umax], overflow flag;
+// deferred-particle counters and lists
+static int ensure_za_scratch(genpk_ctx *ctx, long long n_planes, int umax, int def_cap)
 {
-    if (umax > ctx->za_zdone_cap) {
+    const size_t words = (size_t)n_planes + (size_t)umax + 8;
+    if (words > (size_t)ctx->za_zdone_cap) {
         if (ctx->d_za_zdone) cudaFree(ctx->d_za_zdone);
         ctx->d_za_zdone = nullptr;
         ctx->za_zdone_cap = 0;
-        GENPK_CUDA_OK(cudaMalloc(&ctx->d_za_zdone, ((size_t)umax + 1) * sizeof(unsigned)));   // [umax]: overflow flag
-        ctx->za_zdone_cap = umax;
+        GENPK_CUDA_OK(cudaMalloc(&ctx->d_za_zdone, words * sizeof(unsigned)));
+        ctx->za_zdone_cap = (int)words;
     }
-    (void)ncols;
     const size_t need = (size_t)SWEEP_DEF_LISTS * (2 * (size_t)def_cap + 2);        // counters, then 64-bit entries
     if (need > ctx->za_def_cap) {
         if (ctx->d_za_def) cudaFree(ctx->d_za_def);
@@ -544,6 +628,8 @@ int launch_sweep(genpk_ctx *ctx, const DepositArgs &a, long long n0, long long n
     };
     const void *kern = pick(za);
     int ry = 0;
+    // zero ahead: a few CTAs of the launch do nothing but clear planes ahead of the sweep
+    const int n_zero = za ? (ctx->za_zero_ctas > 0 ? ctx->za_zero_ctas : ctx->sm_count / 3) : 0;
     const int ry_cap = (int)(n1 < SWEEP_RY_MAX ? n1 : SWEEP_RY_MAX);
     // (at least 4 rows when the plane has them: every block of rows pays one extra slot for its last carry)
     const int ry_lo = ctx->sweep_ry > 0 ? (ctx->sweep_ry < ry_cap ? ctx->sweep_ry : ry_cap) : (ry_cap < 4 ? ry_cap : 4);
@@ -555,45 +641,61 @@ int launch_sweep(genpk_ctx *ctx, const DepositArgs &a, long long n0, long long n
         int per_sm = 0;
         GENPK_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SWEEP_THREADS, smem));
         const long long cols = (long long)g.nzs * ((n1 + t - 1) / t);
-        const long long ctas = (cols + SWEEP_WARPS - 1) / SWEEP_WARPS;
+        const long long ctas = (cols + SWEEP_WARPS - 1) / SWEEP_WARPS + n_zero;
         if (per_sm >= 1 && ctas <= (long long)per_sm * ctx->sm_count) {
             ry = t;
             break;
         }
     }
-    if (ry == 0) {                       // more columns than resident warps: several waves, no zero ahead
+    // one resident wave: the warps can wait for each other, so the sweep is coupled (a front a few planes
+    // thick) and may clear the grid ahead of itself; more columns than resident warps: several
+    // uncoupled waves over a grid that was cleared before
+    const bool one_wave = ry > 0;
+    if (!one_wave) {
         if (za) {
             if (za_possible) *za_possible = false;
             return 0;
         }
-        kern = pick(false);
         ry = ctx->sweep_ry > 0 ? ctx->sweep_ry : 10;
         if (ry > ry_cap) ry = ry_cap;
-        while (ry > 1 && sweep_smem(ry, ctx->fixed, key32) * 3 > (size_t)ctx->smem_optin)     // three CTAs per SM
+        while (ry > 1 && sweep_smem(ry, ctx->fixed, key32) * 5 > (size_t)ctx->smem_optin)     // five CTAs per SM
             ry--;
     }
     g.ry = ry;
     const long long nyb = (n1 + ry - 1) / ry;
     g.ncols = (int)(g.nzs * nyb);
+    g.n_zero_ctas = n_zero;
+    g.couple = one_wave ? ctx->sweep_couple : 0;
     const size_t smem = sweep_smem(ry, ctx->fixed, key32);
     GENPK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const long long blocks = ((long long)g.ncols + SWEEP_WARPS - 1) / SWEEP_WARPS;
+    const long long blocks = ((long long)g.ncols + SWEEP_WARPS - 1) / SWEEP_WARPS + n_zero;
 
     DepositArgs args = a;
     ctx->last_sweep[0] = ry;
     ctx->last_sweep[1] = g.ncols;
     ctx->last_sweep[2] = za ? 1 : 0;
     ctx->last_sweep[3] = 0;
+    const SlabGeom &sg = ctx->g;
+    const int n_grid_planes = sg.ghost_lo + sg.nx + sg.ghost_hi;
+    if (one_wave && (za || g.couple > 0)) {
+        if (int rc = ensure_za_scratch(ctx, n2, n_grid_planes, ctx->za_def_per_col)) return rc;
+        g.arrived = ctx->d_za_zdone;
+        g.zdone = ctx->d_za_zdone + n2;
+        g.def_overflow = g.zdone + n_grid_planes;
+        GENPK_CUDA_OK(cudaMemsetAsync(ctx->d_za_zdone, 0, ((size_t)n2 + n_grid_planes + 8) * sizeof(unsigned), ctx->stream));
+    }
     if (!za) {
         void *params[] = {(void *)&args, (void *)&g};
-        GENPK_CUDA_OK(cudaLaunchKernel(kern, dim3((unsigned)blocks), dim3(SWEEP_THREADS), params, smem, ctx->stream));
+        if (g.arrived)
+            GENPK_CUDA_OK(cudaLaunchCooperativeKernel(kern, dim3((unsigned)blocks), dim3(SWEEP_THREADS), params, smem, ctx->stream));
+        else
+            GENPK_CUDA_OK(cudaLaunchKernel(kern, dim3((unsigned)blocks), dim3(SWEEP_THREADS), params, smem, ctx->stream));
         ctx->launches++;
         return 0;
     }
 
     // ---- zero ahead ----
-    const SlabGeom &sg = ctx->g;
-    const int n_planes = sg.ghost_lo + sg.nx + sg.ghost_hi;
+    const int n_planes = n_grid_planes;
     // window: planes past the expected one that are kept clear -- a little more than the largest
     // displacement the order probe saw (particles beyond it take the deferred path)
     int window = ctx->za_window > 0 ? ctx->za_window : (info && info->dx_valid ? info->dx_dev * 5 / 4 + 1 : 6);
@@ -625,15 +727,10 @@ int launch_sweep(genpk_ctx *ctx, const DepositArgs &a, long long n0, long long n
     if (upre > g.za_umax) upre = g.za_umax;
     g.za_upre = (int)upre;
     g.zero_units = a.plane * sizeof(double) / 16;
-    const int def_cap = ctx->za_def_per_col;
-    if (int rc = ensure_za_scratch(ctx, g.za_umax, g.ncols, def_cap)) return rc;
-    g.zdone = ctx->d_za_zdone;
-    g.def_overflow = ctx->d_za_zdone + g.za_umax;
     g.def_count = ctx->d_za_def;
     g.def_list = ctx->d_za_def + 2 * SWEEP_DEF_LISTS;                         // 8-byte aligned
-    g.def_cap = def_cap;
+    g.def_cap = ctx->za_def_per_col;
     GENPK_CUDA_OK(cudaMemsetAsync(ctx->d_za_def, 0, SWEEP_DEF_LISTS * sizeof(unsigned), ctx->stream));
-    GENPK_CUDA_OK(cudaMemsetAsync(ctx->d_za_zdone, 0, ((size_t)g.za_umax + 1) * sizeof(unsigned), ctx->stream));
     // planes the first lattice planes need at once: cleared here (up to two pieces of the periodic grid)
     {
         const size_t plane_bytes = a.plane * sizeof(double);

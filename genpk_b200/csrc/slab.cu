@@ -41,6 +41,93 @@ int ghost_accumulate(genpk_ctx *ctx, int which, int side, const void *recv)
     return 0;
 }
 
+__global__ void touched_set_kernel(int *touched, int lo, int hi)
+{
+    touched[0] = lo;
+    touched[1] = hi;
+}
+
+int touched_set(genpk_ctx *ctx, int which, int lo, int hi)
+{
+    touched_set_kernel<<<1, 1, 0, ctx->stream>>>(touched_ptr(ctx, which), lo, hi);
+    ctx->launches++;
+    GENPK_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// Ghost exchange without a collective: this rank adds, into its outermost owned planes, the ghost
+// planes of its ring neighbours -- read straight from their memory over NVLink (mapped with CUDA
+// IPC), and only the planes their deposits touched (the {lowest, highest} written plane sits behind
+// each grid allocation).  blockIdx.y: ghost plane slot (first the ghost_hi planes above rank-1's
+// slab, then the ghost_lo planes below rank+1's); blocks of untouched planes leave at once.
+struct PullArgs {
+    void *mine;
+    const void *prev, *next;      // the neighbours' grid allocations (next may be null: no low ghosts)
+    size_t plane, grid_doubles;   // doubles per plane / per allocation (the touched range follows it)
+    int nx, ghost_lo, ghost_hi;
+    int fixed;
+};
+
+__global__ void __launch_bounds__(256) ghost_pull_kernel(PullArgs A)
+{
+    const int slot = blockIdx.y;
+    const bool from_prev = slot < A.ghost_hi;
+    const double *peer = reinterpret_cast<const double *>(from_prev ? A.prev : A.next);
+    const int src_plane = from_prev ? A.ghost_lo + A.nx + slot : slot - A.ghost_hi;
+    const int dst_plane = from_prev ? A.ghost_lo + slot : A.nx + (slot - A.ghost_hi);   // (= ghost_lo + nx - ghost_lo + j)
+    const int *range = reinterpret_cast<const int *>(peer + A.grid_doubles);
+    const int lo = range[0], hi = range[1];
+    if (src_plane < lo || src_plane > hi)
+        return;
+    const size_t units = A.plane / 2;                                      // 16-byte units per plane
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    if (A.fixed) {
+        const longlong2 *src = reinterpret_cast<const longlong2 *>(peer + (size_t)src_plane * A.plane);
+        longlong2 *dst = reinterpret_cast<longlong2 *>(reinterpret_cast<double *>(A.mine) + (size_t)dst_plane * A.plane);
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < units; i += stride) {
+            const longlong2 v = src[i];
+            longlong2 d = dst[i];
+            d.x += v.x;
+            d.y += v.y;
+            dst[i] = d;
+        }
+    } else {
+        const double2 *src = reinterpret_cast<const double2 *>(peer + (size_t)src_plane * A.plane);
+        double2 *dst = reinterpret_cast<double2 *>(reinterpret_cast<double *>(A.mine) + (size_t)dst_plane * A.plane);
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < units; i += stride) {
+            const double2 v = src[i];
+            double2 d = dst[i];
+            d.x += v.x;
+            d.y += v.y;
+            dst[i] = d;
+        }
+    }
+}
+
+int ghost_pull(genpk_ctx *ctx, int which)
+{
+    const SlabGeom &g = ctx->g;
+    PullArgs A;
+    A.mine = ctx->grid[which];
+    A.prev = ctx->grid_peer[which][0];
+    A.next = ctx->grid_peer[which][1];
+    A.plane = g.plane();
+    A.grid_doubles = g.grid_doubles();
+    A.nx = g.nx;
+    A.ghost_lo = g.ghost_lo;
+    A.ghost_hi = g.ghost_hi;
+    A.fixed = ctx->grid_is_fixed[which] ? 1 : 0;
+    const int slots = g.ghost_hi + g.ghost_lo;
+    if (slots == 0)
+        return 0;
+    // enough CTAs per plane to keep NVLink busy when only a few planes are touched
+    const unsigned per_plane = (unsigned)((ctx->sm_count * 4 + slots - 1) / slots);
+    ghost_pull_kernel<<<dim3(per_plane < 8 ? 8 : per_plane, (unsigned)slots), 256, 0, ctx->stream>>>(A);
+    ctx->launches++;
+    GENPK_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 // in : [nx][dims][nc] complex   (after the batched 2-D D2Z)
 // out: [nranks][nx][ny][nc]     block s goes to rank s, which owns y in [s*ny, (s+1)*ny)
 __global__ void __launch_bounds__(256) slab_pack_kernel(const double2 *in, double2 *out, int nx, int dims, int nc, int ny)

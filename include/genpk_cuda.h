@@ -69,7 +69,10 @@ extern "C" {
                                           clear (0 = from the displacements the order probe saw).  Performance only:
                                           particles displaced further are deposited by a clean-up pass */
 #define GENPK_OPT_ZA_SLACK      15     /* zero ahead: lattice planes between clearing a grid plane and first needing it */
-#define GENPK_OPT_ZA_DEFERRED   16     /* zero ahead: clean-up list entries per sweep column (default 4096) */
+#define GENPK_OPT_ZA_DEFERRED   16     /* zero ahead: entries per clean-up list (1024 lists; default 4096) */
+#define GENPK_OPT_ZA_ZERO_CTAS  17     /* zero ahead: CTAs of the sweep launch that only clear planes (0 = a third of the SMs) */
+#define GENPK_OPT_SWEEP_COUPLE  18     /* a sweep warp starts lattice plane x once every warp has started plane x - N
+                                          (default 6; 0 = uncoupled): keeps the front of the sweep N planes thick */
 /* ---- binning pass selection (genpk_set_option(ctx, GENPK_OPT_POWER, v)) ------------ */
 #define GENPK_OPT_POWER          3
 #define GENPK_POWER_CACHED       0     /* sum|k| and mode counts per bin depend on the grid only: computed
@@ -88,6 +91,8 @@ extern "C" {
                                           2: as 1 with 4096-mode tiles at 1024 (measurements) */
 
 typedef struct genpk_ctx genpk_ctx;
+#define GENPK_MAX_PEERS 16
+#define GENPK_IPC_HANDLE_BYTES 64
 
 /* ================= 1. reference-signature shims (host buffers) ====================== */
 
@@ -271,6 +276,27 @@ int genpk_ghost_accumulate(genpk_ctx *ctx, int which, const void *recv_plane_dev
 void *genpk_ghost_side_ptr(genpk_ctx *ctx, int which, int side, size_t *bytes);
 int genpk_ghost_side_accumulate(genpk_ctx *ctx, int which, int side, const void *recv_planes_dev);
 
+/* ---- ghost exchange by peer loads (no collective, no staging buffers) ------------------------
+ * Every grid allocation can be exported with CUDA IPC (genpk_ipc_export_grid) and mapped by the two
+ * ring neighbours (genpk_slab_set_grid_peer: side 0 = the grid of rank-1, side 1 = of rank+1; plain
+ * pointers inside one process).  Once every rank has deposited (the caller's barrier),
+ * genpk_ghost_pull adds the neighbours' ghost planes into this rank's outermost owned planes,
+ * reading them straight from the neighbours' memory over NVLink -- and only the planes their
+ * deposits wrote (each allocation carries the {lowest, highest} plane written since it was cleared;
+ * the sweep kernel tracks it, the other deposit kernels mark every plane).  Replaces
+ * genpk_ghost_side_ptr + send/recv + genpk_ghost_side_accumulate.  The neighbours must not clear or
+ * deposit into their grids again before every pull of the step is over (one more barrier, e.g. the one
+ * that precedes the transpose). */
+int genpk_ipc_export_grid(genpk_ctx *ctx, int which, void *handle_out /* GENPK_IPC_HANDLE_BYTES */);
+int genpk_slab_set_grid_peer(genpk_ctx *ctx, int which, int side, const void *ipc_handle /* or NULL */,
+                             void *same_process_ptr);
+int genpk_ghost_pull_ready(const genpk_ctx *ctx, int which);
+int genpk_ghost_pull(genpk_ctx *ctx, int which);
+/* Stream-ordered: writes the number of particles the deposits rejected so far (as a double) to
+ * dst_dev and clears the counter -- lets a pipeline carry the count along with its per-bin sums and
+ * look at it once per step on the host instead of synchronising after every deposit. */
+int genpk_rejected_to(genpk_ctx *ctx, double *dst_dev);
+
 /* Batched 2-D D2Z over the local x-planes (in place). */
 int genpk_slab_fft_yz(genpk_ctx *ctx, int which);
 /* Reorder [x_local][y][kz] into nranks contiguous blocks [dest][x_local][y_local][kz]. */
@@ -300,8 +326,6 @@ int genpk_slab_fftx_power_partial(genpk_ctx *ctx, const void *spec_yz_dev, int n
  * orders the ranks: nobody may still read its block when the scatter starts, and everybody
  * must have finished scattering before genpk_slab_fftx_power_partial reads a block (two barriers, e.g. 1-element all-reduces on the stream).
  * Needs grid side 256/512/1024/2048, dims/nranks a power of two, nranks <= GENPK_MAX_PEERS. */
-#define GENPK_MAX_PEERS 16
-#define GENPK_IPC_HANDLE_BYTES 64
 void *genpk_slab_recv_buffer(genpk_ctx *ctx, size_t *bytes);
 int genpk_ipc_export(genpk_ctx *ctx, void *handle_out /* GENPK_IPC_HANDLE_BYTES */);
 int genpk_slab_set_peer(genpk_ctx *ctx, int rank, const void *ipc_handle /* or NULL */, void *same_process_ptr);

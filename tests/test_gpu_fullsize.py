@@ -200,5 +200,5 @@ def test_c5_slab_block_counts_golden():
     assert np.array_equal(tot[2].astype(np.int64), gold["count2048"])
     assert int(tot[2].sum()) == dims ** 3 - 1
     nz = gold["count2048"] > 0
-    np.testing.assert_allclose(tot[1][nz], gold["ksum2048"][nz], rtol=1e-12)
+    np.testing.assert_allclose(tot[1][nz], gold["ksum2048"][nz], rtol=1e-9)      # 10^7 terms per bin, another summation order
     assert not tot[0].any()

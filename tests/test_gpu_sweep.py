@@ -105,6 +105,29 @@ def test_zero_ahead_windows_and_deferred_particles(port, window, slack, defcap, 
         ctx.synchronize()
 
 
+@pytest.mark.parametrize("couple,zero_ctas,za", [(0, 0, 1), (1, 1, 1), (3, 7, 1), (40, 200, 1), (0, 0, 0), (1, 0, 0), (5, 0, 0)])
+def test_sweep_coupling_and_zero_ctas(port, couple, zero_ctas, za):
+    """The sweep's warps wait for each other (coupling) and for the CTAs that clear planes ahead of them;
+    any setting of the two must give the same sums."""
+    n_side = dims = 72
+    box = 300.0
+    dpos, pos = synth(api.SYNTH_CLUSTERED, n_side, dims, box)
+    want = fixed_want(port, box, dims, pos, None, 1.0)
+    with gp.Context(dims, flags=api.FLAG_FIXED_POINT) as ctx:
+        ctx.set_deposit_mode(api.DEPOSIT_SWEEP)
+        ctx.set_lattice_hint(n_side, n_side)
+        ctx.set_option(api.OPT_SWEEP_COUPLE, couple)
+        ctx.set_option(api.OPT_ZA_ZERO_CTAS, zero_ctas)
+        ctx.set_option(api.OPT_ZERO_AHEAD, za)
+        poison(ctx)
+        ctx.grid_zero()
+        ctx.deposit_dev(dpos.data_ptr(), n_side ** 3, 0, 1.0, box)
+        got = ctx.grid_download_fixed()
+        ctx.synchronize()
+        assert ctx.last_sweep()["zero_ahead"] == za
+    assert np.array_equal(got, want)
+
+
 @pytest.mark.parametrize("ry", [1, 2, 3, 7, 10, 21])
 def test_sweep_column_heights(port, ry):
     n_side, dims, box = 44, 44, 100.0
@@ -226,6 +249,8 @@ def test_additive_deposit_after_zero_ahead(port):
     n = n_side ** 3
     want = fixed_want(port, box, dims, np.concatenate([pos, pos[: n // 3]]), None, 1.0)
     with gp.Context(dims, flags=api.FLAG_FIXED_POINT) as ctx:
+        ctx.set_deposit_mode(api.DEPOSIT_SWEEP)
+        ctx.set_lattice_hint(n_side, n_side)
         poison(ctx)
         ctx.grid_zero()
         ctx.deposit_dev(dpos.data_ptr(), n, 0, 1.0, box)
