@@ -186,12 +186,14 @@ __global__ void __maxnreg__(GENPK_SWEEP_MAXREG) deposit_sweep_kernel(const __gri
     constexpr key_t INVALID = ~(key_t)0;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // shared memory: the particle-row ring of each warp first, at compile-time offsets (with the ring behind
+    // the ry-dependent slot arrays ptxas 12.9 addresses the cp.async destinations as [R+UR+imm] next to the
+    // L2 cache-hint descriptor, an encoding the hardware rejects as an illegal instruction), then the
     // x-carry slots [ry+1][threads]: (high-x sums of the z0 and z1 cells) and the cell they belong to
-    acc2_t *const xv0 = reinterpret_cast<acc2_t *>(smem_raw) + tid;
-    key_t *const xk0 = reinterpret_cast<key_t *>(reinterpret_cast<acc2_t *>(smem_raw) + (size_t)(g.ry + 1) * SWEEP_THREADS) + tid;
-
-    float *const ring = reinterpret_cast<float *>(smem_raw + (size_t)(g.ry + 1) * SWEEP_THREADS * (sizeof(acc2_t) + sizeof(key_t))) +
-                        (size_t)warp * SWEEP_STAGES * SWEEP_ROW_FLOATS;
+    constexpr size_t RING_BYTES = (size_t)SWEEP_WARPS * SWEEP_STAGES * SWEEP_ROW_FLOATS * sizeof(float);
+    float *const ring = reinterpret_cast<float *>(smem_raw) + (size_t)warp * SWEEP_STAGES * SWEEP_ROW_FLOATS;
+    acc2_t *const xv0 = reinterpret_cast<acc2_t *>(smem_raw + RING_BYTES) + tid;
+    key_t *const xk0 = reinterpret_cast<key_t *>(reinterpret_cast<acc2_t *>(smem_raw + RING_BYTES) + (size_t)(g.ry + 1) * SWEEP_THREADS) + tid;
 
     if (ZA && (int)blockIdx.x < g.n_zero_ctas) {
         sweep_zero_role(a, g);
