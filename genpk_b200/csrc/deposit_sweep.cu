@@ -38,8 +38,10 @@ namespace genpk {
 constexpr int SWEEP_THREADS = GENPK_SWEEP_THREADS;
 constexpr int SWEEP_WARPS = SWEEP_THREADS / 32;
 constexpr int SWEEP_RY_MAX = 21;         // x-carry slots per thread: (ry + 1) * 20 B * 128 threads <= 56 KB
-constexpr int SWEEP_STAGES = 4;          // particle rows in flight per warp (cp.async ring)
-constexpr int SWEEP_ROW_FLOATS = 128;    // 96 position floats + 32 masses per staged row
+#ifndef GENPK_SWEEP_AHEAD
+#define GENPK_SWEEP_AHEAD 2
+#endif
+constexpr int SWEEP_AHEAD = GENPK_SWEEP_AHEAD;   // particle rows in flight per lane (registers)
 #ifndef GENPK_SWEEP_MAXREG
 #define GENPK_SWEEP_MAXREG 96
 #endif
@@ -104,14 +106,6 @@ __device__ __forceinline__ void red_add(long long *p, long long v)
 }
 
 constexpr int SWEEP_DEF_LISTS = 1024;    // deferred-particle lists (a column appends to list col % 1024)
-
-__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc, unsigned long long policy)
-{
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 4, %2;\n" ::"r"(d), "l"(gsrc), "l"(policy) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 // Spin until *counter >= want.  Relaxed loads with a back-off: what follows the wait are reductions
 // performed at L2, which the loop's exit orders after the load (no L1 involved, so no acquire --
@@ -186,14 +180,9 @@ __global__ void __maxnreg__(GENPK_SWEEP_MAXREG) deposit_sweep_kernel(const __gri
     constexpr key_t INVALID = ~(key_t)0;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // shared memory: the particle-row ring of each warp first, at compile-time offsets (with the ring behind
-    // the ry-dependent slot arrays ptxas 12.9 addresses the cp.async destinations as [R+UR+imm] next to the
-    // L2 cache-hint descriptor, an encoding the hardware rejects as an illegal instruction), then the
     // x-carry slots [ry+1][threads]: (high-x sums of the z0 and z1 cells) and the cell they belong to
-    constexpr size_t RING_BYTES = (size_t)SWEEP_WARPS * SWEEP_STAGES * SWEEP_ROW_FLOATS * sizeof(float);
-    float *const ring = reinterpret_cast<float *>(smem_raw) + (size_t)warp * SWEEP_STAGES * SWEEP_ROW_FLOATS;
-    acc2_t *const xv0 = reinterpret_cast<acc2_t *>(smem_raw + RING_BYTES) + tid;
-    key_t *const xk0 = reinterpret_cast<key_t *>(reinterpret_cast<acc2_t *>(smem_raw + RING_BYTES) + (size_t)(g.ry + 1) * SWEEP_THREADS) + tid;
+    acc2_t *const xv0 = reinterpret_cast<acc2_t *>(smem_raw) + tid;
+    key_t *const xk0 = reinterpret_cast<key_t *>(reinterpret_cast<acc2_t *>(smem_raw) + (size_t)(g.ry + 1) * SWEEP_THREADS) + tid;
 
     if (ZA && (int)blockIdx.x < g.n_zero_ctas) {
         sweep_zero_role(a, g);
@@ -224,11 +213,11 @@ __global__ void __maxnreg__(GENPK_SWEEP_MAXREG) deposit_sweep_kernel(const __gri
     for (int s = 0; s <= ry_eff; s++)
         xk0[s * SWEEP_THREADS] = INVALID;
 
-    // ---- particle rows: cp.async ring, SWEEP_STAGES - 1 rows ahead of the row being deposited ----
-    // Every lane copies its own particle (three floats, + its mass) and later reads back only what it
-    // copied, so no barrier guards the ring.  Evict-first in L2: the particles must not push grid lines out.
-    unsigned long long policy;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(policy));
+    // ---- particle rows: read straight into registers, SWEEP_AHEAD steps ahead of the row being deposited ----
+    // Streaming loads (ld.global.cs = evict first in L1 and L2): the particles must not push grid lines out
+    // of L2.  (A cp.async ring with an L2 evict-first cache hint is what deposit_march_kernel uses; here ptxas
+    // 12.9 reads the hint descriptor of the prologue copies from uniform registers nobody wrote, and the GPU
+    // answers with "illegal instruction".)
     long long p = (g.x_begin * g.n1 + y0) * g.n0 + iz;       // particle of the row being DEPOSITED (tracked when needed)
     long long lp_index = p;                                  // particle of the row being LOADED (tracked when !FULL)
     const long long plane_inc = (g.n1 - ry_eff + 1) * g.n0;
@@ -240,17 +229,19 @@ __global__ void __maxnreg__(GENPK_SWEEP_MAXREG) deposit_sweep_kernel(const __gri
     const float *lm = MASS ? a.mass + p : nullptr;
     const int n_planes = (int)(g.x_end - g.x_begin);
     int loads_left = n_planes * ry_eff, l_r = 0;
-    float *const my_ring = ring + 3 * lane;
-    auto issue_load = [&](int q) {
+    float ax[SWEEP_AHEAD], ay[SWEEP_AHEAD], az[SWEEP_AHEAD], am[SWEEP_AHEAD];   // rows in flight, oldest first
+#pragma unroll
+    for (int k = 0; k < SWEEP_AHEAD; k++)
+        ax[k] = ay[k] = az[k] = am[k] = 0.f;
+    auto issue_load = [&](float &ox, float &oy, float &oz, float &om) {
         if (loads_left > 0) {
             loads_left--;
             if (lane_in_row && (FULL || lp_index < a.n)) {
-                float *dst = my_ring + (q & (SWEEP_STAGES - 1)) * SWEEP_ROW_FLOATS;
-                cp_async4(dst, lp, policy);
-                cp_async4(dst + 1, lp + 4, policy);
-                cp_async4(dst + 2, lp + 8, policy);
+                ox = __ldcs(reinterpret_cast<const float *>(lp));
+                oy = __ldcs(reinterpret_cast<const float *>(lp) + 1);
+                oz = __ldcs(reinterpret_cast<const float *>(lp) + 2);
                 if (MASS)
-                    cp_async4(ring + (q & (SWEEP_STAGES - 1)) * SWEEP_ROW_FLOATS + 96 + lane, lm, policy);
+                    om = __ldcs(lm);
             }
             const bool last_row = ++l_r == ry_eff;
             lp += row_bytes;
@@ -264,12 +255,10 @@ __global__ void __maxnreg__(GENPK_SWEEP_MAXREG) deposit_sweep_kernel(const __gri
                 if (MASS) lm += inc;
             }
         }
-        cp_async_commit();
     };
 #pragma unroll
-    for (int q = 0; q < SWEEP_STAGES - 1; q++)
-        issue_load(q);
-    int q_step = 0;
+    for (int k = 0; k < SWEEP_AHEAD; k++)
+        issue_load(ax[k], ay[k], az[k], am[k]);
 
     // One row slot: merge what the previous plane left for this row (x), leave this row's high-x
     // sums for the next plane, then hand the z1 sum to the next lane (z) and emit.
@@ -348,14 +337,18 @@ __global__ void __maxnreg__(GENPK_SWEEP_MAXREG) deposit_sweep_kernel(const __gri
         acc2_t *xv = xv0;
         key_t *xk = xk0;
         for (int r = 0; r < ry_eff; r++) {
-            issue_load(q_step + SWEEP_STAGES - 1);
-            cp_async_wait<SWEEP_STAGES - 1>();
-            const float *row = my_ring + (q_step & (SWEEP_STAGES - 1)) * SWEEP_ROW_FLOATS;
-            q_step++;
-            const float px = row[0], py = row[1], pz = row[2];
+            const float px = ax[0], py = ay[0], pz = az[0];
             double m = a.cmass;
             if (MASS)
-                m = (double)row[96 - 2 * lane];                             // ring[slot][96 + lane], fieldize.cpp:63
+                m = (double)am[0];                                          // fieldize.cpp:63
+#pragma unroll
+            for (int k = 0; k + 1 < SWEEP_AHEAD; k++) {
+                ax[k] = ax[k + 1];
+                ay[k] = ay[k + 1];
+                az[k] = az[k + 1];
+                am[k] = am[k + 1];
+            }
+            issue_load(ax[SWEEP_AHEAD - 1], ay[SWEEP_AHEAD - 1], az[SWEEP_AHEAD - 1], am[SWEEP_AHEAD - 1]);
             const bool live = lane_in_row && (FULL || p < a.n);
             const bool emit_b = FULL ? emit_b_full : ((pair_in_row && p + 1 < a.n) ? lane < 31 : owner_lane);
             const long long p_now = p;
@@ -493,7 +486,6 @@ __global__ void __maxnreg__(GENPK_SWEEP_MAXREG) deposit_sweep_kernel(const __gri
             atomicMax(a.touched + 1, t_hi + 1);
         }
     }
-    cp_async_wait<0>();
 }
 
 // ---------------------------------------------------------------------------------
@@ -570,8 +562,7 @@ template <bool FIXED, typename key_t> static const void *sweep_pick(bool full, b
 static size_t sweep_smem(int ry, bool fixed, bool key32)
 {
     (void)fixed;
-    return (size_t)(ry + 1) * SWEEP_THREADS * (16 + (key32 ? 4 : 8)) +
-           (size_t)SWEEP_WARPS * SWEEP_STAGES * SWEEP_ROW_FLOATS * sizeof(float);
+    return (size_t)(ry + 1) * SWEEP_THREADS * (16 + (key32 ? 4 : 8));
 }
 
 // device scratch of the coupled / zero-ahead sweep: arrived[n_planes], zdone[umax], overflow flag;
