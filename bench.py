@@ -61,6 +61,8 @@ def parse_args():
     ap.add_argument("--sweep-ry", type=int, default=0)
     ap.add_argument("--sweep-couple", type=int, default=-1, help="planes a sweep warp may lead the slowest one by (0 = uncoupled)")
     ap.add_argument("--za-zero-ctas", type=int, default=0)
+    ap.add_argument("--sweep-couple-step", type=int, default=0)
+    ap.add_argument("--sweep-poll-strong", action="store_true")
     ap.add_argument("--no-self-check", action="store_true", help="skip the comparison with the committed reference fixtures")
     ap.add_argument("--power", default="cached", choices=["cached", "fused"],
                     help="binning pass: geometry sums cached in the context, or recomputed every call")
@@ -421,6 +423,10 @@ def run_ours(args):
         ctx.set_option(api.OPT_SWEEP_COUPLE, args.sweep_couple)
     if args.za_zero_ctas:
         ctx.set_option(api.OPT_ZA_ZERO_CTAS, args.za_zero_ctas)
+    if args.sweep_couple_step:
+        ctx.set_option(api.OPT_SWEEP_COUPLE_STEP, args.sweep_couple_step)
+    if args.sweep_poll_strong:
+        ctx.set_option(api.OPT_SWEEP_POLL_WEAK, 0)
     if args.march_ry:
         ctx.set_option(api.OPT_MARCH_RY, args.march_ry)
     if args.march_rx:

@@ -256,6 +256,14 @@ int genpk_set_option(genpk_ctx *ctx, int option, int64_t value)
         if (value < 0 || value > 4096) break;
         ctx->sweep_couple = (int)value;
         return 0;
+    case GENPK_OPT_SWEEP_COUPLE_STEP:
+        if (value < 1 || value > 4096) break;
+        ctx->sweep_couple_step = (int)value;
+        return 0;
+    case GENPK_OPT_SWEEP_POLL_WEAK:
+        if (value != 0 && value != 1) break;
+        ctx->sweep_poll_weak = (int)value;
+        return 0;
     case GENPK_OPT_ZA_DEFERRED:
         if (value < 1 || value > (1 << 20)) break;
         ctx->za_def_per_col = (int)value;

@@ -132,7 +132,9 @@ struct genpk_ctx {
     int za_slack = 2;                         // lattice planes between clearing a plane and first needing it
     int za_def_per_col = 4096;                // deferred-particle list entries per list
     int za_zero_ctas = 0;                     // CTAs that only clear planes (0: a third of the SM count)
-    int sweep_couple = 6;                     // a warp starts lattice plane x once every warp has started x - couple (0: uncoupled)
+    int sweep_couple_step = 4;                // sweep warps leave an arrival mark every so many lattice planes ...
+    int sweep_couple = 2;                     // ... and wait for everybody's mark `couple` marks back (0: uncoupled)
+    int sweep_poll_weak = 1;                  // marks are probed with weak L1-bypassing loads
     unsigned *d_za_zdone = nullptr;
     int za_zdone_cap = 0;
     unsigned *d_za_def = nullptr;

@@ -62,8 +62,10 @@ struct SweepArgs {
     long long za_uc0;            // expected plane (in u) of lattice plane x_begin
     unsigned long long za_gstep; // grid planes per lattice plane, 32.32 fixed point
     int n_zero_ctas;             // the first n_zero_ctas CTAs of the launch only clear planes (zero ahead)
-    int couple;                  // > 0: a warp starts lattice plane x only when every warp has started plane x - couple
-    unsigned *arrived;           // [planes swept] warps that have started lattice plane x
+    int couple_step;             // every couple_step lattice planes a warp leaves an arrival mark ...
+    int couple;                  // ... and waits until every warp has left the mark `couple` marks back (0: never waits)
+    int poll_weak;               // probe the marks with weak L1-bypassing loads instead of relaxed.gpu ones
+    unsigned *arrived;           // [marks] warps that have left mark j (= started lattice plane j * couple_step)
     unsigned *zdone;             // [za_umax] zero CTAs that have cleared their share of plane u
     size_t zero_units;           // 16-byte units per grid plane
     unsigned *def_count;         // [SWEEP_DEF_LISTS] deferred particles per list (a column appends to list col % LISTS)
@@ -110,13 +112,23 @@ constexpr int SWEEP_DEF_LISTS = 1024;    // deferred-particle lists (a column ap
 // Spin until *counter >= want.  Relaxed loads with a back-off: what follows the wait are reductions
 // performed at L2, which the loop's exit orders after the load (no L1 involved, so no acquire --
 // an acquire load here costs a whole-L1 invalidate per probe).
-__device__ __forceinline__ void poll_at_least(const unsigned *counter, unsigned want)
+__device__ __forceinline__ unsigned poll_load(const unsigned *counter, int weak)
 {
     unsigned seen;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+    // weak: a plain load that bypasses L1 (ld.global.cg).  A relaxed.gpu load is "strong": it queues behind the
+    // thread's own outstanding reductions, and a probe then costs microseconds.
+    if (weak)
+        asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+    else
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+    return seen;
+}
+__device__ __forceinline__ void poll_at_least(const unsigned *counter, unsigned want, int weak)
+{
+    unsigned seen = poll_load(counter, weak);
     while (seen < want) {
         __nanosleep(64);
-        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+        seen = poll_load(counter, weak);
     }
 }
 
@@ -133,12 +145,14 @@ __device__ __noinline__ void sweep_zero_role(const DepositArgs &a, const SweepAr
     const size_t lo = (size_t)z * share;
     size_t hi = lo + share;
     if (hi > g.zero_units) hi = g.zero_units;
-    int lead = 0;                                             // the sweep's leaders have started this lattice plane
+    const int step = g.couple_step;
+    const int n_marks = (n_planes + step - 1) / step;
+    int lead = 0;                                             // the sweep's leaders have started lattice plane lead * step
     for (int u = g.za_upre; u < g.za_umax; u++) {
-        // plane u comes into reach when the leaders start lattice plane x with uc(x + slack) + ahead > u
+        // plane u comes into reach when the leaders start a lattice plane x with uc(x + slack) + ahead > u
         if (tid == 0) {
-            while (lead < n_planes - 1 && sweep_uc(g, g.x_begin + lead + g.za_slack) + g.za_ahead <= u) {
-                poll_at_least(g.arrived + lead + 1, 1u);
+            while (lead < n_marks - 1 && sweep_uc(g, g.x_begin + (long long)lead * step + g.za_slack) + g.za_ahead <= u) {
+                poll_at_least(g.arrived + lead + 1, 1u, g.poll_weak);
                 lead++;
             }
             s_lead = lead;
@@ -299,6 +313,7 @@ __global__ void __maxnreg__(GENPK_SWEEP_MAXREG) deposit_sweep_kernel(const __gri
 
     // ---- zero ahead / coupling: planes known to be clear by this warp ----
     int ready = g.za_upre;
+    int to_mark = 1, mark = 0;                               // planes until the next arrival mark / its index
     unsigned long long gacc = 0x80000000ull;                 // (x - x_begin) * gstep + 1/2
 
     acc_t c00 = 0, c10 = 0, c01 = 0, c11 = 0;                // y-carry: the four high-y sums of the previous row
@@ -312,12 +327,14 @@ __global__ void __maxnreg__(GENPK_SWEEP_MAXREG) deposit_sweep_kernel(const __gri
         // Coupling: every warp announces the lattice plane it starts and starts plane x only when all
         // warps have started plane x - couple, so the front of the sweep stays `couple` planes thick
         // (L2 locality of the reductions; the zero CTAs clear just ahead of the leaders).
-        if (g.arrived) {
+        if (g.arrived && --to_mark == 0) {
+            to_mark = g.couple_step;
             if (lane == 0) {
-                asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(g.arrived + xi), "r"(1u) : "memory");
-                if (g.couple > 0 && xi >= g.couple)
-                    poll_at_least(g.arrived + (xi - g.couple), (unsigned)g.ncols);
+                asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(g.arrived + mark), "r"(1u) : "memory");
+                if (g.couple > 0 && mark >= g.couple)
+                    poll_at_least(g.arrived + (mark - g.couple), (unsigned)g.ncols, g.poll_weak);
             }
+            mark++;
             __syncwarp();
         }
         if (ZA) {
@@ -328,7 +345,7 @@ __global__ void __maxnreg__(GENPK_SWEEP_MAXREG) deposit_sweep_kernel(const __gri
             if (ready < need) {
                 if (lane == 0)
                     for (int u = ready; u < need; u++)
-                        poll_at_least(g.zdone + u, (unsigned)g.n_zero_ctas);
+                        poll_at_least(g.zdone + u, (unsigned)g.n_zero_ctas, g.poll_weak);
                 ready = need;
                 __syncwarp();
             }
@@ -659,6 +676,8 @@ int launch_sweep(genpk_ctx *ctx, const DepositArgs &a, long long n0, long long n
     g.ncols = (int)(g.nzs * nyb);
     g.n_zero_ctas = n_zero;
     g.couple = one_wave ? ctx->sweep_couple : 0;
+    g.couple_step = ctx->sweep_couple_step > 0 ? ctx->sweep_couple_step : 1;
+    g.poll_weak = ctx->sweep_poll_weak;
     const size_t smem = sweep_smem(ry, ctx->fixed, key32);
     GENPK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long blocks = ((long long)g.ncols + SWEEP_WARPS - 1) / SWEEP_WARPS + n_zero;
@@ -699,7 +718,7 @@ int launch_sweep(genpk_ctx *ctx, const DepositArgs &a, long long n0, long long n
     g.za_periodic = a.slab ? 0 : 1;
     g.za_umax = n_planes;
     g.za_ahead = ahead;
-    g.za_slack = ctx->za_slack;
+    g.za_slack = ctx->za_slack > g.couple_step ? ctx->za_slack : g.couple_step;   // the leaders are known to one mark
     // grid planes per lattice plane of the GLOBAL lattice (a slab rank holds 1/nranks of its planes)
     const double planes_per = (double)sg.nx / (double)n2;
     g.za_gstep = (unsigned long long)llround(planes_per * 4294967296.0);

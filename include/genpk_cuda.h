@@ -71,8 +71,11 @@ extern "C" {
 #define GENPK_OPT_ZA_SLACK      15     /* zero ahead: lattice planes between clearing a grid plane and first needing it */
 #define GENPK_OPT_ZA_DEFERRED   16     /* zero ahead: entries per clean-up list (1024 lists; default 4096) */
 #define GENPK_OPT_ZA_ZERO_CTAS  17     /* zero ahead: CTAs of the sweep launch that only clear planes (0 = a third of the SMs) */
-#define GENPK_OPT_SWEEP_COUPLE  18     /* a sweep warp starts lattice plane x once every warp has started plane x - N
-                                          (default 6; 0 = uncoupled): keeps the front of the sweep N planes thick */
+#define GENPK_OPT_SWEEP_COUPLE  18     /* sweep warps leave an arrival mark every STEP lattice planes and go on only when every
+                                          warp has left the mark N marks back (default 2; 0 = uncoupled): keeps the front of
+                                          the sweep about N*STEP planes thick, which is what keeps the reductions in L2 */
+#define GENPK_OPT_SWEEP_COUPLE_STEP 19 /* STEP above (default 4) */
+#define GENPK_OPT_SWEEP_POLL_WEAK 20   /* 1 (default): marks are probed with weak L1-bypassing loads; 0: relaxed.gpu loads */
 /* ---- binning pass selection (genpk_set_option(ctx, GENPK_OPT_POWER, v)) ------------ */
 #define GENPK_OPT_POWER          3
 #define GENPK_POWER_CACHED       0     /* sum|k| and mode counts per bin depend on the grid only: computed
