@@ -126,7 +126,8 @@ struct genpk_ctx {
     int march_ry = 8, march_rx = 8;           // rows / planes one warp marches over
     // lattice sweep (deposit_sweep.cu)
     int sweep = 1;                            // AUTO picks the sweep kernel for lattice input (0: the march kernel)
-    int sweep_ry = 0;                         // rows per column (0: as few as keep every column resident)
+    int sweep_ry = 0;                         // rows per column (0: 8 in task mode; as few as keep every column resident otherwise)
+    int sweep_rx = 8;                         // > 0: task mode, blocks of rx lattice planes; 0: one persistent sweep (coupled, may zero ahead)
     int zero_ahead = 1;                       // genpk_grid_zero is lazy; a sweep that follows clears the grid ahead of its front
     int za_window = 0;                        // planes ahead of the expected plane kept clear (0: from the order probe)
     int za_slack = 2;                         // lattice planes between clearing a plane and first needing it

@@ -389,7 +389,7 @@ int deposit_device(genpk_ctx *ctx, int which, const float *pos, const float *mas
         info.dx_mean = plan->dx_mean;
         info.dx_dev = plan->dx_dev;
         // a pending genpk_grid_zero: the sweep clears the grid ahead of its own front when it can
-        if (ctx->zero_pending[which] && ctx->zero_ahead) {
+        if (ctx->zero_pending[which] && ctx->zero_ahead && ctx->sweep_rx == 0) {
             bool possible = true;
             if (a.slab)
                 if (int rc = touched_set(ctx, which, 0x7fffffff, -1)) return rc;     // cleared grid: nothing touched yet

@@ -39,8 +39,12 @@ constexpr int SWEEP_THREADS = GENPK_SWEEP_THREADS;
 constexpr int SWEEP_WARPS = SWEEP_THREADS / 32;
 constexpr int SWEEP_RY_MAX = 21;         // x-carry slots per thread: (ry + 1) * 20 B * 128 threads <= 56 KB
 #ifndef GENPK_SWEEP_AHEAD
-#define GENPK_SWEEP_AHEAD 2
+#define GENPK_SWEEP_AHEAD 1
 #endif
+#ifndef GENPK_SWEEP_PREFETCH
+#define GENPK_SWEEP_PREFETCH 5
+#endif
+constexpr int SWEEP_PREFETCH = GENPK_SWEEP_PREFETCH;   // rows ahead that are prefetched into L2
 constexpr int SWEEP_AHEAD = GENPK_SWEEP_AHEAD;   // particle rows in flight per lane (registers)
 #ifndef GENPK_SWEEP_MAXREG
 #define GENPK_SWEEP_MAXREG 96
@@ -49,6 +53,8 @@ constexpr int SWEEP_AHEAD = GENPK_SWEEP_AHEAD;   // particle rows in flight per 
 struct SweepArgs {
     long long n0, n1;            // lattice row length, rows per plane (z fastest)
     long long x_begin, x_end;    // lattice planes swept
+    int rx;                      // > 0: blockIdx.y splits the sweep into blocks of rx lattice planes (independent tasks in
+                                 // launch order: the front is then rx planes thick without any waiting); 0: one sweep
     int ry;                      // lattice rows per column
     int nzs;                     // 31-particle segments per row
     int ncols;                   // nzs * ceil(n1 / ry) columns, one warp each
@@ -241,8 +247,37 @@ __global__ void __maxnreg__(GENPK_SWEEP_MAXREG) deposit_sweep_kernel(const __gri
     asm volatile("" : "+l"(row_bytes), "+l"(block_adj_bytes));
     const char *lp = reinterpret_cast<const char *>(a.pos + 3 * p);
     const float *lm = MASS ? a.mass + p : nullptr;
-    const int n_planes = (int)(g.x_end - g.x_begin);
+    // the lattice planes of this task
+    long long x_first = g.x_begin, x_last = g.x_end;
+    if (g.rx > 0) {
+        x_first = g.x_begin + (long long)blockIdx.y * g.rx;
+        x_last = x_first + g.rx < g.x_end ? x_first + g.rx : g.x_end;
+        const long long skip = (x_first - g.x_begin) * g.n1 * g.n0;
+        p += skip;
+        lp_index += skip;
+        lp += 12 * skip;
+        if (MASS) lm += skip;
+    }
+    const int n_planes = (int)(x_last - x_first);
     int loads_left = n_planes * ry_eff, l_r = 0;
+    // prefetch cursor: the same walk, SWEEP_PREFETCH rows further on (L2 only; the loads proper run one row ahead)
+    const char *pp = lp;
+    int pf_left = loads_left, pf_r = 0;
+    auto prefetch_row = [&]() {
+        if (pf_left > 0) {
+            pf_left--;
+            if (FULL && lane_in_row)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(pp));
+            pp += row_bytes;
+            if (++pf_r == ry_eff) {
+                pp += block_adj_bytes;
+                pf_r = 0;
+            }
+        }
+    };
+#pragma unroll
+    for (int k = 0; k < SWEEP_PREFETCH; k++)
+        prefetch_row();
     float ax[SWEEP_AHEAD], ay[SWEEP_AHEAD], az[SWEEP_AHEAD], am[SWEEP_AHEAD];   // rows in flight, oldest first
 #pragma unroll
     for (int k = 0; k < SWEEP_AHEAD; k++)
@@ -366,6 +401,7 @@ __global__ void __maxnreg__(GENPK_SWEEP_MAXREG) deposit_sweep_kernel(const __gri
                 am[k] = am[k + 1];
             }
             issue_load(ax[SWEEP_AHEAD - 1], ay[SWEEP_AHEAD - 1], az[SWEEP_AHEAD - 1], am[SWEEP_AHEAD - 1]);
+            prefetch_row();
             const bool live = lane_in_row && (FULL || p < a.n);
             const bool emit_b = FULL ? emit_b_full : ((pair_in_row && p + 1 < a.n) ? lane < 31 : owner_lane);
             const long long p_now = p;
@@ -418,7 +454,7 @@ __global__ void __maxnreg__(GENPK_SWEEP_MAXREG) deposit_sweep_kernel(const __gri
                                 const int li = col & (SWEEP_DEF_LISTS - 1);
                                 const unsigned slot = atomicAdd(&g.def_count[li], 1u);
                                 // (p is only tracked when the step needs it)
-                                const long long q = (!FULL || MASS) ? p_now : ((g.x_begin + xi) * g.n1 + y0 + r) * g.n0 + 31LL * zseg + lane;
+                                const long long q = (!FULL || MASS) ? p_now : ((x_first + xi) * g.n1 + y0 + r) * g.n0 + 31LL * zseg + lane;
                                 if (slot < (unsigned)g.def_cap)
                                     reinterpret_cast<unsigned long long *>(g.def_list)[(size_t)li * g.def_cap + slot] = (unsigned long long)q;
                                 else
@@ -638,9 +674,33 @@ int launch_sweep(genpk_ctx *ctx, const DepositArgs &a, long long n0, long long n
     };
     const void *kern = pick(za);
     int ry = 0;
+    const int ry_cap = (int)(n1 < SWEEP_RY_MAX ? n1 : SWEEP_RY_MAX);
+    // ---- task mode: blocks of rx lattice planes x columns, independent CTAs in launch order ----
+    if (ctx->sweep_rx > 0 && !za) {
+        ry = ctx->sweep_ry > 0 ? ctx->sweep_ry : 8;
+        if (ry > ry_cap) ry = ry_cap;
+        g.ry = ry;
+        g.rx = (int)(n2 < ctx->sweep_rx ? n2 : ctx->sweep_rx);
+        g.ncols = (int)(g.nzs * ((n1 + ry - 1) / ry));
+        const size_t smem = sweep_smem(ry, ctx->fixed, key32);
+        GENPK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const long long bx = ((long long)g.ncols + SWEEP_WARPS - 1) / SWEEP_WARPS, by = (n2 + g.rx - 1) / g.rx;
+        if (bx > 0x7fffffffLL || by > 65535) {
+            set_error("deposit: %lld x %lld sweep tasks exceed the launch grid", bx, by);
+            return 1;
+        }
+        DepositArgs args = a;
+        ctx->last_sweep[0] = ry;
+        ctx->last_sweep[1] = g.ncols;
+        ctx->last_sweep[2] = 0;
+        ctx->last_sweep[3] = 0;
+        void *params[] = {(void *)&args, (void *)&g};
+        GENPK_CUDA_OK(cudaLaunchKernel(kern, dim3((unsigned)bx, (unsigned)by), dim3(SWEEP_THREADS), params, smem, ctx->stream));
+        ctx->launches++;
+        return 0;
+    }
     // zero ahead: a few CTAs of the launch do nothing but clear planes ahead of the sweep
     const int n_zero = za ? (ctx->za_zero_ctas > 0 ? ctx->za_zero_ctas : ctx->sm_count / 3) : 0;
-    const int ry_cap = (int)(n1 < SWEEP_RY_MAX ? n1 : SWEEP_RY_MAX);
     // (at least 4 rows when the plane has them: every block of rows pays one extra slot for its last carry)
     const int ry_lo = ctx->sweep_ry > 0 ? (ctx->sweep_ry < ry_cap ? ctx->sweep_ry : ry_cap) : (ry_cap < 4 ? ry_cap : 4);
     for (int t = ry_lo; t <= ry_cap; t++) {

@@ -75,6 +75,9 @@ extern "C" {
                                           warp has left the mark N marks back (default 2; 0 = uncoupled): keeps the front of
                                           the sweep about N*STEP planes thick, which is what keeps the reductions in L2 */
 #define GENPK_OPT_SWEEP_COUPLE_STEP 19 /* STEP above (default 4) */
+#define GENPK_OPT_SWEEP_RX      21     /* N > 0 (default 8): the sweep runs as independent tasks of N lattice planes x one block of
+                                          rows x one segment, in launch order (no waiting; the grid is cleared by a memset);
+                                          0: one persistent sweep over all planes, coupled, which can clear the grid ahead of itself */
 #define GENPK_OPT_SWEEP_POLL_WEAK 20   /* 1 (default): marks are probed with weak L1-bypassing loads; 0: relaxed.gpu loads */
 /* ---- binning pass selection (genpk_set_option(ctx, GENPK_OPT_POWER, v)) ------------ */
 #define GENPK_OPT_POWER          3

@@ -57,6 +57,7 @@ def test_sweep_fixed_point_bit_exact(port, n_side, dims, hint, za):
     with gp.Context(dims, flags=api.FLAG_FIXED_POINT) as ctx:
         ctx.set_deposit_mode(api.DEPOSIT_SWEEP)
         ctx.set_option(api.OPT_ZERO_AHEAD, za)
+        ctx.set_option(api.OPT_SWEEP_RX, 0 if za else 8)     # zero ahead needs the persistent sweep
         if hint == "right":
             ctx.set_lattice_hint(n_side, n_side)
         elif hint == "wrong":
@@ -87,6 +88,7 @@ def test_zero_ahead_windows_and_deferred_particles(port, window, slack, defcap, 
     with gp.Context(dims, flags=api.FLAG_FIXED_POINT if fixed else 0) as ctx:
         ctx.set_deposit_mode(api.DEPOSIT_SWEEP)
         ctx.set_lattice_hint(n_side, n_side)
+        ctx.set_option(api.OPT_SWEEP_RX, 0)
         ctx.set_option(api.OPT_ZA_WINDOW, window)
         ctx.set_option(api.OPT_ZA_SLACK, slack)
         ctx.set_option(api.OPT_ZA_DEFERRED, defcap)
@@ -116,7 +118,9 @@ def test_sweep_coupling_and_zero_ctas(port, couple, zero_ctas, za):
     with gp.Context(dims, flags=api.FLAG_FIXED_POINT) as ctx:
         ctx.set_deposit_mode(api.DEPOSIT_SWEEP)
         ctx.set_lattice_hint(n_side, n_side)
+        ctx.set_option(api.OPT_SWEEP_RX, 0)
         ctx.set_option(api.OPT_SWEEP_COUPLE, couple)
+        ctx.set_option(api.OPT_SWEEP_COUPLE_STEP, 1 + couple % 3)
         ctx.set_option(api.OPT_ZA_ZERO_CTAS, zero_ctas)
         ctx.set_option(api.OPT_ZERO_AHEAD, za)
         poison(ctx)
@@ -129,7 +133,8 @@ def test_sweep_coupling_and_zero_ctas(port, couple, zero_ctas, za):
 
 
 @pytest.mark.parametrize("ry", [1, 2, 3, 7, 10, 21])
-def test_sweep_column_heights(port, ry):
+@pytest.mark.parametrize("rx", [0, 1, 3, 8, 100])
+def test_sweep_column_heights_and_task_lengths(port, ry, rx):
     n_side, dims, box = 44, 44, 100.0
     dpos, pos = synth(api.SYNTH_CLUSTERED, n_side, dims, box)
     want = fixed_want(port, box, dims, pos, None, 1.0)
@@ -137,6 +142,7 @@ def test_sweep_column_heights(port, ry):
         ctx.set_deposit_mode(api.DEPOSIT_SWEEP)
         ctx.set_lattice_hint(n_side, n_side)
         ctx.set_option(api.OPT_SWEEP_RY, ry)
+        ctx.set_option(api.OPT_SWEEP_RX, rx)
         poison(ctx)
         ctx.grid_zero()
         ctx.deposit_dev(dpos.data_ptr(), n_side ** 3, 0, 1.0, box)
@@ -218,7 +224,7 @@ def test_sweep_fp64_vs_oracle_and_auto(port):
         ctx.synchronize()
         o, sw = ctx.last_order(), ctx.last_sweep()
     assert o["lattice"] == 1 and o["n0"] == n_side and o["n1"] == n_side, o
-    assert sw["zero_ahead"] == 1 and sw["columns"] > 0, sw
+    assert sw["columns"] > 0, sw                             # AUTO took the sweep kernel
     assert_grid_close(got, want)
     assert abs(got.sum() - n) <= 1e-10 * n
 
@@ -251,6 +257,7 @@ def test_additive_deposit_after_zero_ahead(port):
     with gp.Context(dims, flags=api.FLAG_FIXED_POINT) as ctx:
         ctx.set_deposit_mode(api.DEPOSIT_SWEEP)
         ctx.set_lattice_hint(n_side, n_side)
+        ctx.set_option(api.OPT_SWEEP_RX, 0)
         poison(ctx)
         ctx.grid_zero()
         ctx.deposit_dev(dpos.data_ptr(), n, 0, 1.0, box)
@@ -288,6 +295,7 @@ def test_sweep_in_slab_contexts(port, P, ghost, za):
         for r in range(P):
             st[r].ctx.set_deposit_mode(api.DEPOSIT_SWEEP)
             st[r].ctx.set_option(api.OPT_ZERO_AHEAD, za)
+            st[r].ctx.set_option(api.OPT_SWEEP_RX, 0 if za else 8)
             st[r].ctx.set_lattice_hint(n_side, n_side)
             st[r].ctx.grid_upload(np.full(st[r].ctx.grid_doubles(), 1.0e300))
             st[r].zero()
@@ -357,7 +365,6 @@ def test_host_chunks_of_a_lattice_bit_exact(n_side, dims):
     with gp.Context(dims, flags=api.FLAG_FIXED_POINT) as ctx:
         ctx.grid_zero()
         ctx.deposit_dev(dpos.data_ptr(), n, 0, 1.0, box)
-        assert ctx.last_sweep()["zero_ahead"] == 1
         want = ctx.grid_download_fixed()
         ctx.grid_zero()
         ctx.deposit(pos, None, 1.0, box)                 # numpy array = host buffer
