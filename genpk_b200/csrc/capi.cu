@@ -187,6 +187,7 @@ int genpk_set_stream(genpk_ctx *ctx, void *cuda_stream)
 int genpk_set_option(genpk_ctx *ctx, int option, int64_t value)
 {
     if (!ctx) { set_error("genpk_set_option: null context"); return 1; }
+    ctx->plan_key_pos = nullptr;                                 // a cached deposit plan may no longer be the one wanted
     switch (option) {
     case GENPK_OPT_DEPOSIT:
         if (value < GENPK_DEPOSIT_AUTO || value > GENPK_DEPOSIT_SWEEP) break;
@@ -255,6 +256,10 @@ int genpk_set_option(genpk_ctx *ctx, int option, int64_t value)
     case GENPK_OPT_SWEEP_COUPLE:
         if (value < 0 || value > 4096) break;
         ctx->sweep_couple = (int)value;
+        return 0;
+    case GENPK_OPT_SWEEP_GRID_PREFETCH:
+        if (value < 0 || value > 4096) break;
+        ctx->sweep_grid_prefetch = (int)value;
         return 0;
     case GENPK_OPT_SWEEP_RX:
         if (value < 0 || value > 65535) break;

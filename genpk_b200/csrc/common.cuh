@@ -67,6 +67,15 @@ enum Stage { ST_DEPOSIT = 0, ST_FFT = 1, ST_POWER = 2, ST_SORT = 3, ST_ZERO = 4,
 
 }  // namespace genpk
 
+namespace genpk {
+struct DepositPlanPod {
+    int mode = 0;
+    long long n0 = 0, n1 = 0;
+    bool have_dx = false;
+    int dx_mean = 0, dx_dev = 0;
+};
+}  // namespace genpk
+
 struct genpk_ctx {
     genpk::SlabGeom g;
     unsigned flags = 0;
@@ -125,8 +134,10 @@ struct genpk_ctx {
     long long lattice_n0 = 0, lattice_n1 = 0; // caller's hint: particles per lattice row, rows per plane
     int march_ry = 8, march_rx = 8;           // rows / planes one warp marches over
     // lattice sweep (deposit_sweep.cu)
-    int sweep = 1;                            // AUTO picks the sweep kernel for lattice input (0: the march kernel)
+    int sweep = 0;                            // 1: AUTO picks the sweep kernel for lattice input; 0 (default): the march kernel
+                                              // (measured equal on C3, profiles/r02; the march kernel is the longer-serving one)
     int sweep_ry = 0;                         // rows per column (0: 8 in task mode; as few as keep every column resident otherwise)
+    int sweep_grid_prefetch = 0;              // task mode: 1 + planes ahead of a task's own planes whose grid lines it prefetches (0: off)
     int sweep_rx = 8;                         // > 0: task mode, blocks of rx lattice planes; 0: one persistent sweep (coupled, may zero ahead)
     int zero_ahead = 1;                       // genpk_grid_zero is lazy; a sweep that follows clears the grid ahead of its front
     int za_window = 0;                        // planes ahead of the expected plane kept clear (0: from the order probe)
@@ -155,6 +166,13 @@ struct genpk_ctx {
     bool peers_set = false;
     int twiddle_n = 0;
     long long last_order[7] = {0, 0, 0, 0, 0, 0, 0};   // last probe verdict (diagnostics)
+    // the plan of the last probed stream: a deposit of the same device array (pointer, count, box) reuses it
+    // instead of probing and synchronising again (a plan is only ever a performance choice)
+    const void *plan_key_pos = nullptr;
+    int64_t plan_key_n = 0;
+    double plan_key_box = 0;
+    int plan_key_mode = -1;
+    genpk::DepositPlanPod plan_cached;
 
     // timing: a ring of event pairs per stage, summed on request (no host sync while recording)
     static constexpr int EV_SLOTS = 128;

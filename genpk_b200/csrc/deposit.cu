@@ -379,8 +379,32 @@ int deposit_device(genpk_ctx *ctx, int which, const float *pos, const float *mas
     // fits in L2) => DIRECT, incoherent => SORTED.  The verdict is one small D2H.
     DepositPlan local;
     if (!plan) {
-        if (int rc = deposit_plan(ctx, pos, n, boxsize, &local))
-            return rc;
+        const bool hit = ctx->plan_key_pos == pos && ctx->plan_key_n == n && ctx->plan_key_box == boxsize &&
+                         ctx->plan_key_mode == ctx->deposit_mode * 2 + ctx->sweep;
+        if (hit) {
+            local.mode = ctx->plan_cached.mode;
+            local.n0 = ctx->plan_cached.n0;
+            local.n1 = ctx->plan_cached.n1;
+            local.have_dx = ctx->plan_cached.have_dx;
+            local.dx_mean = ctx->plan_cached.dx_mean;
+            local.dx_dev = ctx->plan_cached.dx_dev;
+        } else {
+            // the grid can be cleared while the probe runs and its verdict travels to the host
+            if (ctx->zero_pending[which] && !(ctx->zero_ahead && ctx->sweep_rx == 0 && ctx->sweep))
+                if (int rc = materialize_zero(ctx, which)) return rc;
+            if (int rc = deposit_plan(ctx, pos, n, boxsize, &local))
+                return rc;
+            ctx->plan_key_pos = pos;
+            ctx->plan_key_n = n;
+            ctx->plan_key_box = boxsize;
+            ctx->plan_key_mode = ctx->deposit_mode * 2 + ctx->sweep;
+            ctx->plan_cached.mode = local.mode;
+            ctx->plan_cached.n0 = local.n0;
+            ctx->plan_cached.n1 = local.n1;
+            ctx->plan_cached.have_dx = local.have_dx;
+            ctx->plan_cached.dx_mean = local.dx_mean;
+            ctx->plan_cached.dx_dev = local.dx_dev;
+        }
         plan = &local;
     }
     if (plan->mode == GENPK_DEPOSIT_SWEEP) {

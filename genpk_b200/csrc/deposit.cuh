@@ -155,6 +155,18 @@ __device__ __forceinline__ void axis_fast(float p, double units, int &f, double 
     wl = __dsub_rn(1.0, wh);                                // :69  tx
 }
 
+// The same with the high word of x + 1.5*2^52, which is 0x43380000 exactly when 0 <= x < 2^32.
+__device__ __forceinline__ void axis_fast_hi(float p, double units, int &f, int &hi, double &wl, double &wh)
+{
+    const double magic = 6755399441055744.0;
+    const double x = __dmul_rn((double)p, units);           // fieldize.cpp:66
+    const double t = __dadd_rd(x, magic);
+    f = __double2loint(t);                                  // :67
+    hi = __double2hiint(t);
+    wh = __dsub_rn(x, __dsub_rn(t, magic));                 // :68  dx
+    wl = __dsub_rn(1.0, wh);                                // :69  tx
+}
+
 // lo += from when take (one predicated add instead of add + two selects)
 __device__ __forceinline__ void add_if(double &lo, double from, int take)
 {

@@ -38,14 +38,7 @@ namespace genpk {
 constexpr int SWEEP_THREADS = GENPK_SWEEP_THREADS;
 constexpr int SWEEP_WARPS = SWEEP_THREADS / 32;
 constexpr int SWEEP_RY_MAX = 21;         // x-carry slots per thread: (ry + 1) * 20 B * 128 threads <= 56 KB
-#ifndef GENPK_SWEEP_AHEAD
-#define GENPK_SWEEP_AHEAD 1
-#endif
-#ifndef GENPK_SWEEP_PREFETCH
-#define GENPK_SWEEP_PREFETCH 5
-#endif
-constexpr int SWEEP_PREFETCH = GENPK_SWEEP_PREFETCH;   // rows ahead that are prefetched into L2
-constexpr int SWEEP_AHEAD = GENPK_SWEEP_AHEAD;   // particle rows in flight per lane (registers)
+
 #ifndef GENPK_SWEEP_MAXREG
 #define GENPK_SWEEP_MAXREG 96
 #endif
@@ -53,6 +46,9 @@ constexpr int SWEEP_AHEAD = GENPK_SWEEP_AHEAD;   // particle rows in flight per 
 struct SweepArgs {
     long long n0, n1;            // lattice row length, rows per plane (z fastest)
     long long x_begin, x_end;    // lattice planes swept
+    int grid_prefetch;           // task mode: planes ahead whose grid lines a task pulls into L2 when it starts (0: off)
+    long long gp_x0;             // expected grid plane (local) of lattice plane x_begin, for that prefetch
+    unsigned long long gp_xstep, gp_ystep, gp_zstep;   // grid planes / rows / cells per lattice plane / row / site, 32.32
     int rx;                      // > 0: blockIdx.y splits the sweep into blocks of rx lattice planes (independent tasks in
                                  // launch order: the front is then rx planes thick without any waiting); 0: one sweep
     int ry;                      // lattice rows per column
@@ -224,7 +220,7 @@ __global__ void __maxnreg__(GENPK_SWEEP_MAXREG) deposit_sweep_kernel(const __gri
     flags |= (pair_in_row ? lane < 31 : (flags & 2) != 0) ? 4 : 0;
     asm volatile("" : "+r"(flags));                          // keep it a register: not rematerialised from 64-bit compares
     const bool lane_in_row = flags & 1, owner_lane = flags & 2, emit_b_full = flags & 4;
-    const float pos_limit = (float)(2.0e9 / a.units);        // |x| < 2e9 cells, as in axis_cell
+    const float pos_limit = (float)(2.0e9 / a.units);        // |x| < 2e9 cells, as in axis_cell (rare path only)
     const int dims = a.dims;
     const double units = a.units;
     const key_t kplane = (key_t)a.plane, kfd = (key_t)a.fd;
@@ -259,55 +255,64 @@ __global__ void __maxnreg__(GENPK_SWEEP_MAXREG) deposit_sweep_kernel(const __gri
         if (MASS) lm += skip;
     }
     const int n_planes = (int)(x_last - x_first);
-    int loads_left = n_planes * ry_eff, l_r = 0;
-    // prefetch cursor: the same walk, SWEEP_PREFETCH rows further on (L2 only; the loads proper run one row ahead)
-    const char *pp = lp;
-    int pf_left = loads_left, pf_r = 0;
-    auto prefetch_row = [&]() {
-        if (pf_left > 0) {
-            pf_left--;
-            if (FULL && lane_in_row)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(pp));
-            pp += row_bytes;
-            if (++pf_r == ry_eff) {
-                pp += block_adj_bytes;
-                pf_r = 0;
+    int l_r = 0;                                             // row (within the block) of the row lp points at
+    // Task mode: pull the grid lines this task's column is expected to write (its rows and cells, the
+    // planes of this task shifted by grid_prefetch) into L2 as whole 128-byte lines, so that the
+    // reductions find them there instead of missing sector by sector.  Performance only.
+    if (g.grid_prefetch > 0 && g.rx > 0) {
+        const long long gx0 = g.gp_x0 + (long long)(((unsigned long long)(x_first - g.x_begin) * g.gp_xstep) >> 32) + g.grid_prefetch;
+        const long long gx1 = g.gp_x0 + (long long)(((unsigned long long)(x_last - g.x_begin) * g.gp_xstep + 0xffffffffull) >> 32) + g.grid_prefetch;
+        const long long gy0 = (long long)(((unsigned long long)y0 * g.gp_ystep) >> 32);
+        const long long gy1 = (long long)(((unsigned long long)(y0 + ry_eff) * g.gp_ystep + 0xffffffffull) >> 32);
+        const long long gz0 = (long long)(((unsigned long long)(31LL * zseg) * g.gp_zstep) >> 32);
+        const long long gz1 = (long long)(((unsigned long long)(31LL * zseg + 32) * g.gp_zstep + 0xffffffffull) >> 32);
+        const int n_px = (int)(gx1 - gx0), n_py = (int)(gy1 - gy0);
+        const int lines = (int)((gz1 * 8 + 127) / 128 - (gz0 * 8) / 128);
+        const int total = n_px * n_py * lines;
+        const int n_local_planes = a.slab ? a.xl_max + 2 : dims;
+        for (int i = lane; i < total; i += 32) {
+            const int li = i % lines, rest = i / lines;
+            long long px_ = gx0 + rest / n_py, py_ = gy0 + rest % n_py;
+            if (!a.slab) {
+                px_ %= dims;
+                if (px_ < 0) px_ += dims;
+            }
+            if (px_ >= 0 && px_ < n_local_planes && py_ < dims) {
+                const char *line = reinterpret_cast<const char *>(grid) + ((size_t)px_ * a.plane + (size_t)py_ * a.fd) * 8 +
+                                   ((size_t)(gz0 * 8) / 128 + li) * 128;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
             }
         }
-    };
-#pragma unroll
-    for (int k = 0; k < SWEEP_PREFETCH; k++)
-        prefetch_row();
-    float ax[SWEEP_AHEAD], ay[SWEEP_AHEAD], az[SWEEP_AHEAD], am[SWEEP_AHEAD];   // rows in flight, oldest first
-#pragma unroll
-    for (int k = 0; k < SWEEP_AHEAD; k++)
-        ax[k] = ay[k] = az[k] = am[k] = 0.f;
-    auto issue_load = [&](float &ox, float &oy, float &oz, float &om) {
-        if (loads_left > 0) {
-            loads_left--;
-            if (lane_in_row && (FULL || lp_index < a.n)) {
-                ox = __ldcs(reinterpret_cast<const float *>(lp));
-                oy = __ldcs(reinterpret_cast<const float *>(lp) + 1);
-                oz = __ldcs(reinterpret_cast<const float *>(lp) + 2);
-                if (MASS)
-                    om = __ldcs(lm);
-            }
-            const bool last_row = ++l_r == ry_eff;
-            lp += row_bytes;
-            if (last_row) {
-                lp += block_adj_bytes;
-                l_r = 0;
-            }
-            if (!FULL || MASS) {
-                const long long inc = last_row ? plane_inc : g.n0;
-                lp_index += inc;
-                if (MASS) lm += inc;
-            }
+    }
+    // L2 prefetch: the same row one lattice plane further on (ry_eff steps ahead of the load, which itself
+    // runs one row ahead of the deposit); no cursor of its own
+    long long next_plane_bytes = 12 * g.n0 * g.n1;
+    asm volatile("" : "+l"(next_plane_bytes));
+    float ax = 0.f, ay = 0.f, az = 0.f, am = 0.f;             // the row in flight
+    auto issue_load = [&](bool prefetch_ok) {
+        if (lane_in_row && (FULL || lp_index < a.n)) {
+            if (FULL && prefetch_ok)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(lp + next_plane_bytes));
+            ax = __ldcs(reinterpret_cast<const float *>(lp));
+            ay = __ldcs(reinterpret_cast<const float *>(lp) + 1);
+            az = __ldcs(reinterpret_cast<const float *>(lp) + 2);
+            if (MASS)
+                am = __ldcs(lm);
+        }
+        const bool last_row = ++l_r == ry_eff;
+        lp += row_bytes;
+        if (last_row) {
+            lp += block_adj_bytes;
+            l_r = 0;
+        }
+        if (!FULL || MASS) {
+            const long long inc = last_row ? plane_inc : g.n0;
+            lp_index += inc;
+            if (MASS) lm += inc;
         }
     };
-#pragma unroll
-    for (int k = 0; k < SWEEP_AHEAD; k++)
-        issue_load(ax[k], ay[k], az[k], am[k]);
+    if (n_planes > 0)
+        issue_load(x_first + 2 < g.x_end);
 
     // One row slot: merge what the previous plane left for this row (x), leave this row's high-x
     // sums for the next plane, then hand the z1 sum to the next lane (z) and emit.
@@ -388,31 +393,28 @@ __global__ void __maxnreg__(GENPK_SWEEP_MAXREG) deposit_sweep_kernel(const __gri
         }
         acc2_t *xv = xv0;
         key_t *xk = xk0;
+        const bool last_plane = xi + 1 == n_planes;
+        const bool pf_ok = x_first + xi + 3 < g.x_end;        // (the load cursor may already be one plane on)
         for (int r = 0; r < ry_eff; r++) {
-            const float px = ax[0], py = ay[0], pz = az[0];
+            const float px = ax, py = ay, pz = az;
             double m = a.cmass;
             if (MASS)
-                m = (double)am[0];                                          // fieldize.cpp:63
-#pragma unroll
-            for (int k = 0; k + 1 < SWEEP_AHEAD; k++) {
-                ax[k] = ax[k + 1];
-                ay[k] = ay[k + 1];
-                az[k] = az[k + 1];
-                am[k] = am[k + 1];
-            }
-            issue_load(ax[SWEEP_AHEAD - 1], ay[SWEEP_AHEAD - 1], az[SWEEP_AHEAD - 1], am[SWEEP_AHEAD - 1]);
-            prefetch_row();
+                m = (double)am;                                             // fieldize.cpp:63
+            if (!(last_plane && r + 1 == ry_eff))
+                issue_load(pf_ok);                                          // the next step's row
             const bool live = lane_in_row && (FULL || p < a.n);
             const bool emit_b = FULL ? emit_b_full : ((pair_in_row && p + 1 < a.n) ? lane < 31 : owner_lane);
             const long long p_now = p;
             if (!FULL || MASS)
                 p += (r + 1 == ry_eff) ? plane_inc : g.n0;
-            bool ok = live && fabsf(px) < pos_limit && fabsf(py) < pos_limit && fabsf(pz) < pos_limit;
-            int fx, fy, fz;
+            int fx, fy, fz, hx, hy, hz;
             double tx, dx, ty, dy, tz, dz;
-            axis_fast(px, units, fx, tx, dx);
-            axis_fast(py, units, fy, ty, dy);
-            axis_fast(pz, units, fz, tz, dz);
+            axis_fast_hi(px, units, fx, hx, tx, dx);
+            axis_fast_hi(py, units, fy, hy, ty, dy);
+            axis_fast_hi(pz, units, fz, hz, tz, dz);
+            // x + 1.5*2^52 has the high word 0x43380000 exactly when 0 <= x < 2^32 (and x is finite): one test
+            // for "finite, non-negative, floor exact" on all three axes
+            const bool in_range = (((hx ^ 0x43380000) | (hy ^ 0x43380000) | (hz ^ 0x43380000)) == 0);
             int xl = fx;
             if (a.slab)                                                     // slab: the +1 neighbour may be a ghost plane
                 xl = slab_plane(fx, a.x0, a.ghost_lo, dims);
@@ -426,10 +428,12 @@ __global__ void __maxnreg__(GENPK_SWEEP_MAXREG) deposit_sweep_kernel(const __gri
                 const unsigned u1 = (unsigned)(xl - za_lo), u2 = u1 + (unsigned)dims;
                 pass = (u1 <= (unsigned)za_span) | (!a.slab & (u2 <= (unsigned)za_span));
             }
-            if (live && !(ok && inside && pass)) {
+            bool ok = in_range && inside && pass;
+            if (live && !ok) {
                 // rare: rejected (non-finite, outside the slab), at the periodic wrap, or beyond the cleared front
                 if (owner_lane) {
                     bool deposit_now = false;
+                    ok = fabsf(px) < pos_limit && fabsf(py) < pos_limit && fabsf(pz) < pos_limit;   // as axis_cell
                     if (!ok) {
                         n_rejected++;
                     } else {
@@ -681,6 +685,15 @@ int launch_sweep(genpk_ctx *ctx, const DepositArgs &a, long long n0, long long n
         if (ry > ry_cap) ry = ry_cap;
         g.ry = ry;
         g.rx = (int)(n2 < ctx->sweep_rx ? n2 : ctx->sweep_rx);
+        g.grid_prefetch = ctx->sweep_grid_prefetch;
+        {
+            const SlabGeom &sgeo = ctx->g;
+            const double ppx = (double)sgeo.nx / (double)n2;
+            g.gp_xstep = (unsigned long long)llround(ppx * 4294967296.0);
+            g.gp_ystep = (unsigned long long)llround((double)sgeo.dims / (double)n1 * 4294967296.0);
+            g.gp_zstep = (unsigned long long)llround((double)sgeo.dims / (double)n0 * 4294967296.0);
+            g.gp_x0 = (long long)floor(0.5 * ppx) + (info && info->dx_valid ? info->dx_mean : sgeo.ghost_lo);
+        }
         g.ncols = (int)(g.nzs * ((n1 + ry - 1) / ry));
         const size_t smem = sweep_smem(ry, ctx->fixed, key32);
         GENPK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
