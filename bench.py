@@ -78,6 +78,7 @@ def parse_args():
     ap.add_argument("--xpass-narrow-tile", action="store_true", help="fused x pass with 4096-mode tiles at 1024 (two CTAs per SM)")
     ap.add_argument("--fft-yz-batch", type=int, default=-1, help="x planes per 2-D cuFFT call (0 = all, -1 = library default)")
     ap.add_argument("--no-own-ypass", action="store_true", help="cuFFT's 2-D (y,z) plan instead of cuFFT z + own y pass")
+    ap.add_argument("--no-ghost-pull", action="store_true", help="multi-GPU: NCCL send/recv of the ghost planes instead of peer loads")
     ap.add_argument("--no-scatter", action="store_true", help="multi-GPU: pack + all-to-all instead of the y pass storing into peers")
     ap.add_argument("--check-mass", action="store_true",
                     help="before timing: one deposit (+ ghost exchange), the grid must sum to the particle count")
@@ -392,13 +393,15 @@ def run_ours(args):
         pipe = SlabPipeline(dims, stages)
         if not (args.no_scatter or args.no_fused_xpass or args.no_own_ypass):
             stages.enable_scatter()
+        if not args.no_ghost_pull:
+            stages.enable_ghost_pull()
 
         def step_device():
             return pipe.pk(dpos, None, 1.0, BOX, total_mass, nrbins)
 
         def step_host(hpos):
-            d = hpos.to(dev, non_blocking=True)
-            return pipe.pk(d, None, 1.0, BOX, total_mass, nrbins)
+            # the pinned shard goes up in chunks on the library's copy stream while earlier chunks are deposited
+            return pipe.pk(hpos, None, 1.0, BOX, total_mass, nrbins)
 
     if args.no_fused_xpass:
         ctx.set_option(api.OPT_FUSED_XPASS, 0)
@@ -574,6 +577,7 @@ def run_ours(args):
                    "binning_mode": args.power,
                    "x_pass": "fused with binning (fftx_power_kernel)" if fused else "cuFFT", "parallelism": (f"x-slab x{world}, {ghost} ghost planes, particles {pipe.placement}, transpose "
                                    + ("fused into the y pass (peer stores)" if stages.scatter_ready else "pack + all-to-all")
+                                   + (", ghost planes pulled over NVLink (peer loads)" if stages.pull_ready else ", ghost planes by send/recv")
                                    if world > 1
                                    else "single GPU"),
                    "l2": "inputs larger than L2 (no flush needed)"},

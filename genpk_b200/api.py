@@ -412,6 +412,27 @@ class Context:
         h = C.create_string_buffer(ipc_handle, self.IPC_HANDLE_BYTES) if ipc_handle is not None else None
         check(self.lib.genpk_slab_set_peer(self.h, int(rank), h, same_process_ptr or None), "genpk_slab_set_peer")
 
+    def ipc_export_grid(self, which: int = 0) -> bytes:
+        buf = C.create_string_buffer(self.IPC_HANDLE_BYTES)
+        check(self.lib.genpk_ipc_export_grid(self.h, which, buf), "genpk_ipc_export_grid")
+        return buf.raw
+
+    def slab_set_grid_peer(self, side: int, ipc_handle: bytes = None, same_process_ptr: int = 0, which: int = 0):
+        """side 0: the grid of rank-1, side 1: the grid of rank+1 (ghost exchange by peer loads)."""
+        h = C.create_string_buffer(ipc_handle, self.IPC_HANDLE_BYTES) if ipc_handle is not None else None
+        check(self.lib.genpk_slab_set_grid_peer(self.h, which, int(side), h, same_process_ptr or None),
+              "genpk_slab_set_grid_peer")
+
+    def ghost_pull_ready(self, which: int = 0) -> bool:
+        return bool(self.lib.genpk_ghost_pull_ready(self.h, which))
+
+    def ghost_pull(self, which: int = 0):
+        check(self.lib.genpk_ghost_pull(self.h, which), "genpk_ghost_pull")
+
+    def rejected_to(self, dst_ptr: int):
+        """Stream-ordered: (double) rejected-particle count -> *dst_ptr, counter cleared."""
+        check(self.lib.genpk_rejected_to(self.h, dst_ptr), "genpk_rejected_to")
+
     def slab_scatter_supported(self) -> bool:
         return bool(self.lib.genpk_slab_scatter_supported(self.h))
 

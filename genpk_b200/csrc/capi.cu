@@ -65,6 +65,9 @@ static genpk_ctx *create_common(int dims, int device, int nranks, int rank, unsi
     }
     ctx->device = dev;
     ctx->flags = flags;
+    // slab contexts: AUTO takes the sweep kernel for lattice input (same speed as the march kernel, and it
+    // records which planes it wrote, so the ghost exchange moves only those)
+    ctx->sweep = nranks > 1 ? 1 : 0;
     ctx->fixed = (flags & GENPK_FLAG_FIXED_POINT) != 0;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) {

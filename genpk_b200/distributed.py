@@ -45,6 +45,7 @@ class CudaStages:
         self._send = None
         self._sums = None
         self.scatter_ready = False     # every rank's transposed block is known: the y pass stores into them
+        self.pull_ready = False        # the ring neighbours' grids are mapped: ghost planes are pulled over NVLink
         self._recv = None
 
     def close(self):
@@ -68,7 +69,13 @@ class CudaStages:
 
     def deposit(self, pos: torch.Tensor, mass, cmass: float, boxsize: float, which=0):
         n = pos.numel() // 3
-        if n:
+        if not n:
+            return
+        if pos.device.type == "cpu":
+            # host shard (pinned for the overlap): uploaded in chunks on the library's copy stream while
+            # earlier chunks are deposited
+            self.ctx.deposit_host_ptr(pos.data_ptr(), n, mass.data_ptr() if mass is not None else 0, cmass, boxsize, which)
+        else:
             self.ctx.deposit_dev(pos.data_ptr(), n, mass.data_ptr() if mass is not None else 0, cmass, boxsize, which)
 
     # -- ghost plane ---------------------------------------------------------------
@@ -83,6 +90,40 @@ class CudaStages:
 
     def rejected(self) -> int:
         return self.ctx.take_rejected()
+
+    def rejected_to(self, slot: torch.Tensor):
+        """Stream-ordered: this rank's rejected-particle count into a device double (no host round trip)."""
+        self.ctx.rejected_to(slot.data_ptr())
+
+    # -- ghost exchange by peer loads ----------------------------------------------------
+    def enable_ghost_pull(self, group=None, which=0) -> bool:
+        """Exchange the CUDA IPC handles of every rank's grid and map the two ring neighbours', so that
+        genpk_ghost_pull can read their ghost planes over NVLink (no send/recv, no staging buffers)."""
+        if self.pull_ready:
+            return True
+        good = 1
+        try:
+            mine = torch.frombuffer(bytearray(self.ctx.ipc_export_grid(which)), dtype=torch.uint8).to(self.device)
+        except Exception:
+            good = 0
+            mine = torch.zeros(self.ctx.IPC_HANDLE_BYTES, dtype=torch.uint8, device=self.device)
+        handles = [torch.empty_like(mine) for _ in range(self.nranks)]
+        dist.all_gather(handles, mine, group=group)
+        if good:
+            try:
+                prv, nxt = (self.rank - 1) % self.nranks, (self.rank + 1) % self.nranks
+                self.ctx.slab_set_grid_peer(0, bytes(handles[prv].cpu().numpy().tobytes()), 0, which)
+                if self.ghost_planes > 0:
+                    self.ctx.slab_set_grid_peer(1, bytes(handles[nxt].cpu().numpy().tobytes()), 0, which)
+            except Exception:
+                good = 0
+        ok = torch.tensor([good], dtype=torch.int32, device=self.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        self.pull_ready = bool(int(ok.item()))
+        return self.pull_ready
+
+    def ghost_pull(self, which=0):
+        self.ctx.ghost_pull(which)
 
     # -- FFT -----------------------------------------------------------------------
     def fft_yz(self, which=0):
@@ -105,8 +146,8 @@ class CudaStages:
 
     # -- binning ---------------------------------------------------------------------
     def power_partial(self, spec_a: torch.Tensor, spec_b, nrbins: int) -> torch.Tensor:
-        if self._sums is None or self._sums.numel() != 3 * nrbins:
-            self._sums = torch.empty(3 * nrbins, dtype=torch.float64, device=self.device)
+        if self._sums is None or self._sums.numel() != 3 * nrbins + 1:
+            self._sums = torch.zeros(3 * nrbins + 1, dtype=torch.float64, device=self.device)   # [-1]: rejected particles
         self.ctx.slab_power_partial(spec_a.data_ptr(), spec_b.data_ptr() if spec_b is not None else 0, nrbins,
                                     self._sums.data_ptr())
         return self._sums
@@ -156,10 +197,15 @@ class CudaStages:
     def fused_xpass(self, nrbins: int) -> bool:
         return self.ctx.fused_xpass_supported(nrbins)
 
+    def sums_buffer(self, nrbins: int) -> torch.Tensor:
+        if self._sums is None or self._sums.numel() != 3 * nrbins + 1:
+            self._sums = torch.zeros(3 * nrbins + 1, dtype=torch.float64, device=self.device)
+        return self._sums
+
     def fftx_power_partial(self, spec_yz: torch.Tensor, nrbins: int) -> torch.Tensor:
         """x transform + binning of the transposed (y,z)-transformed block in one kernel."""
-        if self._sums is None or self._sums.numel() != 3 * nrbins:
-            self._sums = torch.empty(3 * nrbins, dtype=torch.float64, device=self.device)
+        if self._sums is None or self._sums.numel() != 3 * nrbins + 1:
+            self._sums = torch.zeros(3 * nrbins + 1, dtype=torch.float64, device=self.device)   # [-1]: rejected particles
         self.ctx.slab_fftx_power_partial(spec_yz.data_ptr(), nrbins, self._sums.data_ptr())
         return self._sums
 
@@ -228,6 +274,12 @@ class SlabPipeline:
         """Ring shift of the high-x ghost plane into the next rank's first plane."""
         if self.P == 1:
             return
+        if getattr(self.stages, "pull_ready", False):
+            # every rank has deposited (barrier), then each pulls what its neighbours' deposits left in their
+            # ghost planes straight from their memory: no send/recv, only the planes that were touched
+            self._barrier(self.stages.device)
+            self.stages.ghost_pull(which)
+            return
         nxt, prv = (self.r + 1) % self.P, (self.r - 1) % self.P
         if self.group is not None:
             nxt, prv = dist.get_global_rank(self.group, nxt), dist.get_global_rank(self.group, prv)
@@ -256,7 +308,9 @@ class SlabPipeline:
         return spec
 
     # ---- stages in order -----------------------------------------------------------------
-    def deposit(self, pos, mass=None, cmass=1.0, boxsize=1.0, which=0, zero=True, routed=False):
+    def deposit(self, pos, mass=None, cmass=1.0, boxsize=1.0, which=0, zero=True, routed=False, defer_check=None):
+        """defer_check: a device double that receives this rank's rejected-particle count instead of a
+        host round trip here (the caller reduces it with its sums and looks at it once per step)."""
         if zero:
             self.stages.zero(which)
         if routed or self.P == 1:
@@ -265,7 +319,10 @@ class SlabPipeline:
         if self.placement == "local":
             # optimistic: every particle of the shard lies in this rank's slab or its ghosts
             self.stages.deposit(pos, mass, cmass, boxsize, which)
-            bad = torch.tensor([self.stages.rejected()], dtype=torch.int64, device=pos.device)
+            if defer_check is not None and hasattr(self.stages, "rejected_to"):
+                self.stages.rejected_to(defer_check)
+                return
+            bad = torch.tensor([self.stages.rejected()], dtype=torch.int64, device=self._device_of(pos))
             dist.all_reduce(bad, group=self.group)
             if int(bad.item()) == 0:
                 return
@@ -274,9 +331,15 @@ class SlabPipeline:
                                    "grid already holds earlier deposits: route the particles (placement='route')")
             self.placement = "route"                                # redo this deposit, and route from now on
             self.stages.zero(which)
+        if pos.device.type == "cpu":
+            pos = pos.to(self._device_of(pos), non_blocking=True)
+            mass = mass.to(pos.device, non_blocking=True) if mass is not None else None
         spos, smass, counts = self.stages.route(pos, mass, boxsize)
         rpos, rmass = self.exchange_particles(spos, smass, counts)
         self.stages.deposit(rpos, rmass, cmass, boxsize, which)
+
+    def _device_of(self, t):
+        return getattr(self.stages, "device", t.device) if t.device.type == "cpu" else t.device
 
     def spectrum(self, which=0, x_pass=True):
         with self._Timed(self, "ghost_exchange"):
@@ -295,34 +358,53 @@ class SlabPipeline:
         dist.all_reduce(self._flag, group=self.group)
 
     def _reduce_finalize(self, sums, nrbins, total_mass, total_mass2):
+        """All-reduce of the raw sums (+ the rejected-particle count riding in the last slot when the
+        deposit deferred its check), one D2H, normalisation on the host."""
         with self._Timed(self, "allreduce_d2h"):
             if self.P > 1:
                 dist.all_reduce(sums, group=self.group)
             host = sums.cpu().numpy()
-        return api.power_finalize(host, nrbins, total_mass, total_mass2)
+        self.last_rejected = int(host[3 * nrbins]) if host.size > 3 * nrbins else 0
+        return api.power_finalize(host[:3 * nrbins], nrbins, total_mass, total_mass2)
 
     def power(self, spec_a, spec_b, nrbins, total_mass, total_mass2):
         sums = self.stages.power_partial(spec_a, spec_b, nrbins)
         return self._reduce_finalize(sums, nrbins, total_mass, total_mass2)
 
     def pk(self, pos, mass=None, cmass=1.0, boxsize=1.0, total_mass=1.0, nrbins=None, routed=False):
-        """The per-type step of gen-pk.cpp:208-234 on this rank's particle shard."""
+        """The per-type step of gen-pk.cpp:208-234 on this rank's particle shard (a device tensor, or a
+        pinned host tensor that is uploaded in chunks while earlier chunks are deposited)."""
         nrbins = self.dims if nrbins is None else nrbins
-        self.deposit(pos, mass, cmass, boxsize, 0, True, routed)
         fused = getattr(self.stages, "fused_xpass", None)
+        dev = self._device_of(pos)
         if fused is not None and fused(nrbins) and getattr(self.stages, "scatter_ready", False) and self.P > 1:
             # the y pass stores its results straight into their owner's transposed block (peer
             # stores over NVLink): no pack, no all-to-all.  Barriers: nobody still reads its block
-            # (the previous call's x pass) / every rank has finished storing.
+            # (the previous call's x pass) / every rank has finished storing.  No host round trip
+            # before the sums come back: the deposit's rejected-particle count rides with them.
+            can_defer = hasattr(self.stages, "rejected_to") and hasattr(self.stages, "sums_buffer")
+            sums = self.stages.sums_buffer(nrbins) if can_defer else None
+            optimistic = can_defer and self.placement == "local" and not routed
+            self.deposit(pos, mass, cmass, boxsize, 0, True, routed, defer_check=sums[3 * nrbins:] if optimistic else None)
+            pulled = getattr(self.stages, "pull_ready", False)
             with self._Timed(self, "ghost_exchange"):
-                self.exchange_ghost(0)
-            with self._Timed(self, "barriers"):
-                self._barrier(pos.device)
+                self.exchange_ghost(0)                        # (with peer pulls: starts with the barrier)
+            if not pulled:
+                with self._Timed(self, "barriers"):
+                    self._barrier(dev)
             self.stages.fft_yz_scatter(0)
             with self._Timed(self, "barriers"):
-                self._barrier(pos.device)
-            sums = self.stages.fftx_power_partial(self.stages.recv_block(), nrbins)
-            return self._reduce_finalize(sums, nrbins, total_mass, total_mass)
+                self._barrier(dev)
+            if can_defer and not optimistic:
+                sums[3 * nrbins:] = 0
+            sums = self.stages.fftx_power_partial(self.stages.recv_block(), nrbins)      # (writes the first 3*nrbins slots only)
+            out = self._reduce_finalize(sums, nrbins, total_mass, total_mass)
+            if optimistic and self.last_rejected:
+                # stragglers beyond the ghost planes: this result is incomplete -- route from now on and redo
+                self.placement = "route"
+                return self.pk(pos, mass, cmass, boxsize, total_mass, nrbins, routed)
+            return out
+        self.deposit(pos, mass, cmass, boxsize, 0, True, routed)
         if fused is not None and fused(nrbins):
             # the x transform and the binning of the transposed block share one kernel
             spec = self.spectrum(0, x_pass=False)

@@ -278,3 +278,116 @@ def test_wide_ghost_pipeline_over_nccl(tmp_path, port):
     nz = cr > 0
     np.testing.assert_allclose(got["p"][nz], pr[nz], rtol=1e-5)
     np.testing.assert_allclose(got["k"][nz], kr[nz], rtol=1e-5)
+
+
+@pytest.mark.parametrize("P,ghost,mode", [(2, 6, "sweep"), (4, 8, "sweep"), (8, 4, "march"), (2, 0, "sweep"), (4, 0, "direct")])
+def test_ghost_pull_emulated_on_one_gpu(port, P, ghost, mode):
+    """Ghost exchange by peer loads (genpk_ghost_pull) with the neighbours' grids mapped as plain pointers
+    inside one process: every rank adds its neighbours' ghost planes into its own outermost planes, only the
+    planes their deposits touched (the sweep kernel tracks them; march / direct mark every plane).
+    Fixed-point mode: the assembled grid equals the single-GPU grid bit for bit."""
+    import torch
+    from genpk_b200.distributed import CudaStages
+    dev = torch.device("cuda", 0)
+    n_side = dims = 64
+    box = 640.0
+    n = n_side ** 3
+    d = torch.empty(3 * n, dtype=torch.float32, device=dev)
+    api.synth_particles_dev(api.SYNTH_LATTICE, 1, n_side, 0, n, box, dims, d.data_ptr())
+    torch.cuda.synchronize()
+    rng = np.random.default_rng(8)
+    pos = d.cpu().numpy().reshape(-1, 3)
+    reach = (ghost - 1.5) if ghost else 0.45
+    pos[:, 0] = np.mod(pos[:, 0] + rng.uniform(-reach, reach, n).astype(np.float32) * np.float32(box / dims), box)
+    if not ghost:
+        pos[:, 0] = np.clip(pos[:, 0], 0.01, box - 0.01)
+    pos[:, 1:] += rng.uniform(-3, 3, (n, 2)).astype(np.float32)
+    pos = np.ascontiguousarray(pos, np.float32)
+    want = np.zeros(padded_shape(dims), np.int64)
+    port.fieldize_fixed(box, dims, want, pos, None, 1.0, 1, 40)
+    per = n // P
+    st = [CudaStages(dims, P, r, dev, api.FLAG_FIXED_POINT, ghost) for r in range(P)]
+    nx = dims // P
+    try:
+        for r in range(P):
+            st[r].ctx.set_deposit_mode({"sweep": api.DEPOSIT_SWEEP, "march": api.DEPOSIT_MARCH, "direct": api.DEPOSIT_DIRECT}[mode])
+            st[r].ctx.set_lattice_hint(n_side, n_side)
+            st[r].zero()
+            st[r].deposit(torch.from_numpy(pos[r * per:(r + 1) * per].reshape(-1).copy()).to(dev), None, 1.0, box)
+            assert st[r].rejected() == 0
+        for r in range(P):
+            st[r].ctx.slab_set_grid_peer(0, None, st[(r - 1) % P].ctx.grid_ptr())
+            if ghost:
+                st[r].ctx.slab_set_grid_peer(1, None, st[(r + 1) % P].ctx.grid_ptr())
+            assert st[r].ctx.ghost_pull_ready()
+        torch.cuda.synchronize()
+        for r in range(P):
+            st[r].ghost_pull()
+        torch.cuda.synchronize()
+        for r in range(P):
+            part = st[r].ctx.grid_download_fixed().reshape(nx + (2 * ghost if ghost else 1), dims, 2 * (dims // 2 + 1))
+            assert np.array_equal(part[ghost:ghost + nx], want[r * nx:(r + 1) * nx]), f"slab {r} differs"
+    finally:
+        for s in st:
+            s.close()
+
+
+def _nccl_pull_worker(rank, world, port, dims, n_side, box, ghost, out_dir, host_shards):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from genpk_b200.distributed import CudaStages, SlabPipeline
+        n = n_side ** 3
+        first, count = rank * n // world, (rank + 1) * n // world - rank * n // world
+        dpos = torch.empty(3 * count, dtype=torch.float32, device=dev)
+        api.synth_particles_dev(api.SYNTH_CLUSTERED, 42, n_side, first, count, box, dims, dpos.data_ptr())
+        torch.cuda.synchronize()
+        stages = CudaStages(dims, world, rank, dev, 0, ghost)
+        pipe = SlabPipeline(dims, stages)
+        assert stages.enable_scatter() and stages.enable_ghost_pull()
+        shard = dpos
+        if host_shards:
+            shard = torch.empty(3 * count, dtype=torch.float32, pin_memory=True)
+            shard.copy_(dpos)
+            torch.cuda.synchronize()
+        for _ in range(2):                                        # twice: blocks, ghosts and counters are reused
+            p, c, k = pipe.pk(shard, None, 1.0, box, float(n), dims)
+        stages.check()
+        if rank == 0:
+            np.savez(os.path.join(out_dir, "out.npz"), p=p, c=c, k=k, placement=pipe.placement)
+        stages.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("ghost,host_shards,placement", [(16, False, "local"), (16, True, "local"), (2, False, "route")])
+def test_peer_pull_pipeline_over_nccl(tmp_path, port, ghost, host_shards, placement):
+    """The whole multi-GPU step with no NCCL data collective but the final all-reduce: ghost planes pulled
+    from the neighbours' memory, transpose stored into the owners' blocks, rejected-particle check riding
+    with the sums (ghost = 2 is too thin for the displacements: the pipeline must notice and route)."""
+    import torch
+    import torch.multiprocessing as mp
+    world = min(torch.cuda.device_count(), 8)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
+    n_side = dims = 256
+    box = 1000.0
+    mp.spawn(_nccl_pull_worker, args=(world, _free_port(), dims, n_side, box, ghost, str(tmp_path), host_shards), nprocs=world,
+             join=True)
+    got = np.load(tmp_path / "out.npz")
+    assert str(got["placement"]) == placement
+    n = n_side ** 3
+    d = torch.empty(3 * n, dtype=torch.float32, device="cuda:0")
+    api.synth_particles_dev(api.SYNTH_CLUSTERED, 42, n_side, 0, n, box, dims, d.data_ptr())
+    torch.cuda.synchronize()
+    _, pr, cr, kr = port.pk(box, dims, d.cpu().numpy().reshape(-1, 3), None, 1.0, float(n), dims)
+    assert np.array_equal(got["c"], cr)
+    nz = cr > 0
+    np.testing.assert_allclose(got["p"][nz], pr[nz], rtol=1e-5)
+    np.testing.assert_allclose(got["k"][nz], kr[nz], rtol=1e-5)
