@@ -100,7 +100,9 @@ template <> struct Acc<true> {
 
 // One particle, eight reductions: the arithmetic of deposit_direct_kernel (fieldize.cpp:63-92) for the
 // stragglers of the sweep kernel.  Rejected (non-finite, outside the slab) particles are skipped.
-template <bool FIXED>
+// TRACK: record the planes written in a.touched with atomics (callers that deposit many particles this way
+// track the range themselves: two same-address atomics per particle serialise in one L2 slice).
+template <bool FIXED, bool TRACK = true>
 __device__ __forceinline__ void deposit_single(const DepositArgs &a, float px, float py, float pz, double m)
 {
     const AxisCell cx = axis_cell(px, a.units, a.dims);
@@ -114,7 +116,7 @@ __device__ __forceinline__ void deposit_single(const DepositArgs &a, float px, f
         if (xl < 0 || xl > a.xl_max)
             return;
         xh = xl + 1;
-        if (a.touched) {
+        if (TRACK && a.touched) {
             atomicMin(a.touched, xl);
             atomicMax(a.touched + 1, xh);
         }

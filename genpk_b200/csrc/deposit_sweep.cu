@@ -184,7 +184,7 @@ __device__ __noinline__ void sweep_zero_role(const DepositArgs &a, const SweepAr
 template <bool FIXED>
 __device__ __noinline__ void sweep_edge_particle(const DepositArgs &a, float px, float py, float pz, double m)
 {
-    deposit_single<FIXED>(a, px, py, pz, m);
+    deposit_single<FIXED, false>(a, px, py, pz, m);          // (the sweep tracks the touched planes in registers)
 }
 
 template <bool FIXED, typename key_t, bool FULL, bool MASS, bool ZA>
@@ -433,6 +433,7 @@ __global__ void __maxnreg__(GENPK_SWEEP_MAXREG) deposit_sweep_kernel(const __gri
                 // rare: rejected (non-finite, outside the slab), at the periodic wrap, or beyond the cleared front
                 if (owner_lane) {
                     bool deposit_now = false;
+                    int wl_edge = 0;
                     ok = fabsf(px) < pos_limit && fabsf(py) < pos_limit && fabsf(pz) < pos_limit;   // as axis_cell
                     if (!ok) {
                         n_rejected++;
@@ -454,6 +455,7 @@ __global__ void __maxnreg__(GENPK_SWEEP_MAXREG) deposit_sweep_kernel(const __gri
                                 wpass = (u1 <= (unsigned)za_span) | (!a.slab & (u2 <= (unsigned)za_span));
                             }
                             deposit_now = wpass;
+                            wl_edge = wl;
                             if (ZA && !wpass) {
                                 const int li = col & (SWEEP_DEF_LISTS - 1);
                                 const unsigned slot = atomicAdd(&g.def_count[li], 1u);
@@ -466,8 +468,13 @@ __global__ void __maxnreg__(GENPK_SWEEP_MAXREG) deposit_sweep_kernel(const __gri
                             }
                         }
                     }
-                    if (deposit_now)
+                    if (deposit_now) {
                         sweep_edge_particle<FIXED>(a, px, py, pz, m);
+                        if (a.slab) {
+                            t_lo = wl_edge < t_lo ? wl_edge : t_lo;
+                            t_hi = wl_edge > t_hi ? wl_edge : t_hi;
+                        }
+                    }
                 }
                 ok = false;
             }

@@ -92,7 +92,7 @@ def test_slab_stages_emulated_on_one_gpu(port, P, dims, var_mass, fixed):
             for r in range(P):
                 spec[r * blk: (r + 1) * blk] = sends[r][s * blk: (s + 1) * blk]
             st[s].fft_x(spec)
-            total += st[s].power_partial(spec, None, nrbins)
+            total += st[s].power_partial(spec, None, nrbins)[:3 * nrbins]
             st[s].check()
         p, c, k = api.power_finalize(total.cpu().numpy(), nrbins, tm, tm)
         assert np.array_equal(c, c1)
