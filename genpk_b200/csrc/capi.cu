@@ -65,9 +65,7 @@ static genpk_ctx *create_common(int dims, int device, int nranks, int rank, unsi
     }
     ctx->device = dev;
     ctx->flags = flags;
-    // slab contexts: AUTO takes the sweep kernel for lattice input (same speed as the march kernel, and it
-    // records which planes it wrote, so the ghost exchange moves only those)
-    ctx->sweep = nranks > 1 ? 1 : 0;
+
     ctx->fixed = (flags & GENPK_FLAG_FIXED_POINT) != 0;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) {
@@ -231,6 +229,10 @@ int genpk_set_option(genpk_ctx *ctx, int option, int64_t value)
     case GENPK_OPT_FUSED_XPASS:
         if (value < 0 || value > 2) break;
         ctx->fused_xpass = (int)value;
+        return 0;
+    case GENPK_OPT_F64_POSITIONS:
+        if (value != 0 && value != 1) break;
+        ctx->f64_exact = (int)value;
         return 0;
     case GENPK_OPT_SWEEP:
         if (value != 0 && value != 1) break;
@@ -431,6 +433,15 @@ static int deposit_chunks(genpk_ctx *ctx, int which, const void *positions, bool
             GENPK_CUDA_OK(cudaStreamWaitEvent(ctx->stream, up, 0));
             GENPK_CUDA_OK(cudaEventDestroy(up));
         }
+        if (f64 && ctx->f64_exact) {
+            // a DOUBLE_PRECISION_SNAP build of the reference: the doubles go to the deposit as they are
+            const double *src = on_device ? pos64 + 3 * off : ctx->d_stage_pos64[buf];
+            rc = deposit_device_f64(ctx, which, src, dmass, m, mass, boxsize);
+            if (!on_device)
+                GENPK_CUDA_OK(cudaEventRecord(ctx->stage_free[buf], ctx->stream));
+            off += m;
+            continue;
+        }
         if (f64) {
             const double *src = on_device ? pos64 + 3 * off : ctx->d_stage_pos64[buf];
             narrow_f64_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(src, ctx->d_stage_pos[buf], (size_t)m * 3);
@@ -441,7 +452,7 @@ static int deposit_chunks(genpk_ctx *ctx, int which, const void *positions, bool
         if (!planned) {
             if ((rc = deposit_plan(ctx, dpos, m, boxsize, &plan))) break;
             planned = true;
-            if (plan.mode == GENPK_DEPOSIT_MARCH && plan.n0 > 0) {
+            if ((plan.mode == GENPK_DEPOSIT_MARCH || plan.mode == GENPK_DEPOSIT_SWEEP) && plan.n0 > 0) {
                 const int64_t plane = plan.n1 > 0 ? plan.n0 * plan.n1 : 0;
                 unit = (plane > 0 && plane <= chunk) ? plane : (plan.n0 <= chunk ? plan.n0 : 1);
                 if (off + m < n && m > unit)

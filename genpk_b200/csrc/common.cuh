@@ -86,6 +86,7 @@ struct genpk_ctx {
     bool fixed = false;
     int scale_bits = 40;
     int deposit_mode = GENPK_DEPOSIT_AUTO;
+    int f64_exact = 0;                // genpk_deposit_f64 uses the doubles un-narrowed (a DOUBLE_PRECISION_SNAP reference)
 
     // each grid allocation ends with GRID_TAIL_BYTES of bookkeeping that travels with its IPC handle:
     // int32 {lowest, highest} local x plane written since the grid was cleared (slab contexts)
@@ -195,6 +196,8 @@ int deposit_plan(genpk_ctx *ctx, const float *pos, int64_t n, double boxsize, De
 // plan == nullptr: planned here (one order probe, one small D2H)
 int deposit_device(genpk_ctx *ctx, int which, const float *pos, const float *masses, int64_t n,
                    double mass, double boxsize, const DepositPlan *plan = nullptr);
+int deposit_device_f64(genpk_ctx *ctx, int which, const double *pos, const float *masses, int64_t n, double mass,
+                       double boxsize);
 int fixed_to_double(genpk_ctx *ctx, int which);
 // carries out a pending genpk_grid_zero (every reader of the grid calls this first)
 int materialize_zero(genpk_ctx *ctx, int which);

@@ -21,16 +21,16 @@ namespace genpk {
 // corners.  Those four contributions are handed to the next lane by shuffle and
 // leave with its reductions: ~4 instead of 8 red.add per particle on coherent input,
 // unchanged results (the sum per cell is the same set of terms).
-template <bool FIXED>
+template <bool FIXED, typename pos_t = float>
 __global__ void __launch_bounds__(256) deposit_direct_kernel(DepositArgs a)
 {
     typedef typename Acc<FIXED>::type acc_t;
     const int lane = threadIdx.x & 31;
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = p < a.n;
-    const float *pos = a.pos;
+    const pos_t *pos = sizeof(pos_t) == 8 ? reinterpret_cast<const pos_t *>(a.pos64) : reinterpret_cast<const pos_t *>(a.pos);
     const float *mass = a.mass;
-    float px = 0.f, py = 0.f, pz = 0.f;
+    pos_t px = 0, py = 0, pz = 0;
     double m = a.cmass;
     if (live) {
         px = pos[3 * p];
@@ -230,7 +230,12 @@ static int launch_direct(genpk_ctx *ctx, const DepositArgs &a)
         return 1;
     }
     const int blocks = (int)want;
-    if (ctx->fixed)
+    if (a.pos64) {
+        if (ctx->fixed)
+            deposit_direct_kernel<true, double><<<blocks, threads, 0, ctx->stream>>>(a);
+        else
+            deposit_direct_kernel<false, double><<<blocks, threads, 0, ctx->stream>>>(a);
+    } else if (ctx->fixed)
         deposit_direct_kernel<true><<<blocks, threads, 0, ctx->stream>>>(a);
     else
         deposit_direct_kernel<false><<<blocks, threads, 0, ctx->stream>>>(a);
@@ -355,6 +360,7 @@ int deposit_device(genpk_ctx *ctx, int which, const float *pos, const float *mas
     }
     DepositArgs a;
     a.pos = pos;
+    a.pos64 = nullptr;
     a.mass = masses;
     a.n = n;
     a.cmass = mass;
@@ -430,10 +436,10 @@ int deposit_device(genpk_ctx *ctx, int which, const float *pos, const float *mas
     }
     if (int rc = materialize_zero(ctx, which))
         return rc;
-    if (a.slab)                                          // these kernels do not track what they touch
-        if (int rc = touched_set(ctx, which, 0, g.ghost_lo + g.nx + g.ghost_hi - 1)) return rc;
-    if (plan->mode == GENPK_DEPOSIT_MARCH)
+    if (plan->mode == GENPK_DEPOSIT_MARCH)               // (tracks the planes it writes, like the sweep kernel)
         return launch_march(ctx, a, plan->n0, plan->n1);
+    if (a.slab)                                          // the direct kernel does not track what it touches
+        if (int rc = touched_set(ctx, which, 0, g.ghost_lo + g.nx + g.ghost_hi - 1)) return rc;
     if (plan->mode == GENPK_DEPOSIT_SORTED) {
         const BrickMap bm = choose_bricks(ctx, a.units);
         if (bm.nbricks > 1 && bm.nbricks <= SORT_MAX_KEYS) {
@@ -448,6 +454,45 @@ int deposit_device(genpk_ctx *ctx, int which, const float *pos, const float *mas
             a.mass = masses ? ctx->d_sorted_mass : nullptr;
         }
     }
+    return launch_direct(ctx, a);
+}
+
+// Double-precision positions used as they are (what a DOUBLE_PRECISION_SNAP build of the reference hands to
+// fieldize(), read_fieldize.cpp:24-25): one thread per particle, eight reductions minus the z hand-over.
+int deposit_device_f64(genpk_ctx *ctx, int which, const double *pos, const float *masses, int64_t n, double mass,
+                       double boxsize)
+{
+    const SlabGeom &g = ctx->g;
+    if (n <= 0)
+        return 0;
+    if (!(boxsize > 0)) {
+        set_error("deposit: boxsize must be positive");
+        return 1;
+    }
+    if (int rc = materialize_zero(ctx, which))
+        return rc;
+    DepositArgs a;
+    a.pos = nullptr;
+    a.pos64 = pos;
+    a.mass = masses;
+    a.n = n;
+    a.cmass = mass;
+    a.units = g.dims / boxsize;
+    a.scale = ldexp(1.0, ctx->scale_bits);
+    a.dims = g.dims;
+    a.fd = g.fd;
+    a.x0 = g.x0;
+    a.slab = g.nranks > 1 ? 1 : 0;
+    a.ghost_lo = g.ghost_lo;
+    a.xl_max = g.ghost_lo + g.nx + g.ghost_hi - 2;
+    a.plane = g.plane();
+    a.grid = ctx->grid[which];
+    a.errors = ctx->d_errors;
+    a.touched = a.slab ? touched_ptr(ctx, which) : nullptr;
+    if (ctx->fixed)
+        ctx->grid_is_fixed[which] = true;
+    if (a.slab)
+        if (int rc = touched_set(ctx, which, 0, g.ghost_lo + g.nx + g.ghost_hi - 1)) return rc;
     return launch_direct(ctx, a);
 }
 
@@ -553,6 +598,7 @@ int fieldize_host_shim(double boxsize, int dims, double *out, int64_t n, const f
         if (masses && cudaMemcpy(d_mass, masses, (size_t)n * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) break;
         DepositArgs a;
         a.pos = d_pos;
+        a.pos64 = nullptr;
         a.mass = d_mass;
         a.n = n;
         a.cmass = mass;

@@ -6,6 +6,7 @@ namespace genpk {
 
 struct DepositArgs {
     const float *pos;
+    const double *pos64;   // double-precision positions used un-narrowed (DOUBLE_PRECISION_SNAP, gen-pk.h:25-29), else null
     const float *mass;     // may be null
     int64_t n;
     double cmass;
@@ -50,6 +51,27 @@ __device__ __forceinline__ AxisCell axis_cell(float p, double units, int dims)
 {
     AxisCell c;
     const double x = __dmul_rn((double)p, units);           // fieldize.cpp:66
+    const double fl = floor(x);                             // :67
+    c.wh = __dsub_rn(x, fl);                                // :68  dx
+    c.wl = __dsub_rn(1.0, c.wh);                            // :69  tx
+    c.ok = fabs(x) < 2.0e9;                                 // false for NaN/inf/out of int range
+    int f = c.ok ? (int)fl : 0;
+    if ((unsigned)f >= (unsigned)dims) {                    // :70-75 periodic wrap, negative fix-up
+        f %= dims;
+        if (f < 0)
+            f += dims;
+    }
+    c.lo = f;
+    c.hi = (f + 1 == dims) ? 0 : f + 1;
+    return c;
+}
+
+// The same for a double-precision position (a DOUBLE_PRECISION_SNAP build of the reference: GENPK_FLOAT_TYPE
+// is double and fieldize.cpp:66 multiplies the double itself).
+__device__ __forceinline__ AxisCell axis_cell(double p, double units, int dims)
+{
+    AxisCell c;
+    const double x = __dmul_rn(p, units);                   // fieldize.cpp:66
     const double fl = floor(x);                             // :67
     c.wh = __dsub_rn(x, fl);                                // :68  dx
     c.wl = __dsub_rn(1.0, c.wh);                            // :69  tx

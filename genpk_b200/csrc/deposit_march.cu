@@ -173,6 +173,7 @@ __global__ void __launch_bounds__(MARCH_THREADS, GENPK_MARCH_MINB) deposit_march
         *xk_p = has ? kb : INVALID;
     };
 
+    int t_lo = 0x7fffffff, t_hi = -1;        // slab: lowest / highest low-x plane of a deposited cloud
     int r = 0;
     long long pc = p_first + lane;           // this lane's particle at the current step (only read when !FULL)
     acc_t *xv_p = xc_val0;
@@ -213,6 +214,10 @@ __global__ void __launch_bounds__(MARCH_THREADS, GENPK_MARCH_MINB) deposit_march
         }
         if (live && !ok && owner_lane)
             atomicAdd(a.errors, 1ull);
+        if (a.slab && ok) {                                                  // planes the ghost exchange has to move
+            t_lo = xl < t_lo ? xl : t_lo;
+            t_hi = xl > t_hi ? xl : t_hi;
+        }
         const int ystep = fy + 1 == dims ? 1 - dims : 1;
         const int zoff = fz + 1 == dims ? 1 - dims : 1;                      // +1, or back to 0 at the wrap
         const double mx0 = __dmul_rn(m, tx), mx1 = __dmul_rn(m, dx);
@@ -291,6 +296,14 @@ __global__ void __launch_bounds__(MARCH_THREADS, GENPK_MARCH_MINB) deposit_march
         const key_t xk = xc_key0[s * MARCH_THREADS];
         if (xk != INVALID)
             Acc<FIXED>::red(grid, (size_t)xk, xc_val0[s * MARCH_THREADS]);
+    }
+    if (a.touched) {                         // slab: {lowest, highest} plane written, behind the grid allocation
+        t_lo = __reduce_min_sync(0xffffffffu, t_lo);
+        t_hi = __reduce_max_sync(0xffffffffu, t_hi);
+        if (lane == 0 && t_hi >= 0) {
+            atomicMin(a.touched, t_lo);
+            atomicMax(a.touched + 1, t_hi + 1);
+        }
     }
 }
 

@@ -81,6 +81,9 @@ extern "C" {
 #define GENPK_OPT_SWEEP_GRID_PREFETCH 22 /* task mode: every task first pulls the grid lines of its column, N planes ahead of its own
                                           planes, into L2 (0 = off) */
 #define GENPK_OPT_SWEEP_POLL_WEAK 20   /* 1 (default): marks are probed with weak L1-bypassing loads; 0: relaxed.gpu loads */
+#define GENPK_OPT_F64_POSITIONS 23     /* genpk_deposit_f64: 0 (default) narrows the doubles to float first, as read_fieldize_bigfile.cpp
+                                          :93-94 does; 1 uses them as they are, which is what a reference built with
+                                          -DDOUBLE_PRECISION_SNAP (gen-pk.h:25-29, read_fieldize.cpp:24-25) hands to fieldize() */
 /* ---- binning pass selection (genpk_set_option(ctx, GENPK_OPT_POWER, v)) ------------ */
 #define GENPK_OPT_POWER          3
 #define GENPK_POWER_CACHED       0     /* sum|k| and mode counts per bin depend on the grid only: computed

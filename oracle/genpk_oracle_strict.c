@@ -67,3 +67,42 @@ void oracle_fixed_to_double(const int64_t *q, double *out, size_t ncell, int sca
     for (size_t i = 0; i < ncell; i++)
         out[i] = (double)q[i] * inv;
 }
+
+/* The same rule for double-precision positions used as they are -- what a reference built with
+ * -DDOUBLE_PRECISION_SNAP hands to fieldize() (gen-pk.h:25-29: GENPK_FLOAT_TYPE = double;
+ * fieldize.cpp:66 multiplies the double position itself).  Masses stay float32 arrays cast to
+ * the particle type in that build; here they are taken as float32, which is how they are stored. */
+int oracle_fieldize_fixed_f64(double boxsize, int dims, int64_t *out_q, int64_t n,
+                              const double *positions, const float *masses, double mass,
+                              int extra, int scale_bits)
+{
+    const size_t fd = 2 * (size_t)(dims / 2 + extra);
+    const size_t plane = fd * (size_t)dims;
+    const double units = dims / boxsize;
+    const double scale = ldexp(1.0, scale_bits);
+    for (int64_t p = 0; p < n; p++) {
+        const double m = masses ? (double)masses[p] : mass;
+        int lo[3], hi[3];
+        double wl[3], wh[3];
+        for (int a = 0; a < 3; a++) {
+            const double x = positions[3 * p + a] * units;
+            const double fl = floor(x);
+            const int f = (int)fl;
+            wh[a] = x - fl;
+            wl[a] = 1.0 - wh[a];
+            hi[a] = wrap_cell(f + 1, dims);
+            lo[a] = wrap_cell(f, dims);
+        }
+        for (int c = 0; c < 8; c++) {
+            const int sx = c & 1, sy = (c >> 1) & 1, sz = (c >> 2) & 1;
+            double w = m * (sx ? wh[0] : wl[0]);
+            w = w * (sy ? wh[1] : wl[1]);
+            w = w * (sz ? wh[2] : wl[2]);
+            const int64_t q = llrint(w * scale);
+            const size_t idx = plane * (size_t)(sx ? hi[0] : lo[0]) + fd * (size_t)(sy ? hi[1] : lo[1])
+                             + (size_t)(sz ? hi[2] : lo[2]);
+            out_q[idx] += q;
+        }
+    }
+    return 0;
+}

@@ -28,6 +28,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 PORT_SO = os.path.join(_HERE, "libgenpk_oracle.so")
 REF_SO = os.path.join(_HERE, "_ref", "libgenpk_ref.so")
+REF_F64_SO = os.path.join(_HERE, "_ref", "libgenpk_ref_f64.so")     # fieldize.cpp built with -DDOUBLE_PRECISION_SNAP
 REF_SNAPSHOT = os.path.join(_HERE, "_ref", "test_g2_snap")
 
 _f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
@@ -146,6 +147,23 @@ class Oracle:
         return f(float(boxsize), int(dims), out_q.ctypes.data, n, positions.ctypes.data, mp, float(mass),
                  int(extra), int(scale_bits))
 
+    def fieldize_fixed_f64(self, boxsize, dims, out_q, positions, masses=None, mass=1.0, extra=1, scale_bits=40):
+        """Fixed-point rule on double-precision positions used as they are (DOUBLE_PRECISION_SNAP)."""
+        assert self.kind == "port"
+        positions = np.ascontiguousarray(positions, dtype=np.float64)
+        n = positions.size // 3
+        assert out_q.dtype == np.int64 and out_q.flags.c_contiguous
+        mp = None
+        if masses is not None:
+            masses = np.ascontiguousarray(masses, dtype=np.float32)
+            mp = masses.ctypes.data
+        f = self.lib.oracle_fieldize_fixed_f64
+        f.restype = C.c_int
+        f.argtypes = [C.c_double, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_double, C.c_int,
+                      C.c_int]
+        return f(float(boxsize), int(dims), out_q.ctypes.data, n, positions.ctypes.data, mp, float(mass),
+                 int(extra), int(scale_bits))
+
     def fixed_to_double(self, q, scale_bits):
         assert self.kind == "port"
         out = np.empty(q.shape, np.float64)
@@ -182,6 +200,26 @@ class Oracle:
         fld = np.ascontiguousarray(field, np.float64)
         f(int(n), fld.ctypes.data, out.ctypes.data)
         return out
+
+
+def have_reference_f64() -> bool:
+    return os.path.exists(REF_F64_SO)
+
+
+def ref_fieldize_f64(boxsize, dims, out, positions, masses=None, mass=1.0, extra=1):
+    """fieldize() of the reference compiled with -DDOUBLE_PRECISION_SNAP (gen-pk.h:25-29): positions and
+    masses are double arrays, used as they are (fieldize.cpp:46, 63-69)."""
+    lib = C.CDLL(REF_F64_SO)
+    f = lib.ref_fieldize_f64
+    f.restype = C.c_int
+    f.argtypes = [C.c_double, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_double, C.c_int]
+    positions = np.ascontiguousarray(positions, dtype=np.float64)
+    n = positions.size // 3
+    mp = None
+    if masses is not None:
+        masses = np.ascontiguousarray(masses, dtype=np.float64)
+        mp = masses.ctypes.data
+    return f(float(boxsize), int(dims), out.ctypes.data, n, positions.ctypes.data, mp, float(mass), int(extra))
 
 
 class RefSnapshot:

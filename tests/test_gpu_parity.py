@@ -420,3 +420,46 @@ def test_double_precision_positions_are_narrowed_like_the_reference(var_mass):
     assert want.any()
     assert np.array_equal(got, want)
     assert np.array_equal(got_dev, want)
+
+
+@pytest.mark.parametrize("var_mass", [False, True])
+def test_double_precision_positions_used_as_they_are(port, var_mass):
+    """GENPK_OPT_F64_POSITIONS=1: genpk_deposit_f64 hands the doubles to the deposit un-narrowed, which is what a
+    reference built with -DDOUBLE_PRECISION_SNAP does (gen-pk.h:25-29, read_fieldize.cpp:24-25).  Fixed-point
+    grid bit-exact against the CPU restatement (pinned to that reference build in tests/test_oracle.py), fp64
+    grid within 1e-6 of the reference objects themselves; host and device-resident input."""
+    import torch
+    from oracle.oracle import have_reference_f64, ref_fieldize_f64
+    dims, box, n = 96, 250.0, 300000
+    rng = np.random.default_rng(12)
+    pos64 = (rng.random((n, 3)) * 1.1 - 0.05) * box
+    masses = (10.0 ** rng.uniform(-1, 1, n)).astype(np.float32) if var_mass else None
+    want = np.zeros(padded_shape(dims), np.int64)
+    port.fieldize_fixed_f64(box, dims, want, pos64, masses, 0.5, 1, 40)
+    narrowed = np.zeros(padded_shape(dims), np.int64)
+    port.fieldize_fixed(box, dims, narrowed, pos64.astype(np.float32), masses, 0.5, 1, 40)
+    assert not np.array_equal(want, narrowed)
+    with gp.Context(dims, flags=api.FLAG_FIXED_POINT) as ctx:
+        ctx.set_option(api.OPT_F64_POSITIONS, 1)
+        ctx.grid_zero()
+        ctx.deposit_f64(pos64, masses, 0.5, box)
+        got = ctx.grid_download_fixed()
+        dpos = torch.from_numpy(pos64.reshape(-1).copy()).cuda()
+        dm = torch.from_numpy(masses).cuda() if var_mass else None
+        ctx.grid_zero()
+        ctx.deposit_f64_dev(dpos.data_ptr(), n, dm.data_ptr() if var_mass else 0, 0.5, box)
+        got_dev = ctx.grid_download_fixed()
+        ctx.synchronize()
+    assert np.array_equal(got, want.reshape(-1))
+    assert np.array_equal(got_dev, want.reshape(-1))
+    if have_reference_f64():
+        ref = np.zeros(padded_shape(dims))
+        ref_fieldize_f64(box, dims, ref, pos64, masses, 0.5, 1)
+        with gp.Context(dims) as ctx:
+            ctx.set_option(api.OPT_F64_POSITIONS, 1)
+            ctx.grid_zero()
+            ctx.deposit_f64(pos64, masses, 0.5, box)
+            g = ctx.grid_download()
+            ctx.synchronize()
+        tol = 1e-6 * np.abs(ref).reshape(-1) + 1e-6 * np.abs(ref).mean()
+        assert np.all(np.abs(g - ref.reshape(-1)) <= tol)

@@ -129,3 +129,26 @@ def test_fixed_point_restatement(port):
     port.fieldize_fixed(box, dims, q2, pos[rng.permutation(n)], None, 1.0, 1, S)
     assert np.array_equal(q, q2)
     assert abs(g.sum() - n) < 8 * n * 2.0 ** -S
+
+
+def test_double_precision_restatement_against_the_reference_built_with_double_precision_snap(port):
+    """oracle_fieldize_fixed_f64 (the parity target of GENPK_OPT_F64_POSITIONS=1) against fieldize.cpp compiled
+    unmodified with -DDOUBLE_PRECISION_SNAP: positions with full double mantissas, some outside the box."""
+    from oracle.oracle import have_reference_f64, padded_shape, ref_fieldize_f64
+    if not have_reference_f64():
+        pytest.skip("oracle/_ref/libgenpk_ref_f64.so not built (needs /root/reference)")
+    rng = np.random.default_rng(21)
+    dims, box, n = 24, 50.0, 20000
+    pos = (rng.random((n, 3)) * 1.2 - 0.1) * box
+    masses = (10.0 ** rng.uniform(-1, 1, n)).astype(np.float32)
+    for m in (None, masses):
+        want = np.zeros(padded_shape(dims))
+        assert ref_fieldize_f64(box, dims, want, pos, m, 0.7, 1) == 0
+        q = np.zeros(padded_shape(dims), np.int64)
+        port.fieldize_fixed_f64(box, dims, q, pos, m, 0.7, 1, 40)
+        got = port.fixed_to_double(q, 40)
+        np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-9 * want.mean())
+        # and it is NOT what narrowing the positions to float first gives
+        narrowed = np.zeros(padded_shape(dims), np.int64)
+        port.fieldize_fixed(box, dims, narrowed, pos.astype(np.float32), m, 0.7, 1, 40)
+        assert not np.array_equal(narrowed, q)

@@ -17,3 +17,4 @@ run() { name=$1; shift; echo "== $name: $*"; timeout 400 $T "$@" > gpurun_out/r2
 run c3_n2_pull --check-mass
 run c3_n2_sendrecv --no-ghost-pull --no-e2e
 run c3_n2_pull_fixed --fixed-point --no-e2e
+run c3_n2_march --no-sweep --no-e2e
