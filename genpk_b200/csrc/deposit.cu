@@ -396,7 +396,8 @@ int deposit_device(genpk_ctx *ctx, int which, const float *pos, const float *mas
             local.dx_dev = ctx->plan_cached.dx_dev;
         } else {
             // the grid can be cleared while the probe runs and its verdict travels to the host
-            if (ctx->zero_pending[which] && !(ctx->zero_ahead && ctx->sweep_rx == 0 && ctx->sweep))
+            const bool may_sweep = ctx->deposit_mode == GENPK_DEPOSIT_SWEEP || (ctx->deposit_mode == GENPK_DEPOSIT_AUTO && ctx->sweep);
+            if (ctx->zero_pending[which] && !(ctx->zero_ahead && ctx->sweep_rx == 0 && may_sweep))
                 if (int rc = materialize_zero(ctx, which)) return rc;
             if (int rc = deposit_plan(ctx, pos, n, boxsize, &local))
                 return rc;

@@ -209,14 +209,15 @@ def test_sweep_rejects_non_finite_positions(port):
 
 
 def test_sweep_fp64_vs_oracle_and_auto(port):
-    """fp64 accumulation (tolerance 1e-6) through AUTO: the probe must find the lattice and AUTO must
-    pick the sweep with zero ahead."""
+    """fp64 accumulation (tolerance 1e-6) through AUTO with GENPK_OPT_SWEEP: the probe must find the lattice
+    and AUTO must pick the sweep kernel."""
     n_side, dims, box = 128, 128, 250.0
     dpos, pos = synth(api.SYNTH_CLUSTERED, n_side, dims, box)
     n = n_side ** 3
     want = np.zeros(padded_shape(dims))
     port.fieldize(box, dims, want, pos, None, 1.0, 1)
     with gp.Context(dims) as ctx:
+        ctx.set_option(api.OPT_SWEEP, 1)                     # AUTO: the sweep kernel instead of the march kernel
         poison(ctx)
         ctx.grid_zero()
         ctx.deposit_dev(dpos.data_ptr(), n, 0, 1.0, box)
