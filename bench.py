@@ -62,7 +62,6 @@ def parse_args():
     ap.add_argument("--sweep-couple", type=int, default=-1, help="planes a sweep warp may lead the slowest one by (0 = uncoupled)")
     ap.add_argument("--za-zero-ctas", type=int, default=0)
     ap.add_argument("--sweep-couple-step", type=int, default=0)
-    ap.add_argument("--sweep-grid-prefetch", type=int, default=-1)
     ap.add_argument("--sweep-rx", type=int, default=-1, help="lattice planes per sweep task (0 = one persistent sweep)")
     ap.add_argument("--sweep-poll-strong", action="store_true")
     ap.add_argument("--no-self-check", action="store_true", help="skip the comparison with the committed reference fixtures")
@@ -428,8 +427,6 @@ def run_ours(args):
         ctx.set_option(api.OPT_SWEEP_COUPLE, args.sweep_couple)
     if args.za_zero_ctas:
         ctx.set_option(api.OPT_ZA_ZERO_CTAS, args.za_zero_ctas)
-    if args.sweep_grid_prefetch >= 0:
-        ctx.set_option(api.OPT_SWEEP_GRID_PREFETCH, args.sweep_grid_prefetch)
     if args.sweep_rx >= 0:
         ctx.set_option(api.OPT_SWEEP_RX, args.sweep_rx)
     if args.sweep_couple_step:

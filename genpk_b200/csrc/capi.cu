@@ -262,10 +262,6 @@ int genpk_set_option(genpk_ctx *ctx, int option, int64_t value)
         if (value < 0 || value > 4096) break;
         ctx->sweep_couple = (int)value;
         return 0;
-    case GENPK_OPT_SWEEP_GRID_PREFETCH:
-        if (value < 0 || value > 4096) break;
-        ctx->sweep_grid_prefetch = (int)value;
-        return 0;
     case GENPK_OPT_SWEEP_RX:
         if (value < 0 || value > 65535) break;
         ctx->sweep_rx = (int)value;

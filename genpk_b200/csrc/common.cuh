@@ -138,7 +138,6 @@ struct genpk_ctx {
     int sweep = 0;                            // 1: AUTO picks the sweep kernel for lattice input; 0 (default): the march kernel
                                               // (measured equal on C3, profiles/r02; the march kernel is the longer-serving one)
     int sweep_ry = 0;                         // rows per column (0: 8 in task mode; as few as keep every column resident otherwise)
-    int sweep_grid_prefetch = 0;              // task mode: 1 + planes ahead of a task's own planes whose grid lines it prefetches (0: off)
     int sweep_rx = 8;                         // > 0: task mode, blocks of rx lattice planes; 0: one persistent sweep (coupled, may zero ahead)
     int zero_ahead = 1;                       // genpk_grid_zero is lazy; a sweep that follows clears the grid ahead of its front
     int za_window = 0;                        // planes ahead of the expected plane kept clear (0: from the order probe)

@@ -46,9 +46,8 @@ constexpr int SWEEP_RY_MAX = 21;         // x-carry slots per thread: (ry + 1) *
 struct SweepArgs {
     long long n0, n1;            // lattice row length, rows per plane (z fastest)
     long long x_begin, x_end;    // lattice planes swept
-    int grid_prefetch;           // task mode: planes ahead whose grid lines a task pulls into L2 when it starts (0: off)
-    long long gp_x0;             // expected grid plane (local) of lattice plane x_begin, for that prefetch
-    unsigned long long gp_xstep, gp_ystep, gp_zstep;   // grid planes / rows / cells per lattice plane / row / site, 32.32
+    long long row_bytes;         // 12 * n0: bytes between lattice rows of the particle array
+    long long plane_bytes;       // 12 * n0 * n1: bytes between lattice planes
     int rx;                      // > 0: blockIdx.y splits the sweep into blocks of rx lattice planes (independent tasks in
                                  // launch order: the front is then rx planes thick without any waiting); 0: one sweep
     int ry;                      // lattice rows per column
@@ -239,8 +238,8 @@ __global__ void __maxnreg__(GENPK_SWEEP_MAXREG) deposit_sweep_kernel(const __gri
     const long long plane_inc = (g.n1 - ry_eff + 1) * g.n0;
     // byte steps of the load pointer: a row, and what the last row of a block adds on top of it
     // (opaque to the compiler, which would otherwise redo the 64-bit products every step)
-    long long row_bytes = 12 * g.n0, block_adj_bytes = 12 * (plane_inc - g.n0);
-    asm volatile("" : "+l"(row_bytes), "+l"(block_adj_bytes));
+    long long block_adj_bytes = 12 * (plane_inc - g.n0);
+    asm volatile("" : "+l"(block_adj_bytes));
     const char *lp = reinterpret_cast<const char *>(a.pos + 3 * p);
     const float *lm = MASS ? a.mass + p : nullptr;
     // the lattice planes of this task
@@ -256,43 +255,13 @@ __global__ void __maxnreg__(GENPK_SWEEP_MAXREG) deposit_sweep_kernel(const __gri
     }
     const int n_planes = (int)(x_last - x_first);
     int l_r = 0;                                             // row (within the block) of the row lp points at
-    // Task mode: pull the grid lines this task's column is expected to write (its rows and cells, the
-    // planes of this task shifted by grid_prefetch) into L2 as whole 128-byte lines, so that the
-    // reductions find them there instead of missing sector by sector.  Performance only.
-    if (g.grid_prefetch > 0 && g.rx > 0) {
-        const long long gx0 = g.gp_x0 + (long long)(((unsigned long long)(x_first - g.x_begin) * g.gp_xstep) >> 32) + g.grid_prefetch;
-        const long long gx1 = g.gp_x0 + (long long)(((unsigned long long)(x_last - g.x_begin) * g.gp_xstep + 0xffffffffull) >> 32) + g.grid_prefetch;
-        const long long gy0 = (long long)(((unsigned long long)y0 * g.gp_ystep) >> 32);
-        const long long gy1 = (long long)(((unsigned long long)(y0 + ry_eff) * g.gp_ystep + 0xffffffffull) >> 32);
-        const long long gz0 = (long long)(((unsigned long long)(31LL * zseg) * g.gp_zstep) >> 32);
-        const long long gz1 = (long long)(((unsigned long long)(31LL * zseg + 32) * g.gp_zstep + 0xffffffffull) >> 32);
-        const int n_px = (int)(gx1 - gx0), n_py = (int)(gy1 - gy0);
-        const int lines = (int)((gz1 * 8 + 127) / 128 - (gz0 * 8) / 128);
-        const int total = n_px * n_py * lines;
-        const int n_local_planes = a.slab ? a.xl_max + 2 : dims;
-        for (int i = lane; i < total; i += 32) {
-            const int li = i % lines, rest = i / lines;
-            long long px_ = gx0 + rest / n_py, py_ = gy0 + rest % n_py;
-            if (!a.slab) {
-                px_ %= dims;
-                if (px_ < 0) px_ += dims;
-            }
-            if (px_ >= 0 && px_ < n_local_planes && py_ < dims) {
-                const char *line = reinterpret_cast<const char *>(grid) + ((size_t)px_ * a.plane + (size_t)py_ * a.fd) * 8 +
-                                   ((size_t)(gz0 * 8) / 128 + li) * 128;
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
-            }
-        }
-    }
     // L2 prefetch: the same row one lattice plane further on (ry_eff steps ahead of the load, which itself
     // runs one row ahead of the deposit); no cursor of its own
-    long long next_plane_bytes = 12 * g.n0 * g.n1;
-    asm volatile("" : "+l"(next_plane_bytes));
     float ax = 0.f, ay = 0.f, az = 0.f, am = 0.f;             // the row in flight
     auto issue_load = [&](bool prefetch_ok) {
         if (lane_in_row && (FULL || lp_index < a.n)) {
             if (FULL && prefetch_ok)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(lp + next_plane_bytes));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(lp + g.plane_bytes));
             ax = __ldcs(reinterpret_cast<const float *>(lp));
             ay = __ldcs(reinterpret_cast<const float *>(lp) + 1);
             az = __ldcs(reinterpret_cast<const float *>(lp) + 2);
@@ -300,7 +269,7 @@ __global__ void __maxnreg__(GENPK_SWEEP_MAXREG) deposit_sweep_kernel(const __gri
                 am = __ldcs(lm);
         }
         const bool last_row = ++l_r == ry_eff;
-        lp += row_bytes;
+        lp += g.row_bytes;
         if (last_row) {
             lp += block_adj_bytes;
             l_r = 0;
@@ -666,6 +635,8 @@ int launch_sweep(genpk_ctx *ctx, const DepositArgs &a, long long n0, long long n
     const long long n2 = (rows + n1 - 1) / n1;
     g.n0 = n0;
     g.n1 = n1;
+    g.row_bytes = 12 * n0;
+    g.plane_bytes = 12 * n0 * n1;
     g.x_begin = 0;
     g.x_end = n2;
     g.nzs = n0 >= 2 ? (int)((n0 - 2) / 31 + 1) : 1;
@@ -692,15 +663,6 @@ int launch_sweep(genpk_ctx *ctx, const DepositArgs &a, long long n0, long long n
         if (ry > ry_cap) ry = ry_cap;
         g.ry = ry;
         g.rx = (int)(n2 < ctx->sweep_rx ? n2 : ctx->sweep_rx);
-        g.grid_prefetch = ctx->sweep_grid_prefetch;
-        {
-            const SlabGeom &sgeo = ctx->g;
-            const double ppx = (double)sgeo.nx / (double)n2;
-            g.gp_xstep = (unsigned long long)llround(ppx * 4294967296.0);
-            g.gp_ystep = (unsigned long long)llround((double)sgeo.dims / (double)n1 * 4294967296.0);
-            g.gp_zstep = (unsigned long long)llround((double)sgeo.dims / (double)n0 * 4294967296.0);
-            g.gp_x0 = (long long)floor(0.5 * ppx) + (info && info->dx_valid ? info->dx_mean : sgeo.ghost_lo);
-        }
         g.ncols = (int)(g.nzs * ((n1 + ry - 1) / ry));
         const size_t smem = sweep_smem(ry, ctx->fixed, key32);
         GENPK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -78,8 +78,6 @@ extern "C" {
 #define GENPK_OPT_SWEEP_RX      21     /* N > 0 (default 8): the sweep runs as independent tasks of N lattice planes x one block of
                                           rows x one segment, in launch order (no waiting; the grid is cleared by a memset);
                                           0: one persistent sweep over all planes, coupled, which can clear the grid ahead of itself */
-#define GENPK_OPT_SWEEP_GRID_PREFETCH 22 /* task mode: every task first pulls the grid lines of its column, N planes ahead of its own
-                                          planes, into L2 (0 = off) */
 #define GENPK_OPT_SWEEP_POLL_WEAK 20   /* 1 (default): marks are probed with weak L1-bypassing loads; 0: relaxed.gpu loads */
 #define GENPK_OPT_F64_POSITIONS 23     /* genpk_deposit_f64: 0 (default) narrows the doubles to float first, as read_fieldize_bigfile.cpp
                                           :93-94 does; 1 uses them as they are, which is what a reference built with
