@@ -76,6 +76,7 @@ def parse_args():
                     help="cuFFT x pass + bin_power_kernel instead of the fused x-pass/binning kernel")
     ap.add_argument("--xpass-narrow-tile", action="store_true", help="fused x pass with 4096-mode tiles at 1024 (two CTAs per SM)")
     ap.add_argument("--fft-yz-batch", type=int, default=-1, help="x planes per 2-D cuFFT call (0 = all, -1 = library default)")
+    ap.add_argument("--no-tma", action="store_true", help="column kernels: per-thread cp.async tile fills instead of TMA bulk tensor copies")
     ap.add_argument("--no-own-ypass", action="store_true", help="cuFFT's 2-D (y,z) plan instead of cuFFT z + own y pass")
     ap.add_argument("--no-ghost-pull", action="store_true", help="multi-GPU: NCCL send/recv of the ghost planes instead of peer loads")
     ap.add_argument("--no-scatter", action="store_true", help="multi-GPU: pack + all-to-all instead of the y pass storing into peers")
@@ -408,6 +409,8 @@ def run_ours(args):
         ctx.set_option(api.OPT_FUSED_XPASS, 2)
     if args.no_own_ypass:
         ctx.set_option(api.OPT_OWN_YPASS, 0)
+    if args.no_tma:
+        ctx.set_option(api.OPT_TMA, 0)
     if args.fft_yz_batch >= 0:
         ctx.set_option(api.OPT_FFT_YZ_BATCH, args.fft_yz_batch)
     fused = ctx.fused_xpass_supported(nrbins)

@@ -226,6 +226,10 @@ int genpk_set_option(genpk_ctx *ctx, int option, int64_t value)
         if (value != 0 && value != 1) break;
         ctx->own_ypass = (int)value;
         return 0;
+    case GENPK_OPT_TMA:
+        if (value != 0 && value != 1) break;
+        ctx->use_tma = (int)value;
+        return 0;
     case GENPK_OPT_FUSED_XPASS:
         if (value < 0 || value > 2) break;
         ctx->fused_xpass = (int)value;

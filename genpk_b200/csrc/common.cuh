@@ -156,6 +156,7 @@ struct genpk_ctx {
 
     // fused x pass (fftx_power.cu)
     int fused_xpass = 1;                      // 0: always cuFFT's x pass + bin_power_kernel
+    int use_tma = 1;                          // column kernels fill their tiles with bulk tensor copies (0: per-thread cp.async)
     int own_ypass = 1;                        // 1: (y,z) transform = cuFFT 1-D r2c along z + fft_cols_kernel along y
     int smem_optin = 0;                       // opt-in shared memory per CTA of this device
     double *d_twiddle = nullptr;              // exp(-2 pi i t/dims), t < dims

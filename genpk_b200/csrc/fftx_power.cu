@@ -21,6 +21,8 @@
 //
 // Supported: dims in {256, 512, 1024, 2048}, auto spectra.  Everything else (other sizes,
 // cross spectra, callers that want the transformed grid) keeps the cuFFT + bin_power path.
+#include <cuda.h>
+
 #include "common.cuh"
 #include "fftx_core.cuh"
 
@@ -29,6 +31,8 @@ namespace genpk {
 using namespace fftx;
 
 struct FftxArgs {
+    alignas(64) CUtensorMap tmap;   // the spectrum as {2*nc doubles, n_mid rows, dims slabs}; box {2C, 1, 256}
+    int use_tma;
     const double2 *spec;      // [dims][n_mid][nc]
     const double2 *tw;        // exp(-2 pi i t / dims), t < dims
     int dims, nc, n_mid, mid0;
@@ -43,6 +47,76 @@ struct FftxArgs {
     double *sums;             // nrbins P sums, accumulated into
     int hists;                // histograms per CTA (1 or 2: even / odd tile columns)
 };
+
+// ---- TMA: a tile [N][C] of complex doubles is N rows of C*16 contiguous bytes at a fixed pitch -- a 3-D tensor
+// box {C complex, rows, 1}.  One elected thread arms an mbarrier with the tile's byte count and issues
+// N/256 bulk tensor copies (a box dimension holds at most 256); nobody computes an address, nobody waits on
+// a copy it issued itself.  Columns past the end of a row are zero-filled by the copy engine.
+constexpr int TMA_BOX_ROWS = 256;
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE;\n\tbra WAIT;\n\tDONE:\n\t}"
+                 ::"r"(addr), "r"(parity) : "memory");
+}
+// box at coordinates (c0 doubles along a row, c1, c2) of the 3-D tensor behind `map` -> shared memory
+__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *map, int c0, int c1, int c2, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2),
+                   "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+typedef CUresult (*tmap_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library does not link libcuda)
+static tmap_encode_fn tmap_encoder()
+{
+    static tmap_encode_fn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<tmap_encode_fn>(p);
+    }
+    return fn;
+}
+
+// Tensor of complex doubles viewed as doubles: inner extent 2*cols (valid columns), `rows` rows `row_pitch` complex
+// apart, `slabs` slabs `slab_pitch` complex apart; box = {2*C doubles, box_rows, box_slabs}.
+static int make_tile_map(CUtensorMap *map, const void *base, long long cols, long long rows, long long row_pitch, long long slabs,
+                         long long slab_pitch, int C, int box_rows, int box_slabs)
+{
+    tmap_encode_fn enc = tmap_encoder();
+    if (!enc) {
+        set_error("TMA: cuTensorMapEncodeTiled is not available from this driver");
+        return 1;
+    }
+    const cuuint64_t dims[3] = {(cuuint64_t)(2 * cols), (cuuint64_t)rows, (cuuint64_t)slabs};
+    const cuuint64_t strides[2] = {(cuuint64_t)row_pitch * 16, (cuuint64_t)slab_pitch * 16};
+    const cuuint32_t box[3] = {(cuuint32_t)(2 * C), (cuuint32_t)box_rows, (cuuint32_t)box_slabs};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void *>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("TMA: cuTensorMapEncodeTiled failed with %d (cols %lld rows %lld pitch %lld)", (int)r, cols, rows, row_pitch);
+        return 1;
+    }
+    return 0;
+}
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
 {
@@ -112,7 +186,7 @@ __global__ void __launch_bounds__(PL::THREADS, PL::TILE == 4096 ? 2 : 1) fftx_po
 {
     constexpr int N = PL::N, C = PL::C, TILE_MODES = PL::TILE, CTA_THREADS = PL::THREADS;
     constexpr int R2 = PL::R2, R3 = PL::R3;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     cd *const stage = reinterpret_cast<cd *>(smem_raw);                                 // [N][C], the next tile
     cd *const E = reinterpret_cast<cd *>(smem_raw + (size_t)TILE_MODES * 16);           // [N/2][C] complex exchange
     double *const P = reinterpret_cast<double *>(E);                                    // [N][C] |X|^2, same bytes
@@ -151,7 +225,24 @@ __global__ void __launch_bounds__(PL::THREADS, PL::TILE == 4096 ? 2 : 1) fftx_po
             m++;
         }
     };
+    __shared__ __align__(8) unsigned long long tile_bar;
+    if (A.use_tma && tid == 0) {
+        mbar_init(&tile_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    unsigned tile_parity = 0;
     auto issue = [&](int g, int m) {
+        if (A.use_tma) {
+            // one thread, N/256 bulk tensor copies: x runs along the third tensor dimension
+            if (tid == 0 && m < A.n_mid) {
+                mbar_expect_tx(&tile_bar, (unsigned)(TILE_MODES * 16));
+#pragma unroll 1
+                for (int x = 0; x < N; x += TMA_BOX_ROWS)
+                    tma_load_3d(stage + (size_t)x * C, &A.tmap, 2 * g * C, m, x, &tile_bar);
+            }
+            return;
+        }
         if (m < A.n_mid) {
             const int kz = g * C + c;
             if (kz < A.nc) {
@@ -177,15 +268,23 @@ __global__ void __launch_bounds__(PL::THREADS, PL::TILE == 4096 ? 2 : 1) fftx_po
         kj = kj <= A.dims / 2 ? kj : kj - A.dims;                    // KVAL, powerspectrum.c:33
 
         cd v[EPT], w[EPT];
-        cp_async_wait_all();
+        if (A.use_tma) {
+            mbar_wait(&tile_bar, tile_parity);
+            tile_parity ^= 1u;
+        } else {
+            cp_async_wait_all();
+        }
 #pragma unroll
         for (int i = 0; i < EPT; i++)
             v[i] = valid ? stage[PL::load_n(t, i) * C + c] : make_double2(0.0, 0.0);
         loads_landed(v);
-        issue(g_next, m_next);                                       // the slots are free: the next tile has the whole tile time to arrive
+        if (!A.use_tma)
+            issue(g_next, m_next);                                   // the slots are free: the next tile has the whole tile time to arrive
         PL::pass1(v, t, A.tw);
 
         __syncthreads();                                             // the previous tile's bin walk has left P
+        if (A.use_tma)
+            issue(g_next, m_next);                                   // (every thread has taken its part of the staged tile)
         exchange<N, C, false, PL::ONE_UNIT2>(E, v, w, c, [&](int i) { return t + PL::ex1_w_part(i); },
                        [&](int i) { return b_ex1r + PL::ex1_r_part(i); });
         PL::pass2(w, t, A.tw);
@@ -219,6 +318,8 @@ __global__ void __launch_bounds__(PL::THREADS, PL::TILE == 4096 ? 2 : 1) fftx_po
 // rows of C*16 bytes (cuFFT's strided pass reaches about half the copy bandwidth here).
 // ---------------------------------------------------------------------------------
 struct FftColsArgs {
+    alignas(64) CUtensorMap tmap;   // the planes as {2*nc doubles, N rows, n_planes slabs}; box {2C, 256, 1}
+    int use_tma;
     double2 *spec;            // [n_planes][N][nc], transformed in place
     const double2 *tw;
     int nc;
@@ -240,7 +341,7 @@ __global__ void __launch_bounds__(PL::THREADS, PL::TILE == 4096 ? 2 : 1) fft_col
 {
     constexpr int N = PL::N, C = PL::C, TILE_MODES = PL::TILE;
     constexpr int R2 = PL::R2, R3 = PL::R3;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     cd *const stage = reinterpret_cast<cd *>(smem_raw);                                 // [N][C], the next tile
     cd *const E = reinterpret_cast<cd *>(smem_raw + (size_t)TILE_MODES * 16);           // [N/2][C] complex exchange
     const int tid = threadIdx.x;
@@ -264,7 +365,24 @@ __global__ void __launch_bounds__(PL::THREADS, PL::TILE == 4096 ? 2 : 1) fft_col
             o++;
         }
     };
+    __shared__ __align__(8) unsigned long long tile_bar;
+    if (A.use_tma && tid == 0) {
+        mbar_init(&tile_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    unsigned tile_parity = 0;
     auto issue = [&](int g, int o) {
+        if (A.use_tma) {
+            // one thread, N/256 bulk tensor copies of 256 rows x C*16 bytes each
+            if (tid == 0 && o < A.n_planes) {
+                mbar_expect_tx(&tile_bar, (unsigned)(TILE_MODES * 16));
+#pragma unroll 1
+                for (int y = 0; y < N; y += TMA_BOX_ROWS)
+                    tma_load_3d(stage + (size_t)y * C, &A.tmap, 2 * g * C, y, o, &tile_bar);
+            }
+            return;
+        }
         if (o < A.n_planes) {
             const int kz = g * C + c;
             if (kz < A.nc) {
@@ -287,15 +405,23 @@ __global__ void __launch_bounds__(PL::THREADS, PL::TILE == 4096 ? 2 : 1) fft_col
         const int kz = g * C + c;
         const bool valid = kz < A.nc;
         cd v[EPT], w[EPT];
-        cp_async_wait_all();
+        if (A.use_tma) {
+            mbar_wait(&tile_bar, tile_parity);
+            tile_parity ^= 1u;
+        } else {
+            cp_async_wait_all();
+        }
 #pragma unroll
         for (int i = 0; i < EPT; i++)
             v[i] = valid ? stage[PL::load_n(t, i) * C + c] : make_double2(0.0, 0.0);
         PL::pass1(v, t, A.tw);
         // (issued after pass 1 here: right after the fill these loads would queue up behind the
         // previous tile's store burst -- measured 3.9 -> 5.3 ms, profiles/r01/s29)
-        issue(g_next, o_next);                                       // another tile: never the rows written below
+        if (!A.use_tma)
+            issue(g_next, o_next);                                   // another tile: never the rows written below
         __syncthreads();                                             // the previous tile's last exchange read is over
+        if (A.use_tma)
+            issue(g_next, o_next);                                   // (every thread has taken its part of the staged tile)
         exchange<N, C, false, PL::ONE_UNIT2>(E, v, w, c, [&](int i) { return t + PL::ex1_w_part(i); },
                        [&](int i) { return b_ex1r + PL::ex1_r_part(i); });
         PL::pass2(w, t, A.tw);
@@ -438,9 +564,16 @@ int fftx_power_raw(genpk_ctx *ctx, const double *spec_yz, int n_mid, int mid0, i
     A.sums = sums_dev;
     A.hists = fftx_hists(ctx, nrbins);
     const size_t smem = fftx_smem_bytes(ctx, nrbins);
+    A.use_tma = 0;
+    int tma_rc = 0;
     auto tiles = [&](int C) {
         A.groups = (A.nc + C - 1) / C;
         A.n_tiles = (long long)n_mid * A.groups;
+        if (ctx->use_tma && tmap_encoder()) {
+            // {2*nc doubles} x {n_mid rows, row_pitch apart} x {dims values of x, x_stride apart}; box {2C, 1, 256}
+            tma_rc = make_tile_map(&A.tmap, spec_yz, A.nc, n_mid, A.row_pitch, A.dims, A.x_stride, C, 1, TMA_BOX_ROWS);
+            A.use_tma = tma_rc == 0 ? 1 : 0;
+        }
     };
     // (tests/fftx_emu.cpp instantiates the same plans on the host)
     typedef Plan<4, 8, 8, 4096> P256;
@@ -468,6 +601,9 @@ template <class PL, bool SCATTER> static int launch_cols(genpk_ctx *ctx, FftCols
     A.groups = (A.nc + PL::C - 1) / PL::C;
     A.n_planes = n_planes;
     A.n_tiles = (long long)n_planes * A.groups;
+    A.use_tma = 0;
+    if (ctx->use_tma && tmap_encoder())
+        A.use_tma = make_tile_map(&A.tmap, A.spec, A.nc, PL::N, A.nc, n_planes, A.plane_stride, PL::C, TMA_BOX_ROWS, 1) == 0 ? 1 : 0;
     GENPK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     GENPK_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PL::THREADS, smem));

@@ -99,6 +99,9 @@ extern "C" {
                                           grid side allows; 0: always cuFFT's x pass + the binning pass;
                                           2: as 1 with 4096-mode tiles at 1024 (measurements) */
 
+#define GENPK_OPT_TMA           24     /* 1 (default): the column kernels (y pass, fused x pass) fill their shared-memory tiles with
+                                          TMA bulk tensor copies behind an mbarrier; 0: per-thread cp.async (measurements) */
+
 typedef struct genpk_ctx genpk_ctx;
 #define GENPK_MAX_PEERS 16
 #define GENPK_IPC_HANDLE_BYTES 64

@@ -207,3 +207,24 @@ def test_scatter_y_pass_emulated_on_one_gpu(dims, P):
     finally:
         for s in st:
             s.close()
+
+
+@pytest.mark.parametrize("dims", [256, 512, 1024])
+def test_tma_tile_fills_give_the_same_bits_as_cp_async(dims):
+    """GENPK_OPT_TMA: the column kernels fill their tiles with bulk tensor copies (one thread, an mbarrier)
+    or with per-thread cp.async; the arithmetic is the same, so P(k) must be bit-identical (fixed-point
+    deposit: identical grids), for the y pass + fused x pass and for the last, partly empty column group."""
+    box, n = 1000.0, 300000
+    pos, _ = _particles(n, box, 17 + dims)
+    out = {}
+    for tma in (1, 0):
+        with gp.Context(dims, flags=api.FLAG_FIXED_POINT) as ctx:
+            ctx.set_option(api.OPT_TMA, tma)
+            ctx.grid_zero()
+            ctx.deposit(pos, None, 1.0, box)
+            out[tma] = ctx.fft_power(dims, float(n), float(n))
+            ctx.synchronize()
+    assert np.array_equal(out[1][1], out[0][1])
+    assert int(out[1][1].astype(np.int64).sum()) == dims ** 3 - 1
+    np.testing.assert_allclose(out[1][0], out[0][0], rtol=1e-12, atol=0)      # bin sums are shared-memory atomics: order may differ
+    assert np.array_equal(out[1][2], out[0][2])
