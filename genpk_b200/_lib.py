@@ -43,6 +43,8 @@ SIGNATURES = {
     "genpk_power_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, c_f64p, c_i32p, c_f64p, C.c_double,
                                   C.c_double]),
     "genpk_fft_power": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_f64p, c_i32p, c_f64p, C.c_double, C.c_double]),
+    "genpk_fft_power_cross": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, c_f64p, c_i32p, c_f64p, C.c_double,
+                                        C.c_double]),
     "genpk_fused_xpass_supported": (C.c_int, [C.c_void_p, C.c_int]),
     "genpk_pk_from_particles": (C.c_int, [C.c_void_p, c_f32p, c_f32p, C.c_int64, C.c_double, C.c_double, C.c_double,
                                           C.c_int, c_f64p, c_i32p, c_f64p]),

@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include <new>
+#include <vector>
 
 #include "common.cuh"
 
@@ -585,6 +586,87 @@ int genpk_fft_power(genpk_ctx *ctx, int which, int nrbins, double *power, int *c
                                   ctx->stream));
     GENPK_CUDA_OK(cudaStreamSynchronize(ctx->stream));
     return genpk_power_finalize(ctx->h_sums, nrbins, total_mass, total_mass2, power, count, keffs);
+}
+
+// a <- a + b, b <- a - b over two padded real grids (cross spectra by polarisation, see below)
+__global__ void sum_diff_kernel(double *a, double *b, size_t n)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double x = a[i], y = b[i];
+        a[i] = x + y;
+        b[i] = x - y;
+    }
+}
+
+// Cross spectrum of two real-space grids on the fused path.  powerspectrum() wants, per mode,
+// re1*re2 + im1*im2 (powerspectrum.c:68,77,86) = (|F1 + F2|^2 - |F1 - F2|^2) / 4, and the transform is
+// linear: the grids are replaced by their sum and difference, each goes through the fused auto path
+// (z pass, y pass, x pass + binning in one kernel, the x-transformed spectrum never written), and the
+// per-bin sums are combined on the host.  Two transforms either way; what is saved is the x pass's write
+// and the binning pass's read of both spectra (64 B/mode).  Rounding: the two auto sums are accurate to
+// a few ulp each, so the cross sum carries an absolute error of ~1e-15 * the auto power of the bin --
+// far inside the 1e-5 relative tolerance unless the fields are uncorrelated to ten digits.
+int genpk_fft_power_cross(genpk_ctx *ctx_a, int a, genpk_ctx *ctx_b, int b, int nrbins, double *power, int *count,
+                          double *keffs, double total_mass, double total_mass2)
+{
+    if (!check_which(ctx_a, a, "genpk_fft_power_cross") || !check_which(ctx_b, b, "genpk_fft_power_cross")) return 1;
+    if (nrbins < 1 || !power || !count || !keffs) { set_error("genpk_fft_power_cross: bad arguments"); return 1; }
+    if (ctx_a == ctx_b && a == b)
+        return genpk_fft_power(ctx_a, a, nrbins, power, count, keffs, total_mass, total_mass2);
+    if (ctx_a->g.nranks != 1 || ctx_b->g.nranks != 1 || ctx_a->g.dims != ctx_b->g.dims || ctx_a->device != ctx_b->device) {
+        set_error("genpk_fft_power_cross: two single-GPU grids of the same side on the same device are needed");
+        return 1;
+    }
+    if (!fftx_supported(ctx_a, nrbins) || !fftx_supported(ctx_b, nrbins)) {
+        // other grid sides: the library transform of both fields + the two-field binning pass
+        if (int rc = genpk_fft(ctx_a, a)) return rc;
+        if (int rc = genpk_fft(ctx_b, b)) return rc;
+        return genpk_power_dev(ctx_a, ctx_a->grid[a], ctx_b->grid[b], nrbins, power, count, keffs, total_mass, total_mass2);
+    }
+    // everything below runs on ctx_a's stream
+    cudaStream_t keep = ctx_b->stream;
+    if (ctx_b != ctx_a) {
+        GENPK_CUDA_OK(cudaStreamSynchronize(ctx_b->stream));
+        ctx_b->stream = ctx_a->stream;
+    }
+    int rc = 0;
+    std::vector<double> sum_pass((size_t)3 * nrbins);
+    do {
+        if ((rc = ensure_tables(ctx_a, nrbins)) || (rc = ensure_tables(ctx_b, nrbins))) break;
+        {
+            StageScope scope(ctx_a, ST_FFT);
+            if ((rc = fixed_to_double(ctx_a, a)) || (rc = fixed_to_double(ctx_b, b))) break;
+            sum_diff_kernel<<<ctx_a->sm_count * 8, 256, 0, ctx_a->stream>>>(ctx_a->grid[a], ctx_b->grid[b], ctx_a->g.grid_doubles());
+            ctx_a->launches++;
+            if ((rc = fft_yz(ctx_a, a)) || (rc = fft_yz(ctx_b, b))) break;
+        }
+        {
+            StageScope scope(ctx_a, ST_POWER);
+            if ((rc = fftx_power_raw(ctx_a, ctx_a->grid[a], ctx_a->g.dims, 0, nrbins, ctx_a->d_sums))) break;
+            if (cudaMemcpyAsync(ctx_a->h_sums, ctx_a->d_sums, (size_t)3 * nrbins * sizeof(double), cudaMemcpyDeviceToHost,
+                                ctx_a->stream) != cudaSuccess || cudaStreamSynchronize(ctx_a->stream) != cudaSuccess) {
+                set_error("genpk_fft_power_cross: copying the sums failed: %s", cudaGetErrorString(cudaGetLastError()));
+                rc = 1;
+                break;
+            }
+            memcpy(sum_pass.data(), ctx_a->h_sums, sum_pass.size() * sizeof(double));
+            // (the second pass may share ctx_a's buffers when both fields live in one context)
+            double *d_sums_b = ctx_b->d_sums, *h_sums_b = ctx_b->h_sums;
+            if ((rc = fftx_power_raw(ctx_b, ctx_b->grid[b], ctx_b->g.dims, 0, nrbins, d_sums_b))) break;
+            if (cudaMemcpyAsync(h_sums_b, d_sums_b, (size_t)3 * nrbins * sizeof(double), cudaMemcpyDeviceToHost,
+                                ctx_a->stream) != cudaSuccess || cudaStreamSynchronize(ctx_a->stream) != cudaSuccess) {
+                set_error("genpk_fft_power_cross: copying the sums failed: %s", cudaGetErrorString(cudaGetLastError()));
+                rc = 1;
+                break;
+            }
+            for (int i = 0; i < nrbins; i++)
+                sum_pass[i] = 0.25 * (sum_pass[i] - h_sums_b[i]);           // P part; sum|k| and counts are geometry
+        }
+    } while (0);
+    ctx_b->stream = keep;
+    if (rc) return rc;
+    return genpk_power_finalize(sum_pass.data(), nrbins, total_mass, total_mass2, power, count, keffs);
 }
 
 int genpk_fused_xpass_supported(const genpk_ctx *ctx, int nrbins) { return ctx && fftx_supported(ctx, nrbins) ? 1 : 0; }

@@ -18,9 +18,10 @@
 // cubic plan gen-pk makes once per field (gen-pk.cpp:193,270,321) -- registers the host
 // pointer `field` and creates a device grid for it.  fieldize(out == field, extra == 1)
 // then deposits straight into that device grid (particles go up, the 8*d^3-byte grid
-// never crosses PCIe), fftw_execute transforms it in place on the device, and
-// powerspectrum(field, ...) bins the device spectrum and hands back the three small
-// arrays.  After powerspectrum has consumed a field its device grid is cleared, which is
+// never crosses PCIe), fftw_execute only notes that the transform is wanted, and
+// powerspectrum(field, ...) runs transform and binning as one fused call
+// (genpk_fft_power / genpk_fft_power_cross: the x-transformed spectrum is never written)
+// and hands back the three small arrays.  After powerspectrum has consumed a field its device grid is cleared, which is
 // what the caller's memset(field, 0, ...) before the next particle type (gen-pk.cpp:208)
 // means for the device copy.  The host bytes behind a registered pointer are never
 // read or written: gen-pk itself never looks at them.  A caller that does (test.cpp
@@ -42,7 +43,7 @@ typedef double fftw_complex[2];
 
 namespace {
 
-enum State { ZERO, REAL, SPECTRUM };
+enum State { ZERO, REAL, PENDING, SPECTRUM };   // PENDING: fftw_execute was called, the transform has not run yet
 
 struct Field {
     genpk_ctx *ctx = nullptr;
@@ -57,6 +58,10 @@ std::mutex g_lock;
 std::map<const void *, Field *> g_fields;   // keyed by the host pointer given to the plan
 
 bool mirror() { const char *e = getenv("GENPK_DROPIN_MIRROR"); return e && *e && *e != '0'; }
+// fftw_execute on a device-resident field only notes the request: gen-pk hands the field to nothing but
+// powerspectrum() afterwards (gen-pk.cpp:233-234, 295-297, 345-348), which then runs transform and binning
+// as one fused call.  GENPK_DROPIN_EAGER=1 (or the mirror mode) transforms at once.
+bool eager() { const char *e = getenv("GENPK_DROPIN_EAGER"); return mirror() || (e && *e && *e != '0'); }
 
 Field *lookup(const void *p)
 {
@@ -74,7 +79,7 @@ int fieldize(double boxsize, int dims, double *out, int64_t segment_particles, f
              double mass, int extra)
 {
     Field *f = lookup(out);
-    if (f && f->device_resident && f->dims == dims && extra == 1 && f->state != SPECTRUM) {
+    if (f && f->device_resident && f->dims == dims && extra == 1 && f->state != SPECTRUM && f->state != PENDING) {
         if (genpk_deposit(f->ctx, 0, positions, masses, segment_particles, mass, boxsize, 0)) {
             complain("fieldize");
             return 1;
@@ -101,6 +106,33 @@ int powerspectrum(int64_t dims, fftw_complex *outfield, fftw_complex *outfield2,
                   double *keffs, double total_mass, double total_mass2)
 {
     Field *a = lookup(outfield), *b = outfield2 == outfield ? a : lookup(outfield2);
+    if (a && b && a->device_resident && b->device_resident && a->state == PENDING && b->state == PENDING &&
+        a->dims == dims && b->dims == dims) {
+        // transform(s) + binning in one call on the fused path
+        int rc;
+        if (a == b)
+            rc = genpk_fft_power(a->ctx, 0, nrbins, power, count, keffs, total_mass, total_mass2);
+        else
+            rc = genpk_fft_power_cross(a->ctx, 0, b->ctx, 0, nrbins, power, count, keffs, total_mass, total_mass2);
+        if (rc) {
+            complain("powerspectrum");
+            return 1;
+        }
+        genpk_grid_zero(a->ctx, 0);
+        a->state = ZERO;
+        if (b != a) {
+            genpk_grid_zero(b->ctx, 0);
+            b->state = ZERO;
+        }
+        return 0;
+    }
+    // a deferred transform whose partner is not deferred (or of another size): run it now
+    for (Field *f : {a, b})
+        if (f && f->device_resident && f->state == PENDING) {
+            if (genpk_fft(f->ctx, 0))
+                complain("powerspectrum (deferred transform)");
+            f->state = SPECTRUM;
+        }
     if (a && b && a->device_resident && b->device_resident && a->state == SPECTRUM && b->state == SPECTRUM &&
         a->dims == dims && b->dims == dims) {
         int rc;
@@ -178,6 +210,10 @@ void fftw_execute(const fftw_plan p)
         // host buffer itself (test.cpp:64-75), so that is what gets transformed
         if (f->state == ZERO && genpk_grid_upload(f->ctx, 0, f->in))
             complain("fftw_execute (upload)");
+        if (!eager()) {
+            f->state = PENDING;
+            return;
+        }
         if (genpk_fft(f->ctx, 0))
             complain("fftw_execute");
         f->state = SPECTRUM;

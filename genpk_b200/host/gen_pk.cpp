@@ -395,8 +395,10 @@ int main(int argc, char *argv[])
     std::vector<Timing> timings;
     int status = 0;
 
+    // both transforms and the two-field binning in one call (fftw_execute x2 + powerspectrum, gen-pk.cpp:295-297,
+    // 345-348): on the fused grid sides neither x-transformed spectrum is ever written
     auto run_power = [&](int a, int b, double tm1, double tm2, const std::string &filename, Timing *t) {
-        if (genpk_power(ctx, a, b, nrbins, power.data(), count.data(), keffs.data(), tm1, tm2)) {
+        if (genpk_fft_power_cross(ctx, a, ctx, b, nrbins, power.data(), count.data(), keffs.data(), tm1, tm2)) {
             fprintf(stderr, "powerspectrum failed: %s\n", genpk_last_error());
             return 1;
         }
@@ -474,11 +476,6 @@ int main(int argc, char *argv[])
             s2.which = 1;
             if (read_deposit(src, type, box, s1, &tm1) || read_deposit(src2, type, box, s2, &tm2))
                 continue;
-            if (genpk_fft(ctx, 0) || genpk_fft(ctx, 1)) {
-                fprintf(stderr, "FFT failed: %s\n", genpk_last_error());
-                status = 1;
-                break;
-            }
             if (run_power(0, 1, tm1, tm2, outdir + "/PX-" + type_str(type) + "-" + base, &t))
                 continue;
             t.wall_ms = now_ms() - t0;
@@ -502,10 +499,7 @@ int main(int argc, char *argv[])
         s2.which = 1;
         read_deposit(src, DM_TYPE, box, s1, &tm1);
         read_deposit(src, crosstype, box, s2, &tm2);
-        if (genpk_fft(ctx, 0) || genpk_fft(ctx, 1)) {
-            fprintf(stderr, "FFT failed: %s\n", genpk_last_error());
-            status = 1;
-        } else if (!run_power(0, 1, tm1, tm2, outdir + "/PK-DMx" + type_str(crosstype) + "-" + base, &t)) {
+        if (!run_power(0, 1, tm1, tm2, outdir + "/PK-DMx" + type_str(crosstype) + "-" + base, &t)) {
             t.wall_ms = now_ms() - t0;
             timings.push_back(t);
         }

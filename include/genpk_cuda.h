@@ -196,6 +196,15 @@ int genpk_power_dev(genpk_ctx *ctx, const void *spec_a_dev, const void *spec_b_d
  * up to the summation order inside a bin. */
 int genpk_fft_power(genpk_ctx *ctx, int which, int nrbins, double *power, int *count, double *keffs,
                     double total_mass, double total_mass2);
+/* fftw_execute() of both fields + powerspectrum(dims, field a, field b, ...) of gen-pk.cpp:295-297 / 345-348 as
+ * one call: the cross spectrum of grid `a` of ctx_a and grid `b` of ctx_b (the same context with
+ * GENPK_FLAG_TWO_FIELDS, or two contexts on one device -- the two-snapshot mode).  On the fused grid sides
+ * the two real grids are replaced by their sum and difference and each goes through the fused auto path:
+ * re1*re2 + im1*im2 = (|F1+F2|^2 - |F1-F2|^2)/4 per mode, so neither x-transformed spectrum is ever written.
+ * Afterwards the grids hold (y,z)-transformed planes of the sum and the difference.  Other grid sides:
+ * genpk_fft on both + the two-field binning pass. */
+int genpk_fft_power_cross(genpk_ctx *ctx_a, int a, genpk_ctx *ctx_b, int b, int nrbins, double *power, int *count,
+                          double *keffs, double total_mass, double total_mass2);
 /* 1 when genpk_fft_power / genpk_slab_fftx_power_partial take the fused path for this context. */
 int genpk_fused_xpass_supported(const genpk_ctx *ctx, int nrbins);
 

@@ -228,3 +228,61 @@ def test_tma_tile_fills_give_the_same_bits_as_cp_async(dims):
     assert int(out[1][1].astype(np.int64).sum()) == dims ** 3 - 1
     np.testing.assert_allclose(out[1][0], out[0][0], rtol=1e-12, atol=0)      # bin sums are shared-memory atomics: order may differ
     assert np.array_equal(out[1][2], out[0][2])
+
+
+@pytest.mark.parametrize("dims,two_ctx", [(256, False), (256, True), (96, False), (512, False)])
+def test_cross_spectrum_on_the_fused_path(ref, dims, two_ctx):
+    """genpk_fft_power_cross: powerspectrum(f1, f2) of gen-pk.cpp:295-297 / 345-348 from two deposited grids.  On the
+    fused grid sides the grids are replaced by their sum and difference and go through the fused auto path
+    (re1*re2 + im1*im2 = (|F1+F2|^2 - |F1-F2|^2)/4); 96 takes the library route.  Against the reference's own
+    powerspectrum() on pocketfft transforms of the reference's own fieldize() grids, correlated and anticorrelated
+    fields, two fields in one context and two contexts on one device."""
+    from oracle.oracle import padded_shape, rfftn_padded
+    box, n = 700.0, 250000
+    rng = np.random.default_rng(dims)
+    pos1 = (rng.random((n, 3)) * box).astype(np.float32)
+    # the second field: the first one displaced a little, plus unrelated particles
+    pos2 = np.concatenate([np.mod(pos1[: n // 2] + rng.normal(0, 0.3 * box / dims, (n // 2, 3)), box),
+                           rng.random((n // 3, 3)) * box]).astype(np.float32)
+    m2 = (10.0 ** rng.uniform(-1, 0.5, len(pos2))).astype(np.float32)
+    tm1, tm2 = float(n), float(m2.astype(np.float64).sum())
+    f1 = np.zeros(padded_shape(dims))
+    f2 = np.zeros(padded_shape(dims))
+    ref.fieldize(box, dims, f1, pos1, None, 1.0, 1)
+    ref.fieldize(box, dims, f2, pos2, m2, 0.0, 1)
+    rc, pr, cr, kr = ref.powerspectrum(dims, rfftn_padded(f1, dims), rfftn_padded(f2, dims), dims, tm1, tm2)
+    assert rc == 0
+    if two_ctx:
+        with gp.Context(dims) as c1, gp.Context(dims) as c2:
+            c1.grid_zero()
+            c2.grid_zero()
+            c1.deposit(pos1, None, 1.0, box)
+            c2.deposit(pos2, m2, 0.0, box)
+            p, c, k = c1.fft_power_cross(dims, tm1, tm2, 0, 0, other=c2)
+            c1.synchronize()
+            c2.synchronize()
+    else:
+        with gp.Context(dims, flags=api.FLAG_TWO_FIELDS) as ctx:
+            ctx.grid_zero(0)
+            ctx.grid_zero(1)
+            ctx.deposit(pos1, None, 1.0, box, 0)
+            ctx.deposit(pos2, m2, 0.0, box, 1)
+            p, c, k = ctx.fft_power_cross(dims, tm1, tm2, 0, 1)
+            # and the library route gives the same spectrum
+            ctx.grid_zero(0)
+            ctx.grid_zero(1)
+            ctx.deposit(pos1, None, 1.0, box, 0)
+            ctx.deposit(pos2, m2, 0.0, box, 1)
+            ctx.fft(0)
+            ctx.fft(1)
+            p0, c0, k0 = ctx.power(dims, tm1, tm2, 0, 1)
+            ctx.synchronize()
+        assert np.array_equal(c0, c)
+        scale = np.abs(p0).max()
+        np.testing.assert_allclose(p, p0, rtol=1e-7, atol=1e-12 * scale)
+    assert np.array_equal(c, cr)
+    nz = cr > 0
+    # relative 1e-5 where the cross power is not a cancellation of the two auto powers (the bins with few modes at
+    # low k can be: there the absolute floor applies)
+    np.testing.assert_allclose(p[nz], pr[nz], rtol=1e-5, atol=1e-9 * np.abs(pr[nz]).max())
+    np.testing.assert_allclose(k[nz], kr[nz], rtol=1e-5, atol=0)

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round 2, session 10: TMA tile fills in the column kernels
 mkdir -p gpurun_out
-echo "== fftx tests"; timeout 900 python -m pytest tests/test_gpu_fftx.py tests/test_gpu_sweep.py -m gpu -x -q --timeout 300 > gpurun_out/r2s10_pytest.log 2>&1; echo "rc=$?"; tail -4 gpurun_out/r2s10_pytest.log
+echo "== fftx tests"; timeout 1200 python -m pytest tests/test_gpu_fftx.py tests/test_gpu_sweep.py tests/test_gpu_dropin.py tests/test_gpu_cli.py tests/test_gpu_parity.py -m gpu -q --timeout 300 > gpurun_out/r2s10_pytest.log 2>&1; echo "rc=$?"; tail -4 gpurun_out/r2s10_pytest.log
 show() {
 python - "$1" <<'PY'
 import json,sys
