@@ -227,7 +227,7 @@ def test_tma_tile_fills_give_the_same_bits_as_cp_async(dims):
     assert np.array_equal(out[1][1], out[0][1])
     assert int(out[1][1].astype(np.int64).sum()) == dims ** 3 - 1
     np.testing.assert_allclose(out[1][0], out[0][0], rtol=1e-12, atol=0)      # bin sums are shared-memory atomics: order may differ
-    assert np.array_equal(out[1][2], out[0][2])
+    np.testing.assert_allclose(out[1][2], out[0][2], rtol=1e-12, atol=0)      # (the geometry sums are atomics too)
 
 
 @pytest.mark.parametrize("dims,two_ctx", [(256, False), (256, True), (96, False), (512, False)])
