@@ -85,6 +85,17 @@ SIGNATURES = {
     "genpk_slab_set_peer": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "genpk_slab_scatter_supported": (C.c_int, [C.c_void_p]),
     "genpk_slab_fft_yz_scatter": (C.c_int, [C.c_void_p, C.c_int]),
+    # 4. N GPUs behind one handle
+    "genpk_multi_create": (C.c_void_p, [C.c_int, C.c_int, C.c_void_p, C.c_uint]),
+    "genpk_multi_destroy": (None, [C.c_void_p]),
+    "genpk_multi_ngpus": (C.c_int, [C.c_void_p]),
+    "genpk_multi_rank_ctx": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "genpk_multi_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int64]),
+    "genpk_multi_grid_zero": (C.c_int, [C.c_void_p]),
+    "genpk_multi_deposit": (C.c_int, [C.c_void_p, c_f32p, c_f32p, C.c_int64, C.c_double, C.c_double]),
+    "genpk_multi_fft_power": (C.c_int, [C.c_void_p, C.c_int, c_f64p, c_i32p, c_f64p, C.c_double, C.c_double]),
+    "genpk_multi_pk_from_particles": (C.c_int, [C.c_void_p, c_f32p, c_f32p, C.c_int64, C.c_double, C.c_double, C.c_double,
+                                                C.c_int, c_f64p, c_i32p, c_f64p]),
     "genpk_power_finalize": (C.c_int, [c_f64p, C.c_int, C.c_double, C.c_double, c_f64p, c_i32p, c_f64p]),
     "genpk_bin_thresholds": (C.c_int, [C.c_int, C.c_int, C.c_uint, C.c_void_p]),
     # synthetic particle sets

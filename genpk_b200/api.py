@@ -455,6 +455,81 @@ class Context:
         check(self.lib.genpk_slab_fft_yz_scatter(self.h, which), "genpk_slab_fft_yz_scatter")
 
 
+class MultiContext:
+    """N GPUs of one box behind one handle (genpk_multi_*): single process, slab decomposition in x, host
+    particles in any order.  devices: ordinals of the GPUs (several slabs may share one)."""
+
+    def __init__(self, dims: int, ngpus: int, devices=None, flags: int = 0):
+        self.lib = _lib.load()
+        self.dims, self.ngpus = int(dims), int(ngpus)
+        dev = None
+        if devices is not None:
+            dev = (C.c_int * self.ngpus)(*[int(d) for d in devices])
+        self.h = self.lib.genpk_multi_create(self.dims, self.ngpus, dev, int(flags))
+        if not self.h:
+            raise _lib.GenPKError("genpk_multi_create failed: " + _lib.last_error())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.genpk_multi_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, option: int, value: int):
+        check(self.lib.genpk_multi_set_option(self.h, option, value), "genpk_multi_set_option")
+
+    def grid_zero(self):
+        check(self.lib.genpk_multi_grid_zero(self.h), "genpk_multi_grid_zero")
+
+    def deposit(self, positions, masses=None, mass=1.0, boxsize=1.0):
+        positions = _f32(positions)
+        n = positions.size // 3
+        mp = None
+        if masses is not None:
+            masses = _f32(masses)
+            mp = masses.ctypes.data
+        check(self.lib.genpk_multi_deposit(self.h, positions.ctypes.data, mp, n, float(mass), float(boxsize)),
+              "genpk_multi_deposit")
+
+    def deposit_host_ptr(self, pos_ptr: int, n: int, mass_ptr: int = 0, mass=1.0, boxsize=1.0):
+        check(self.lib.genpk_multi_deposit(self.h, pos_ptr, mass_ptr or None, int(n), float(mass), float(boxsize)),
+              "genpk_multi_deposit")
+
+    def fft_power(self, nrbins=None, total_mass=1.0, total_mass2=None):
+        nrbins = self.dims if nrbins is None else int(nrbins)
+        total_mass2 = total_mass if total_mass2 is None else total_mass2
+        power = np.zeros(nrbins, np.float64)
+        count = np.zeros(nrbins, np.int32)
+        keffs = np.zeros(nrbins, np.float64)
+        check(self.lib.genpk_multi_fft_power(self.h, nrbins, power.ctypes.data, count.ctypes.data, keffs.ctypes.data,
+                                             float(total_mass), float(total_mass2)), "genpk_multi_fft_power")
+        return power, count, keffs
+
+    def pk_from_particles_ptr(self, pos_host_ptr: int, n: int, mass=1.0, boxsize=1.0, total_mass=1.0, nrbins=None):
+        nrbins = self.dims if nrbins is None else int(nrbins)
+        power = np.zeros(nrbins, np.float64)
+        count = np.zeros(nrbins, np.int32)
+        keffs = np.zeros(nrbins, np.float64)
+        check(self.lib.genpk_multi_pk_from_particles(self.h, pos_host_ptr, None, int(n), float(mass), float(boxsize),
+                                                     float(total_mass), nrbins, power.ctypes.data, count.ctypes.data,
+                                                     keffs.ctypes.data), "genpk_multi_pk_from_particles")
+        return power, count, keffs
+
+    def rank_context_handle(self, rank: int) -> int:
+        return self.lib.genpk_multi_rank_ctx(self.h, int(rank))
+
+
 def power_finalize(sums: np.ndarray, nrbins: int, total_mass: float, total_mass2: float):
     """powerspectrum.c:102-108 applied to all-reduced raw sums [3][nrbins]."""
     sums = np.ascontiguousarray(sums, np.float64)

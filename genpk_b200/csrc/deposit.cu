@@ -563,8 +563,10 @@ int fixed_to_double(genpk_ctx *ctx, int which)
         return rc;
     if (!ctx->grid_is_fixed[which])
         return 0;
-    const size_t n = ctx->g.grid_doubles();
-    fixed_to_double_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->grid[which], n,
+    // the owned planes only: after the ghost exchange nothing reads the ghost planes of this rank but its
+    // neighbours, which may still be pulling them (as int64) while this rank goes on to its transform
+    const size_t n = ctx->g.owned_doubles();
+    fixed_to_double_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->grid[which] + ctx->g.owned_offset(), n,
                                                                       ldexp(1.0, -ctx->scale_bits));
     ctx->launches++;
     GENPK_CUDA_OK(cudaGetLastError());

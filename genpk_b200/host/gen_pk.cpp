@@ -10,6 +10,7 @@
 // Extensions (defaults keep the reference's behaviour):
 //   -g DIMS            FFT grid side instead of the rule of gen-pk.cpp:169-172
 //   --fixed            deterministic int64 fixed-point accumulation
+//   --gpus N           x-slab decomposition over N GPUs of this box (one process, genpk_multi_*)
 //   --synthetic K:N[:SEED]  no snapshot: N^3 device-generated particles, K = uniform|lattice|clustered
 //   --json FILE        per-type stage timings
 //   --info             print the header lines and the grid side, then exit (no GPU needed)
@@ -81,7 +82,8 @@ static void help()
             "If -c is specified the code computes the cross-correlation of that particle type with \n"
             "the CDM (type 1) (within the file specified by -i)\n"
             "-s (1,0) Determines whether stars are included in the baryon type.\n"
-            "B200 extensions: -g dims | --fixed | --synthetic kind:n[:seed] | --json file | --info | --dump type file\n");
+            "B200 extensions: -g dims | --fixed | --gpus N | --synthetic kind:n[:seed] | --json file | --info | --dump type file\n"
+            "(HDF5 snapshots are not supported in this build: the image has no HDF5)\n");
 }
 
 // One opened snapshot of either format.
@@ -139,6 +141,7 @@ static bool open_source(const std::string &path, Source *s)
 // Consumer of particle chunks: the GPU deposit, or a file dump.
 struct Sink {
     genpk_ctx *ctx = nullptr;
+    genpk_multi *multi = nullptr;      // --gpus N: the chunk is split over the GPUs and routed on the device
     int which = 0;
     FILE *dump_pos = nullptr, *dump_mass = nullptr;
     int put(const float *pos, const float *masses, int64_t n, double mass, double box)
@@ -149,7 +152,7 @@ struct Sink {
                 fwrite(masses, sizeof(float), (size_t)n, dump_mass);
             return 0;
         }
-        if (genpk_deposit(ctx, which, pos, masses, n, mass, box, 0)) {
+        if (multi ? genpk_multi_deposit(multi, pos, masses, n, mass, box) : genpk_deposit(ctx, which, pos, masses, n, mass, box, 0)) {
             fprintf(stderr, "deposit failed: %s\n", genpk_last_error());
             return 1;
         }
@@ -157,7 +160,7 @@ struct Sink {
     }
     // double-precision positions go up as they are stored and are narrowed on the GPU
     // (the dump mode keeps the host narrowing: it shows what the reference's reader hands over)
-    bool takes_f64() const { return dump_pos == nullptr; }
+    bool takes_f64() const { return dump_pos == nullptr && multi == nullptr; }
     int put64(const double *pos, const float *masses, int64_t n, double mass, double box)
     {
         if (genpk_deposit_f64(ctx, which, pos, masses, n, mass, box, 0)) {
@@ -287,9 +290,11 @@ int main(int argc, char *argv[])
     int crosstype = -1, dump_type = -1;
     bool stars_are_baryons = false, fixed = false, info_only = false;
     int64_t grid_override = 0;
+    int ngpus = 1;
     static const option long_opts[] = {{"fixed", no_argument, nullptr, 1000},    {"synthetic", required_argument, nullptr, 1001},
                                        {"json", required_argument, nullptr, 1002}, {"info", no_argument, nullptr, 1003},
-                                       {"dump", required_argument, nullptr, 1004}, {nullptr, 0, nullptr, 0}};
+                                       {"dump", required_argument, nullptr, 1004}, {"gpus", required_argument, nullptr, 1005},
+                                       {nullptr, 0, nullptr, 0}};
     int c;
     while ((c = getopt_long(argc, argv, "i:j:o:c:s:g:h", long_opts, nullptr)) != -1) {
         switch (c) {
@@ -304,6 +309,7 @@ int main(int argc, char *argv[])
         case 1002: json_path = optarg; break;
         case 1003: info_only = true; break;
         case 1004:
+        case 1005: ngpus = atoi(optarg); break;
             dump_type = atoi(optarg);
             if (optind < argc)
                 dump_path = argv[optind++];
@@ -383,7 +389,20 @@ int main(int argc, char *argv[])
     // ---- GPU context: the field of gen-pk.cpp:176-193 lives in HBM ---------------------------
     const bool two_fields = crosstype >= 0 || !jinfiles.empty();
     unsigned flags = (fixed ? GENPK_FLAG_FIXED_POINT : 0) | (two_fields ? GENPK_FLAG_TWO_FIELDS : 0);
-    genpk_ctx *ctx = genpk_create((int)field_dims, -1, flags);
+    genpk_multi *multi = nullptr;
+    if (ngpus > 1) {
+        // --gpus N: x-slab decomposition over N GPUs of this box, one process (genpk_multi_*)
+        if (two_fields || !synthetic.empty()) {
+            fprintf(stderr, "--gpus applies to the per-type spectra of a snapshot (no -c / -j / --synthetic)\n");
+            return 1;
+        }
+        multi = genpk_multi_create((int)field_dims, ngpus, nullptr, flags);
+        if (!multi) {
+            fprintf(stderr, "Error setting up %d GPUs: %s\n", ngpus, genpk_last_error());
+            return 1;
+        }
+    }
+    genpk_ctx *ctx = multi ? genpk_multi_rank_ctx(multi, 0) : genpk_create((int)field_dims, -1, flags);
     if (!ctx) {
         fprintf(stderr, "Error allocating memory for grid: %s\n", genpk_last_error());
         return 1;
@@ -419,7 +438,10 @@ int main(int argc, char *argv[])
             Timing t;
             t.label = type_str(type);
             const double t0 = now_ms();
-            genpk_grid_zero(ctx, 0);                                               // :208
+            if (multi)
+                genpk_multi_grid_zero(multi);
+            else
+                genpk_grid_zero(ctx, 0);                                           // :208
             double total_mass = 0;
             if (syn_side) {
                 float *dpos = nullptr;
@@ -442,6 +464,7 @@ int main(int argc, char *argv[])
             } else {
                 Sink sink;
                 sink.ctx = ctx;
+                sink.multi = multi;
                 read_deposit(src, type, box, sink, &total_mass);                   // :221,227
                 if (type == BARYON_TYPE && stars_are_baryons)
                     read_deposit(src, STARS_TYPE, box, sink, &total_mass);         // :228-230
@@ -449,8 +472,9 @@ int main(int argc, char *argv[])
             printf("total_mass in type %d = %g\n", type, total_mass);             // :232
             // :233-238: fftw_execute + powerspectrum as one call (the last FFT pass and the binning share a
             // kernel for grid sides 256/512/1024/2048; the library's 3-D plan + binning pass otherwise)
-            if (genpk_fft_power(ctx, 0, nrbins, power.data(), count.data(), keffs.data(), total_mass, total_mass) ||
-                genpk_synchronize(ctx)) {
+            if (multi ? genpk_multi_fft_power(multi, nrbins, power.data(), count.data(), keffs.data(), total_mass, total_mass)
+                      : (genpk_fft_power(ctx, 0, nrbins, power.data(), count.data(), keffs.data(), total_mass, total_mass) ||
+                         genpk_synchronize(ctx))) {
                 fprintf(stderr, "FFT / powerspectrum failed: %s\n", genpk_last_error());
                 status = 1;
                 break;
@@ -519,6 +543,9 @@ int main(int argc, char *argv[])
             fclose(fj);
         }
     }
-    genpk_destroy(ctx);
+    if (multi)
+        genpk_multi_destroy(multi);
+    else
+        genpk_destroy(ctx);
     return status;
 }

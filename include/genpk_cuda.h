@@ -353,6 +353,31 @@ int genpk_slab_set_peer(genpk_ctx *ctx, int rank, const void *ipc_handle /* or N
 int genpk_slab_scatter_supported(const genpk_ctx *ctx);
 int genpk_slab_fft_yz_scatter(genpk_ctx *ctx, int which);
 
+/* ================= 4. N GPUs of one box behind one handle ========================================
+ * The per-particle-type loop of gen-pk.cpp:202-239 on N GPUs, single process, no collective library: the grid is
+ * slab-decomposed in x (dims divisible by ngpus); host particles in ANY order are split N ways, every GPU uploads
+ * its part over its own PCIe link and groups it by owner slab on the device, the runs move with peer copies over
+ * NVLink, each GPU deposits what it owns; the ghost plane is pulled from the neighbour's memory, the FFT transpose
+ * is stored straight into the owners' blocks by the y pass (grid sides 256..2048, dims/ngpus a power of two; peer
+ * copies of packed blocks otherwise), the last FFT pass is fused with the binning, and the per-bin partial sums are
+ * added on the host.  devices: ngpus device ordinals, or NULL for 0..ngpus-1 (wrapping: several slabs may share
+ * a device).  Same results as the single-GPU handle API (counts bit-exact; the fixed-point grid bit for bit). */
+typedef struct genpk_multi genpk_multi;
+genpk_multi *genpk_multi_create(int dims, int ngpus, const int *devices, unsigned flags);
+void genpk_multi_destroy(genpk_multi *m);
+int genpk_multi_ngpus(const genpk_multi *m);
+genpk_ctx *genpk_multi_rank_ctx(genpk_multi *m, int rank);              /* the slab context of one GPU (diagnostics) */
+int genpk_multi_set_option(genpk_multi *m, int option, int64_t value);  /* genpk_set_option on every slab */
+int genpk_multi_grid_zero(genpk_multi *m);                              /* memset(field, 0, ...), gen-pk.cpp:208 */
+/* fieldize() (additive across calls until the next genpk_multi_grid_zero): host arrays, any particle order. */
+int genpk_multi_deposit(genpk_multi *m, const float *positions, const float *masses, int64_t n, double mass, double boxsize);
+/* fftw_execute + powerspectrum (gen-pk.cpp:233-234); power/count/keffs on the host. */
+int genpk_multi_fft_power(genpk_multi *m, int nrbins, double *power, int *count, double *keffs, double total_mass,
+                          double total_mass2);
+/* zero + deposit + fft_power in one call. */
+int genpk_multi_pk_from_particles(genpk_multi *m, const float *positions, const float *masses, int64_t n, double mass,
+                                  double boxsize, double total_mass, int nrbins, double *power, int *count, double *keffs);
+
 /* Normalisation of powerspectrum.c:102-108 applied to reduced raw sums (host). */
 int genpk_power_finalize(const double *sums_host, int nrbins, double total_mass, double total_mass2,
                          double *power, int *count, double *keffs);

@@ -82,6 +82,31 @@ def test_config1_per_type_spectra(tmp_path):
 
 
 @needs_snap
+@pytest.mark.parametrize("gpus", [2, 4])
+def test_config1_on_several_gpus_equals_one_gpu(tmp_path, gpus):
+    """gen-pk --gpus N (x-slabs over N GPUs of the box; with fewer GPUs the slabs share devices): in the
+    deterministic mode the N-GPU grid equals the single-GPU grid bit for bit, so the printed PK- files are the same
+    to the last digit the reference prints (7 significant digits, utils.cpp:17); and they match the golden
+    spectra the reference objects produced."""
+    gold = np.load(os.path.join(GOLD, "test_g2_snap.npz"))
+    one, many = tmp_path / "one", tmp_path / "many"
+    one.mkdir()
+    many.mkdir()
+    gen_pk("-i", SNAP, "-o", str(one), "--fixed")
+    gen_pk("-i", SNAP, "-o", str(many), "--fixed", "--gpus", str(gpus))
+    for t in (0, 1, 4):
+        name = f"PK-{TYPE_STR[t]}-test_g2_snap"
+        a, b = open(one / name).read(), open(many / name).read()
+        ka, pa, ca = read_pk(one / name)
+        kb, pb, cb = read_pk(many / name)
+        assert np.array_equal(ca, cb)
+        np.testing.assert_allclose(pb, pa, rtol=2e-6)            # at most the last printed digit (summation order of the bins)
+        np.testing.assert_allclose(kb, ka, rtol=2e-6)
+        assert_file_matches(many / name, gold[f"power{t}"], gold[f"count{t}"], gold[f"keffs{t}"])
+        assert len(b.splitlines()) == len(a.splitlines()) == 29
+
+
+@needs_snap
 def test_stars_are_baryons_and_cross_modes(tmp_path, orc):
     gold = np.load(os.path.join(GOLD, "test_g2_snap.npz"))
     box, dims = float(gold["box"]), 32
