@@ -193,7 +193,11 @@ class Context:
         self.set_option(OPT_POWER, mode)
 
     def set_scale_bits(self, bits: int):
+        """Fixed-point scale: q = llrint(w * 2^bits); -1 = from the particle masses of the first deposit after a zero."""
         self.set_option(OPT_SCALE_BITS, bits)
+
+    def grid_scale_bits(self, which: int = 0) -> int:
+        return int(self.lib.genpk_grid_scale_bits(self.h, which))
 
     def synchronize(self):
         check(self.lib.genpk_synchronize(self.h), "genpk_synchronize")

@@ -157,6 +157,7 @@ void genpk_destroy(genpk_ctx *ctx)
     if (ctx->d_brick_counts) cudaFree(ctx->d_brick_counts);
     if (ctx->d_errors) cudaFree(ctx->d_errors);
     if (ctx->d_order) cudaFree(ctx->d_order);
+    if (ctx->d_maxmass) cudaFree(ctx->d_maxmass);
     if (ctx->d_za_zdone) cudaFree(ctx->d_za_zdone);
     if (ctx->d_za_def) cudaFree(ctx->d_za_def);
     if (ctx->d_twiddle) cudaFree(ctx->d_twiddle);
@@ -196,7 +197,7 @@ int genpk_set_option(genpk_ctx *ctx, int option, int64_t value)
         ctx->deposit_mode = (int)value;
         return 0;
     case GENPK_OPT_SCALE_BITS:
-        if (value < 0 || value > 62) break;
+        if (value < -1 || value > 62) break;
         ctx->scale_bits = (int)value;
         return 0;
     case GENPK_OPT_LATTICE_N0:
@@ -336,6 +337,7 @@ int genpk_grid_zero(genpk_ctx *ctx, int which)
     // a lattice sweep, which clears the grid ahead of its own front instead (deposit_sweep.cu) and
     // saves one write and one read of the whole grid.
     ctx->zero_pending[which] = true;
+    ctx->grid_scale_latched[which] = false;                      // the next deposit fixes the fixed-point scale anew
     if (!ctx->zero_ahead)
         if (int rc = materialize_zero(ctx, which)) return rc;
     // an all-zero grid is valid in either representation: take it from the context's mode, so a
@@ -699,7 +701,7 @@ int genpk_grid_download(genpk_ctx *ctx, int which, double *host)
     GENPK_CUDA_OK(cudaMemcpyAsync(host, ctx->grid[which], n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     GENPK_CUDA_OK(cudaStreamSynchronize(ctx->stream));
     if (ctx->grid_is_fixed[which]) {                         // exact: (double)q * 2^-S
-        const double inv = ldexp(1.0, -ctx->scale_bits);
+        const double inv = ldexp(1.0, -ctx->grid_scale_bits[which]);
         for (size_t i = 0; i < n; i++) {
             long long q;
             memcpy(&q, &host[i], sizeof(q));
@@ -778,6 +780,11 @@ int genpk_last_order(const genpk_ctx *ctx, int64_t out[7])
     if (!ctx || !out) { set_error("genpk_last_order: bad arguments"); return 1; }
     for (int i = 0; i < 7; i++) out[i] = ctx->last_order[i];
     return 0;
+}
+
+int genpk_grid_scale_bits(const genpk_ctx *ctx, int which)
+{
+    return ctx && which >= 0 && which <= 1 ? ctx->grid_scale_bits[which] : -1;
 }
 
 int genpk_last_sweep(const genpk_ctx *ctx, int64_t out[4])

@@ -84,7 +84,10 @@ struct genpk_ctx {
     size_t l2_bytes = 0;
     cudaStream_t stream = nullptr;
     bool fixed = false;
-    int scale_bits = 40;
+    int scale_bits = 40;              // GENPK_OPT_SCALE_BITS: q = llrint(w * 2^bits); -1 = chosen per grid from the particle masses
+    int grid_scale_bits[2] = {40, 40};   // what each grid's sums are scaled by (latched at the first deposit after a zero)
+    bool grid_scale_latched[2] = {false, false};
+    float *d_maxmass = nullptr;       // scratch of the per-particle-mass maximum
     int deposit_mode = GENPK_DEPOSIT_AUTO;
     int f64_exact = 0;                // genpk_deposit_f64 uses the doubles un-narrowed (a DOUBLE_PRECISION_SNAP reference)
 
@@ -199,6 +202,9 @@ int deposit_device(genpk_ctx *ctx, int which, const float *pos, const float *mas
 int deposit_device_f64(genpk_ctx *ctx, int which, const double *pos, const float *masses, int64_t n, double mass,
                        double boxsize);
 int fixed_to_double(genpk_ctx *ctx, int which);
+// fixed-point mode: the scale of grid `which` (latched at the first deposit after a zero; automatic scales
+// look at the masses of that deposit)
+int latch_scale(genpk_ctx *ctx, int which, const float *masses_dev, int64_t n, double mass);
 // carries out a pending genpk_grid_zero (every reader of the grid calls this first)
 int materialize_zero(genpk_ctx *ctx, int which);
 // binpower.cu

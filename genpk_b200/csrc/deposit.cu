@@ -365,7 +365,9 @@ int deposit_device(genpk_ctx *ctx, int which, const float *pos, const float *mas
     a.n = n;
     a.cmass = mass;
     a.units = g.dims / boxsize;                       // fieldize.cpp:52
-    a.scale = ldexp(1.0, ctx->scale_bits);
+    if (int rc = latch_scale(ctx, which, masses, n, mass))
+        return rc;
+    a.scale = ldexp(1.0, ctx->grid_scale_bits[which]);
     a.dims = g.dims;
     a.fd = g.fd;
     a.x0 = g.x0;
@@ -479,7 +481,9 @@ int deposit_device_f64(genpk_ctx *ctx, int which, const double *pos, const float
     a.n = n;
     a.cmass = mass;
     a.units = g.dims / boxsize;
-    a.scale = ldexp(1.0, ctx->scale_bits);
+    if (int rc = latch_scale(ctx, which, masses, n, mass))
+        return rc;
+    a.scale = ldexp(1.0, ctx->grid_scale_bits[which]);
     a.dims = g.dims;
     a.fd = g.fd;
     a.x0 = g.x0;
@@ -543,6 +547,52 @@ int deposit_plan(genpk_ctx *ctx, const float *pos, int64_t n, double boxsize, De
     return 0;
 }
 
+__global__ void max_mass_kernel(const float *m, int64_t n, float *out)
+{
+    float best = 0.f;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float v = fabsf(m[i]);
+        if (v < 3.0e38f && v > best) best = v;              // (NaN and inf compare false / are skipped)
+    }
+    for (int o = 16; o > 0; o >>= 1)
+        best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if ((threadIdx.x & 31) == 0 && best > 0.f)
+        atomicMax(reinterpret_cast<int *>(out), __float_as_int(best));   // positive floats order like their bits
+}
+
+// The scale of a grid's fixed-point sums is fixed by the first deposit after genpk_grid_zero.  A given number of
+// bits (GENPK_OPT_SCALE_BITS >= 0) is used as it is.  -1: S = 40 - ceil(log2(largest particle mass of this
+// deposit)), so that one contribution keeps ~40 significant bits whatever the mass unit (stellar masses of 1e-8
+// lose everything at S = 40) and 2^23 such particles fit in a cell.
+int latch_scale(genpk_ctx *ctx, int which, const float *masses_dev, int64_t n, double mass)
+{
+    if (!ctx->fixed || ctx->grid_scale_latched[which])
+        return 0;
+    int bits = ctx->scale_bits;
+    if (bits < 0) {
+        double biggest = fabs(mass);
+        if (masses_dev) {
+            if (!ctx->d_maxmass)
+                GENPK_CUDA_OK(cudaMalloc(&ctx->d_maxmass, sizeof(float)));
+            GENPK_CUDA_OK(cudaMemsetAsync(ctx->d_maxmass, 0, sizeof(float), ctx->stream));
+            max_mass_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(masses_dev, n, ctx->d_maxmass);
+            ctx->launches++;
+            float h = 0.f;
+            GENPK_CUDA_OK(cudaMemcpyAsync(&h, ctx->d_maxmass, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+            GENPK_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+            biggest = h;
+        }
+        bits = 40;
+        if (biggest > 0 && biggest < 1e300)
+            bits = 40 - (int)ceil(log2(biggest));
+        bits = bits < 0 ? 0 : (bits > 62 ? 62 : bits);
+    }
+    ctx->grid_scale_bits[which] = bits;
+    ctx->grid_scale_latched[which] = true;
+    return 0;
+}
+
 int materialize_zero(genpk_ctx *ctx, int which)
 {
     if (!ctx->zero_pending[which])
@@ -567,7 +617,7 @@ int fixed_to_double(genpk_ctx *ctx, int which)
     // neighbours, which may still be pulling them (as int64) while this rank goes on to its transform
     const size_t n = ctx->g.owned_doubles();
     fixed_to_double_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->grid[which] + ctx->g.owned_offset(), n,
-                                                                      ldexp(1.0, -ctx->scale_bits));
+                                                                      ldexp(1.0, -ctx->grid_scale_bits[which]));
     ctx->launches++;
     GENPK_CUDA_OK(cudaGetLastError());
     ctx->grid_is_fixed[which] = false;

@@ -10,6 +10,7 @@
 // process); one host thread per GPU drives the uploads so that the PCIe links run side by side.
 //
 // N contexts may share a device (devices = {0, 0, ...}): that is how the path is tested on one GPU.
+#include <math.h>
 #include <string.h>
 
 #include <algorithm>
@@ -56,6 +57,7 @@ struct genpk_multi {
     std::vector<genpk::RankBuf> buf;
     std::vector<cudaEvent_t> ev_a, ev_b, ev_c;          // per rank: deposit done / scatter (or pack) done / spectrum consumed
     bool scatter = false;
+    bool scale_latched = false;                         // fixed point: one scale for all slabs, fixed by the first deposit after a zero
     std::vector<std::vector<int64_t>> counts;           // [source][dest] of the current call
     std::string thread_error;
 };
@@ -288,6 +290,7 @@ int genpk_multi_grid_zero(genpk_multi *m)
         if (use_device(m, r)) { set_error("cudaSetDevice failed"); return 1; }
         if (int rc = genpk_grid_zero(m->ctx[r], 0)) return rc;
     }
+    m->scale_latched = false;
     return 0;
 }
 
@@ -304,6 +307,30 @@ int genpk_multi_deposit(genpk_multi *m, const float *positions, const float *mas
         return genpk_deposit(m->ctx[0], 0, positions, masses, n, mass, boxsize, 0);
     }
     const int P = m->n;
+    if (m->ctx[0]->fixed && !m->scale_latched) {
+        // every slab must scale its fixed-point sums alike (ghost planes are added as integers): the automatic
+        // scale (GENPK_OPT_SCALE_BITS = -1) is taken here, from all the masses of this first deposit
+        int bits = m->ctx[0]->scale_bits;
+        if (bits < 0) {
+            double biggest = fabs(mass);
+            if (masses) {
+                float h = 0.f;
+                for (int64_t i = 0; i < n; i++) {
+                    const float v = fabsf(masses[i]);
+                    if (v < 3.0e38f && v > h) h = v;
+                }
+                biggest = h;
+            }
+            bits = 40;
+            if (biggest > 0 && biggest < 1e300) bits = 40 - (int)ceil(log2(biggest));
+            bits = bits < 0 ? 0 : (bits > 62 ? 62 : bits);
+        }
+        for (int r = 0; r < P; r++) {
+            m->ctx[r]->grid_scale_bits[0] = bits;
+            m->ctx[r]->grid_scale_latched[0] = true;
+        }
+        m->scale_latched = true;
+    }
     // ---- phase 1: upload + route, every rank its own share ----
     int rc = for_each_rank_parallel(m, [&](int q) -> int {
         const int64_t lo = n * q / P, cnt = n * (q + 1) / P - lo;

@@ -309,11 +309,11 @@ int main(int argc, char *argv[])
         case 1002: json_path = optarg; break;
         case 1003: info_only = true; break;
         case 1004:
-        case 1005: ngpus = atoi(optarg); break;
             dump_type = atoi(optarg);
             if (optind < argc)
                 dump_path = argv[optind++];
             break;
+        case 1005: ngpus = atoi(optarg); break;
         case 'h':
         default:
             help();
@@ -406,6 +406,13 @@ int main(int argc, char *argv[])
     if (!ctx) {
         fprintf(stderr, "Error allocating memory for grid: %s\n", genpk_last_error());
         return 1;
+    }
+    if (fixed) {
+        // --fixed: the scale of the integer sums follows the mass unit of each particle type
+        if (multi ? genpk_multi_set_option(multi, GENPK_OPT_SCALE_BITS, -1) : genpk_set_option(ctx, GENPK_OPT_SCALE_BITS, -1)) {
+            fprintf(stderr, "%s\n", genpk_last_error());
+            return 1;
+        }
     }
     std::vector<double> power(nrbins), keffs(nrbins);
     std::vector<int> count(nrbins);

@@ -53,7 +53,11 @@ extern "C" {
 #define GENPK_DEPOSIT_SWEEP      5     /* lattice-ordered input: persistent warps sweep the lattice along x; merges in
                                           registers (y), shared memory (x) and one shuffle (z); clears the grid ahead
                                           of its own front when it follows genpk_grid_zero (AUTO's choice for lattices) */
-#define GENPK_OPT_SCALE_BITS     2     /* fixed-point mode: q = llrint(w * 2^bits), default 40 */
+#define GENPK_OPT_SCALE_BITS     2     /* fixed-point mode: q = llrint(w * 2^bits), default 40.  -1: chosen per grid at the first
+                                          deposit after genpk_grid_zero as 40 - ceil(log2(largest particle mass of that
+                                          deposit)), which keeps ~40 significant bits per contribution whatever the mass
+                                          unit and 2^23 such particles per cell of headroom (single-GPU contexts; a
+                                          multi-GPU handle picks one scale for all slabs).  genpk_grid_scale_bits() tells */
 /* Lattice hint for GENPK_DEPOSIT_MARCH / AUTO: particle p sits near lattice site
  * (ix,iy,iz) with p = (ix*N1 + iy)*N0 + iz.  0 = let the order probe find it.  Only
  * ever a performance hint: results do not depend on it. */
@@ -241,6 +245,7 @@ int genpk_stage_reset(genpk_ctx *ctx);
 int64_t genpk_launch_count(const genpk_ctx *ctx);
 /* Verdict of the last order probe of this context: {coherent, lattice, n0, n1,
  * score_z, score_y, score_x} (scores per mille; diagnostics for the bench line). */
+int genpk_grid_scale_bits(const genpk_ctx *ctx, int which);    /* the scale the grid's fixed-point sums carry now */
 int genpk_last_order(const genpk_ctx *ctx, int64_t out[7]);
 /* The last sweep deposit of this context: {rows per column, columns (= warps), zero ahead used (0/1),
  * zero-ahead window in planes}. */

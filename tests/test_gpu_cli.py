@@ -102,6 +102,8 @@ def test_config1_on_several_gpus_equals_one_gpu(tmp_path, gpus):
         assert np.array_equal(ca, cb)
         np.testing.assert_allclose(pb, pa, rtol=2e-6)            # at most the last printed digit (summation order of the bins)
         np.testing.assert_allclose(kb, ka, rtol=2e-6)
+        # the scale of the integer sums follows each type's mass unit (stellar masses of 1e-8 here), so every type
+        # matches the reference's double-precision spectra
         assert_file_matches(many / name, gold[f"power{t}"], gold[f"count{t}"], gold[f"keffs{t}"])
         assert len(b.splitlines()) == len(a.splitlines()) == 29
 

@@ -463,3 +463,33 @@ def test_double_precision_positions_used_as_they_are(port, var_mass):
             ctx.synchronize()
         tol = 1e-6 * np.abs(ref).reshape(-1) + 1e-6 * np.abs(ref).mean()
         assert np.all(np.abs(g - ref.reshape(-1)) <= tol)
+
+
+def test_automatic_fixed_point_scale_follows_the_mass_unit(port):
+    """GENPK_OPT_SCALE_BITS = -1: particle masses of 1e-8 (the stars of test_g2_snap) lose five digits at the default
+    2^40; the automatic scale is 40 - ceil(log2(max mass)), latched at the first deposit after a zero."""
+    rng = np.random.default_rng(4)
+    dims, box, n = 32, 100.0, 5000
+    pos = (rng.random((n, 3)) * box).astype(np.float32)
+    masses = (10.0 ** rng.uniform(-9, -7.2, n)).astype(np.float32)
+    want = np.zeros(padded_shape(dims))
+    port.fieldize(box, dims, want, pos, masses, 0.0, 1)
+    with gp.Context(dims, flags=api.FLAG_FIXED_POINT) as ctx:
+        ctx.grid_zero()
+        ctx.deposit(pos, masses, 0.0, box)
+        coarse = ctx.grid_download()
+        assert ctx.grid_scale_bits() == 40
+        ctx.set_scale_bits(-1)
+        ctx.grid_zero()
+        ctx.deposit(pos, masses, 0.0, box)
+        fine = ctx.grid_download()
+        bits = ctx.grid_scale_bits()
+        q = ctx.grid_download_fixed()
+        ctx.synchronize()
+    assert bits == 40 - int(np.ceil(np.log2(float(masses.max()))))
+    ref_q = np.zeros(padded_shape(dims), np.int64)
+    port.fieldize_fixed(box, dims, ref_q, pos, masses, 0.0, 1, bits)
+    assert np.array_equal(q, ref_q.reshape(-1))                   # the same rule, bit for bit, at the chosen scale
+    tol = 1e-9 * np.abs(want).max()
+    assert np.abs(fine - want.reshape(-1)).max() <= tol
+    assert np.abs(coarse - want.reshape(-1)).max() > 100 * tol    # (what the default scale does to such masses)
