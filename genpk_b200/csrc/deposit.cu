@@ -586,7 +586,7 @@ int latch_scale(genpk_ctx *ctx, int which, const float *masses_dev, int64_t n, d
         bits = 40;
         if (biggest > 0 && biggest < 1e300)
             bits = 40 - (int)ceil(log2(biggest));
-        bits = bits < 0 ? 0 : (bits > 62 ? 62 : bits);
+        bits = bits < 0 ? 0 : (bits > 400 ? 400 : bits);       // only the double 2^bits has to exist
     }
     ctx->grid_scale_bits[which] = bits;
     ctx->grid_scale_latched[which] = true;

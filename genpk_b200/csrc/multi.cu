@@ -323,7 +323,7 @@ int genpk_multi_deposit(genpk_multi *m, const float *positions, const float *mas
             }
             bits = 40;
             if (biggest > 0 && biggest < 1e300) bits = 40 - (int)ceil(log2(biggest));
-            bits = bits < 0 ? 0 : (bits > 62 ? 62 : bits);
+            bits = bits < 0 ? 0 : (bits > 400 ? 400 : bits);
         }
         for (int r = 0; r < P; r++) {
             m->ctx[r]->grid_scale_bits[0] = bits;
