@@ -76,6 +76,8 @@ def parse_args():
                     help="cuFFT x pass + bin_power_kernel instead of the fused x-pass/binning kernel")
     ap.add_argument("--xpass-narrow-tile", action="store_true", help="fused x pass with 4096-mode tiles at 1024 (two CTAs per SM)")
     ap.add_argument("--fft-yz-batch", type=int, default=-1, help="x planes per 2-D cuFFT call (0 = all, -1 = library default)")
+    ap.add_argument("--zero-after", action="store_true", help="fused x pass: store zeros behind the tiles it reads (the next "
+                    "step's genpk_grid_zero is free; measured slower than the memset, profiles/r02)")
     ap.add_argument("--no-tma", action="store_true", help="column kernels: per-thread cp.async tile fills instead of TMA bulk tensor copies")
     ap.add_argument("--no-own-ypass", action="store_true", help="cuFFT's 2-D (y,z) plan instead of cuFFT z + own y pass")
     ap.add_argument("--no-ghost-pull", action="store_true", help="multi-GPU: NCCL send/recv of the ghost planes instead of peer loads")
@@ -411,6 +413,8 @@ def run_ours(args):
         ctx.set_option(api.OPT_OWN_YPASS, 0)
     if args.no_tma:
         ctx.set_option(api.OPT_TMA, 0)
+    if args.zero_after:
+        ctx.set_option(api.OPT_ZERO_AFTER_POWER, 1)
     if args.fft_yz_batch >= 0:
         ctx.set_option(api.OPT_FFT_YZ_BATCH, args.fft_yz_batch)
     fused = ctx.fused_xpass_supported(nrbins)

@@ -25,6 +25,7 @@ OPT_SWEEP, OPT_SWEEP_RY, OPT_ZERO_AHEAD, OPT_ZA_WINDOW, OPT_ZA_SLACK, OPT_ZA_DEF
 OPT_ZA_ZERO_CTAS, OPT_SWEEP_COUPLE, OPT_SWEEP_COUPLE_STEP, OPT_SWEEP_POLL_WEAK, OPT_SWEEP_RX = 17, 18, 19, 20, 21
 OPT_F64_POSITIONS = 23
 OPT_TMA = 24
+OPT_ZERO_AFTER_POWER = 25
 POWER_CACHED, POWER_FUSED = 0, 1
 DEPOSIT_AUTO, DEPOSIT_DIRECT, DEPOSIT_SORTED, DEPOSIT_TILED, DEPOSIT_MARCH, DEPOSIT_SWEEP = 0, 1, 2, 3, 4, 5
 STAGE_DEPOSIT, STAGE_FFT, STAGE_POWER, STAGE_SORT, STAGE_ZERO = 0, 1, 2, 3, 4

@@ -232,6 +232,10 @@ int genpk_set_option(genpk_ctx *ctx, int option, int64_t value)
         if (value != 0 && value != 1) break;
         ctx->use_tma = (int)value;
         return 0;
+    case GENPK_OPT_ZERO_AFTER_POWER:
+        if (value != 0 && value != 1) break;
+        ctx->zero_after_power = (int)value;
+        return 0;
     case GENPK_OPT_FUSED_XPASS:
         if (value < 0 || value > 2) break;
         ctx->fused_xpass = (int)value;
@@ -336,7 +340,8 @@ int genpk_grid_zero(genpk_ctx *ctx, int which)
     // Lazy: the memset runs when the grid is next read or deposited into -- unless that next use is
     // a lattice sweep, which clears the grid ahead of its own front instead (deposit_sweep.cu) and
     // saves one write and one read of the whole grid.
-    ctx->zero_pending[which] = true;
+    // A grid that the fused x pass has just left all zeros (GENPK_OPT_ZERO_AFTER_POWER) needs nothing.
+    ctx->zero_pending[which] = !ctx->grid_clean[which];
     ctx->grid_scale_latched[which] = false;                      // the next deposit fixes the fixed-point scale anew
     if (!ctx->zero_ahead)
         if (int rc = materialize_zero(ctx, which)) return rc;
@@ -582,7 +587,9 @@ int genpk_fft_power(genpk_ctx *ctx, int which, int nrbins, double *power, int *c
     }
     {
         StageScope scope(ctx, ST_POWER);
-        if (int rc = fftx_power_raw(ctx, ctx->grid[which], ctx->g.dims, 0, nrbins, ctx->d_sums)) return rc;
+        bool zeroed = ctx->zero_after_power != 0;
+        if (int rc = fftx_power_raw(ctx, ctx->grid[which], ctx->g.dims, 0, nrbins, ctx->d_sums, 0, &zeroed)) return rc;
+        ctx->grid_clean[which] = zeroed;                   // (nothing of the grid's content survives this call either way)
     }
     GENPK_CUDA_OK(cudaMemcpyAsync(ctx->h_sums, ctx->d_sums, (size_t)3 * nrbins * sizeof(double), cudaMemcpyDeviceToHost,
                                   ctx->stream));
@@ -645,7 +652,9 @@ int genpk_fft_power_cross(genpk_ctx *ctx_a, int a, genpk_ctx *ctx_b, int b, int 
         }
         {
             StageScope scope(ctx_a, ST_POWER);
-            if ((rc = fftx_power_raw(ctx_a, ctx_a->grid[a], ctx_a->g.dims, 0, nrbins, ctx_a->d_sums))) break;
+            bool zeroed = ctx_a->zero_after_power != 0;
+            if ((rc = fftx_power_raw(ctx_a, ctx_a->grid[a], ctx_a->g.dims, 0, nrbins, ctx_a->d_sums, 0, &zeroed))) break;
+            ctx_a->grid_clean[a] = zeroed;
             if (cudaMemcpyAsync(ctx_a->h_sums, ctx_a->d_sums, (size_t)3 * nrbins * sizeof(double), cudaMemcpyDeviceToHost,
                                 ctx_a->stream) != cudaSuccess || cudaStreamSynchronize(ctx_a->stream) != cudaSuccess) {
                 set_error("genpk_fft_power_cross: copying the sums failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -655,7 +664,9 @@ int genpk_fft_power_cross(genpk_ctx *ctx_a, int a, genpk_ctx *ctx_b, int b, int 
             memcpy(sum_pass.data(), ctx_a->h_sums, sum_pass.size() * sizeof(double));
             // (the second pass may share ctx_a's buffers when both fields live in one context)
             double *d_sums_b = ctx_b->d_sums, *h_sums_b = ctx_b->h_sums;
-            if ((rc = fftx_power_raw(ctx_b, ctx_b->grid[b], ctx_b->g.dims, 0, nrbins, d_sums_b))) break;
+            zeroed = ctx_b->zero_after_power != 0;
+            if ((rc = fftx_power_raw(ctx_b, ctx_b->grid[b], ctx_b->g.dims, 0, nrbins, d_sums_b, 0, &zeroed))) break;
+            ctx_b->grid_clean[b] = zeroed;
             if (cudaMemcpyAsync(h_sums_b, d_sums_b, (size_t)3 * nrbins * sizeof(double), cudaMemcpyDeviceToHost,
                                 ctx_a->stream) != cudaSuccess || cudaStreamSynchronize(ctx_a->stream) != cudaSuccess) {
                 set_error("genpk_fft_power_cross: copying the sums failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -731,6 +742,7 @@ int genpk_grid_upload(genpk_ctx *ctx, int which, const double *host)
 {
     if (!check_which(ctx, which, "genpk_grid_upload")) return 1;
     ctx->zero_pending[which] = false;                            // overwritten as a whole
+    ctx->grid_clean[which] = false;
     GENPK_CUDA_OK(cudaMemcpyAsync(ctx->grid[which], host, ctx->g.grid_doubles() * sizeof(double), cudaMemcpyHostToDevice,
                                   ctx->stream));
     GENPK_CUDA_OK(cudaStreamSynchronize(ctx->stream));

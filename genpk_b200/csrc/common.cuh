@@ -154,6 +154,8 @@ struct genpk_ctx {
     int za_zdone_cap = 0;
     unsigned *d_za_def = nullptr;
     size_t za_def_cap = 0;
+    bool grid_clean[2] = {false, false};      // the grid is all zeros already (the fused x pass left it so): genpk_grid_zero has nothing to do
+    int zero_after_power = 0;                 // GENPK_OPT_ZERO_AFTER_POWER
     bool zero_pending[2] = {false, false};    // genpk_grid_zero has been asked for but not yet carried out
     long long last_sweep[4] = {0, 0, 0, 0};   // rows per column, columns, zero ahead used, window (diagnostics)
 
@@ -214,7 +216,9 @@ int power_raw(genpk_ctx *ctx, const double *spec_a, const double *spec_b, int n_
 int power_seed_sums(genpk_ctx *ctx, int n_outer, int outer0, int n_mid, int mid0, int nrbins, double *sums_dev);
 // fftx_power.cu
 bool fftx_supported(const genpk_ctx *ctx, int nrbins);
-int fftx_power_raw(genpk_ctx *ctx, const double *spec_yz, int n_mid, int mid0, int nrbins, double *sums_dev, int row_pitch = 0);
+// zero_after (in: wanted, out: done): the block is overwritten with zeros as it is read
+int fftx_power_raw(genpk_ctx *ctx, const double *spec_yz, int n_mid, int mid0, int nrbins, double *sums_dev, int row_pitch = 0,
+                   bool *zero_after = nullptr);
 int recv_row_pitch(const genpk_ctx *ctx);
 bool fft_cols_supported(const genpk_ctx *ctx);
 int fft_cols_y(genpk_ctx *ctx, double *spec, int n_planes);

@@ -365,6 +365,7 @@ int deposit_device(genpk_ctx *ctx, int which, const float *pos, const float *mas
     a.n = n;
     a.cmass = mass;
     a.units = g.dims / boxsize;                       // fieldize.cpp:52
+    ctx->grid_clean[which] = false;
     if (int rc = latch_scale(ctx, which, masses, n, mass))
         return rc;
     a.scale = ldexp(1.0, ctx->grid_scale_bits[which]);
@@ -481,6 +482,7 @@ int deposit_device_f64(genpk_ctx *ctx, int which, const double *pos, const float
     a.n = n;
     a.cmass = mass;
     a.units = g.dims / boxsize;
+    ctx->grid_clean[which] = false;
     if (int rc = latch_scale(ctx, which, masses, n, mass))
         return rc;
     a.scale = ldexp(1.0, ctx->grid_scale_bits[which]);
@@ -595,6 +597,7 @@ int latch_scale(genpk_ctx *ctx, int which, const float *masses_dev, int64_t n, d
 
 int materialize_zero(genpk_ctx *ctx, int which)
 {
+    ctx->grid_clean[which] = false;                          // whoever asks is about to read or write the grid
     if (!ctx->zero_pending[which])
         return 0;
     ctx->zero_pending[which] = false;

@@ -32,7 +32,9 @@ using namespace fftx;
 
 struct FftxArgs {
     alignas(64) CUtensorMap tmap;   // the spectrum as {2*nc doubles, n_mid rows, dims slabs}; box {2C, 1, 256}
+    alignas(64) CUtensorMap zmap;   // the same tensor with box {2C, 1, ZERO_BOX_ROWS}: zero stores behind the read
     int use_tma;
+    int zero_after;           // 1: every tile is overwritten with zeros once it has been read (the grid is clear for the next deposit)
     const double2 *spec;      // [dims][n_mid][nc]
     const double2 *tw;        // exp(-2 pi i t / dims), t < dims
     int dims, nc, n_mid, mid0;
@@ -53,6 +55,7 @@ struct FftxArgs {
 // N/256 bulk tensor copies (a box dimension holds at most 256); nobody computes an address, nobody waits on
 // a copy it issued itself.  Columns past the end of a row are zero-filled by the copy engine.
 constexpr int TMA_BOX_ROWS = 256;
+constexpr int ZERO_BOX_ROWS = 32;   // rows of a zero store: the source is a C*16*32-byte block of zeros (4 KB at C = 8)
 
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
 {
@@ -76,6 +79,15 @@ __device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *m
                  ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2),
                    "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
 }
+
+// shared memory box -> the box at (c0, c1, c2) of the tensor; completion is tracked by the bulk async-group
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, int c0, int c1, int c2, const void *smem_src)
+{
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+                 ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"((unsigned)__cvta_generic_to_shared(smem_src)) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 typedef CUresult (*tmap_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -226,9 +238,15 @@ __global__ void __launch_bounds__(PL::THREADS, PL::TILE == 4096 ? 2 : 1) fftx_po
         }
     };
     __shared__ __align__(8) unsigned long long tile_bar;
+    __shared__ __align__(128) double zero_block[ZERO_BOX_ROWS * C * 2];
     if (A.use_tma && tid == 0) {
         mbar_init(&tile_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (A.zero_after) {
+        for (int i = tid; i < ZERO_BOX_ROWS * C * 2; i += CTA_THREADS)
+            zero_block[i] = 0.0;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the copy engine reads what these stores wrote
     }
     __syncthreads();
     unsigned tile_parity = 0;
@@ -271,6 +289,16 @@ __global__ void __launch_bounds__(PL::THREADS, PL::TILE == 4096 ? 2 : 1) fftx_po
         if (A.use_tma) {
             mbar_wait(&tile_bar, tile_parity);
             tile_parity ^= 1u;
+            // the tile has left global memory: zeros go back in its place, N/32 bulk stores of 32 rows spread over
+            // the warps (each from the same block of zeros; nothing ever waits on them before the kernel ends)
+            if (A.zero_after && (tid & 31) == 0) {
+                constexpr int PER_WARP = N / ZERO_BOX_ROWS / (CTA_THREADS / 32);
+                static_assert(PER_WARP >= 1 && PER_WARP * (CTA_THREADS / 32) * ZERO_BOX_ROWS == N, "zero stores do not tile the column");
+#pragma unroll
+                for (int j = 0; j < PER_WARP; j++)
+                    tma_store_3d(&A.zmap, 2 * g * C, m, ((tid >> 5) * PER_WARP + j) * ZERO_BOX_ROWS, zero_block);
+                tma_store_commit();
+            }
         } else {
             cp_async_wait_all();
         }
@@ -301,6 +329,8 @@ __global__ void __launch_bounds__(PL::THREADS, PL::TILE == 4096 ? 2 : 1) fftx_po
             bin_walk<PL>(P, t, c, kj, kz, A.dims / 2, sW, sT, A.nrbins, A.half_bpu, hist, A.hists);
     }
     cp_async_wait_all();
+    if (A.zero_after && (tid & 31) == 0)
+        tma_store_wait_all();
     __syncthreads();
     for (int i = tid; i < A.nrbins; i += CTA_THREADS) {
         double sum = 0.0;
@@ -466,10 +496,13 @@ static size_t fftx_smem_bytes_h(const genpk_ctx *ctx, int nrbins, int hists)
     return tile * 16 + tile * 8 + (size_t)nrbins * 8 * hists + (size_t)(nrbins + 1) * 4 + (size_t)(dims / 2 + 1) * 4 + 16;
 }
 
+// the kernel's static shared memory: the block of zeros behind the zero stores, the tile barrier
+constexpr size_t FFTX_STATIC_SMEM = ZERO_BOX_ROWS * 8 * 16 + 128;
+
 // two histograms (even / odd tile columns) when they fit
 static int fftx_hists(const genpk_ctx *ctx, int nrbins)
 {
-    return fftx_smem_bytes_h(ctx, nrbins, 2) <= (size_t)ctx->smem_optin ? 2 : 1;
+    return fftx_smem_bytes_h(ctx, nrbins, 2) + FFTX_STATIC_SMEM <= (size_t)ctx->smem_optin ? 2 : 1;
 }
 
 size_t fftx_smem_bytes(const genpk_ctx *ctx, int nrbins) { return fftx_smem_bytes_h(ctx, nrbins, fftx_hists(ctx, nrbins)); }
@@ -481,7 +514,7 @@ bool fftx_supported(const genpk_ctx *ctx, int nrbins)
         return false;
     if (d != 256 && d != 512 && d != 1024 && d != 2048)
         return false;
-    return nrbins >= 1 && fftx_smem_bytes(ctx, nrbins) <= (size_t)ctx->smem_optin;
+    return nrbins >= 1 && fftx_smem_bytes(ctx, nrbins) + FFTX_STATIC_SMEM <= (size_t)ctx->smem_optin;
 }
 
 // Rows of the library-owned transposed block start on 128-byte boundaries (nc = dims/2+1 is odd:
@@ -539,8 +572,11 @@ template <class PL> static int launch_fftx(genpk_ctx *ctx, const FftxArgs &A, si
 // P sums of the block [dims][n_mid][nc] of a (y,z)-transformed spectrum whose first mid
 // row is global ky index mid0, with the x transform done on the fly.  sums_dev: 3*nrbins
 // doubles (P from this pass, K and N from the cached geometry pass).
-int fftx_power_raw(genpk_ctx *ctx, const double *spec_yz, int n_mid, int mid0, int nrbins, double *sums_dev, int row_pitch)
+int fftx_power_raw(genpk_ctx *ctx, const double *spec_yz, int n_mid, int mid0, int nrbins, double *sums_dev, int row_pitch,
+                   bool *zero_after)
 {
+    const bool want_zero = zero_after && *zero_after;
+    if (zero_after) *zero_after = false;
     if (!fftx_supported(ctx, nrbins)) {
         set_error("fused x pass: unsupported grid side %d / nrbins %d", ctx->g.dims, nrbins);
         return 1;
@@ -565,6 +601,7 @@ int fftx_power_raw(genpk_ctx *ctx, const double *spec_yz, int n_mid, int mid0, i
     A.hists = fftx_hists(ctx, nrbins);
     const size_t smem = fftx_smem_bytes(ctx, nrbins);
     A.use_tma = 0;
+    A.zero_after = 0;
     int tma_rc = 0;
     auto tiles = [&](int C) {
         A.groups = (A.nc + C - 1) / C;
@@ -573,6 +610,13 @@ int fftx_power_raw(genpk_ctx *ctx, const double *spec_yz, int n_mid, int mid0, i
             // {2*nc doubles} x {n_mid rows, row_pitch apart} x {dims values of x, x_stride apart}; box {2C, 1, 256}
             tma_rc = make_tile_map(&A.tmap, spec_yz, A.nc, n_mid, A.row_pitch, A.dims, A.x_stride, C, 1, TMA_BOX_ROWS);
             A.use_tma = tma_rc == 0 ? 1 : 0;
+            // zero stores behind the read (the caller's block is every row of the tensor: rows of 2*nc doubles,
+            // which in the padded grid layout is the whole row)
+            if (A.use_tma && want_zero &&
+                make_tile_map(&A.zmap, spec_yz, A.nc, n_mid, A.row_pitch, A.dims, A.x_stride, C, 1, ZERO_BOX_ROWS) == 0) {
+                A.zero_after = 1;
+                *zero_after = true;
+            }
         }
     };
     // (tests/fftx_emu.cpp instantiates the same plans on the host)

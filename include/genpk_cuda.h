@@ -105,6 +105,11 @@ extern "C" {
 
 #define GENPK_OPT_TMA           24     /* 1 (default): the column kernels (y pass, fused x pass) fill their shared-memory tiles with
                                           TMA bulk tensor copies behind an mbarrier; 0: per-thread cp.async (measurements) */
+#define GENPK_OPT_ZERO_AFTER_POWER 25  /* 1: the fused x pass of genpk_fft_power / genpk_fft_power_cross / genpk_pk_from_particles
+                                          overwrites every tile of the grid with zeros (TMA bulk tensor stores) right after reading it,
+                                          and the genpk_grid_zero that follows has nothing left to do; needs GENPK_OPT_TMA.  0 (default):
+                                          measured at 1024^3 the stores cost the x pass 1.45 ms and the memset they replace 1.19 ms
+                                          (profiles/r02/README.md).  The grid content after those calls is unspecified either way. */
 
 typedef struct genpk_ctx genpk_ctx;
 #define GENPK_MAX_PEERS 16

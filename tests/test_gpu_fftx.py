@@ -286,3 +286,44 @@ def test_cross_spectrum_on_the_fused_path(ref, dims, two_ctx):
     # low k can be: there the absolute floor applies)
     np.testing.assert_allclose(p[nz], pr[nz], rtol=1e-5, atol=1e-9 * np.abs(pr[nz]).max())
     np.testing.assert_allclose(k[nz], kr[nz], rtol=1e-5, atol=0)
+
+
+@pytest.mark.parametrize("dims,fixed", [(256, False), (512, False), (1024, False), (2048, False), (256, True)])
+def test_fused_x_pass_leaves_the_grid_zero(dims, fixed):
+    """GENPK_OPT_ZERO_AFTER_POWER: the fused x pass stores zeros behind every tile it reads (TMA bulk stores), the
+    genpk_grid_zero that follows is free, and a second P(k) of the same particles is the first one bit for bit."""
+    box, n = 300.0, 200000
+    pos, masses = _particles(n, box, dims + 7, True)
+    tm = float(masses.astype(np.float64).sum())
+    with gp.Context(dims, flags=api.FLAG_FIXED_POINT if fixed else 0) as ctx:
+        ctx.set_option(api.OPT_DEPOSIT, api.DEPOSIT_SORTED)          # (an order-independent deposit: the two passes can be compared bit for bit)
+        ctx.set_option(api.OPT_ZERO_AFTER_POWER, 1)
+        ctx.grid_zero()
+        ctx.deposit(pos, masses, 1.0, box)
+        p1, c1, k1 = ctx.fft_power(dims, tm, tm)
+        ctx.stage_reset()
+        ctx.grid_zero()
+        ctx.deposit(pos, masses, 1.0, box)
+        assert ctx.stage_total_ms(api.STAGE_ZERO)[1] == 0, "a memset ran although the x pass had cleared the grid"
+        p2, c2, k2 = ctx.fft_power(dims, tm, tm)
+        ctx.grid_zero()
+        if dims <= 1024:                                             # (a 2048^3 grid is 69 GB of host memory)
+            left = ctx.grid_download()
+            assert not left.any(), "the x pass left something behind"
+            del left
+        # switched off: the memset is back and nothing else changes
+        ctx.set_option(api.OPT_ZERO_AFTER_POWER, 0)
+        ctx.deposit(pos, masses, 1.0, box)
+        p3, c3, k3 = ctx.fft_power(dims, tm, tm)
+        ctx.stage_reset()
+        ctx.grid_zero()
+        ctx.deposit(pos, masses, 1.0, box)
+        assert ctx.stage_total_ms(api.STAGE_ZERO)[1] == 1
+        p4, c4, k4 = ctx.fft_power(dims, tm, tm)
+        ctx.synchronize()
+    for p, c, k in ((p2, c2, k2), (p3, c3, k3), (p4, c4, k4)):
+        assert np.array_equal(c, c1)
+        if fixed:
+            assert np.array_equal(p, p1) and np.array_equal(k, k1)
+        else:
+            np.testing.assert_allclose(p[c1 > 0], p1[c1 > 0], rtol=1e-10, atol=0)   # fp64 atomics: order of additions
