@@ -76,6 +76,9 @@ def parse_args():
                     help="cuFFT x pass + bin_power_kernel instead of the fused x-pass/binning kernel")
     ap.add_argument("--xpass-narrow-tile", action="store_true", help="fused x pass with 4096-mode tiles at 1024 (two CTAs per SM)")
     ap.add_argument("--fft-yz-batch", type=int, default=-1, help="x planes per 2-D cuFFT call (0 = all, -1 = library default)")
+    ap.add_argument("--fused-zy", type=int, default=-1, help="GENPK_OPT_FUSED_ZY: 1 one persistent kernel for the z and y passes "
+                    "(default), 2 with 8192-mode tiles, 0 library z pass + column kernel")
+    ap.add_argument("--zy-lag", type=int, default=0, help="GENPK_OPT_ZY_LAG: planes between a plane's z tiles and its y tiles")
     ap.add_argument("--zero-after", action="store_true", help="fused x pass: store zeros behind the tiles it reads (the next "
                     "step's genpk_grid_zero is free; measured slower than the memset, profiles/r02)")
     ap.add_argument("--no-tma", action="store_true", help="column kernels: per-thread cp.async tile fills instead of TMA bulk tensor copies")
@@ -415,6 +418,10 @@ def run_ours(args):
         ctx.set_option(api.OPT_TMA, 0)
     if args.zero_after:
         ctx.set_option(api.OPT_ZERO_AFTER_POWER, 1)
+    if args.fused_zy >= 0:
+        ctx.set_option(api.OPT_FUSED_ZY, args.fused_zy)
+    if args.zy_lag > 0:
+        ctx.set_option(api.OPT_ZY_LAG, args.zy_lag)
     if args.fft_yz_batch >= 0:
         ctx.set_option(api.OPT_FFT_YZ_BATCH, args.fft_yz_batch)
     fused = ctx.fused_xpass_supported(nrbins)
@@ -489,6 +496,7 @@ def run_ours(args):
     if pipe is not None:
         pipe.profile = True
     launches0 = ctx.launch_count()
+    libcalls0 = ctx.library_calls()
     sampler = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -502,6 +510,7 @@ def run_ours(args):
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     launches = ctx.launch_count() - launches0
+    libcalls = ctx.library_calls() - libcalls0
     ms_step = ms_total / args.steps
     value = n_total / (ms_step * 1e-3) / 1e6
     stage_ms = {}
@@ -591,7 +600,7 @@ def run_ours(args):
         "binning_gcells_per_s": (dims ** 2 * (dims // 2 + 1) / (stage_ms["binning"] * 1e-3) / 1e9)
         if stage_ms["binning"] else None,
         "roofline": roofline, "roofline_all": roof,
-        "gpu_launches": int(launches), "cufft_execs_per_step": 1 if (world == 1 or fused) else 2,
+        "gpu_launches": int(launches), "cufft_execs_per_step": libcalls / args.steps,
         "e2e": e2e, "clocks": clocks, "self_check": self_check,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

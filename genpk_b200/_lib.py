@@ -57,6 +57,7 @@ SIGNATURES = {
     "genpk_stage_total_ms": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int64)]),
     "genpk_stage_reset": (C.c_int, [C.c_void_p]),
     "genpk_launch_count": (C.c_int64, [C.c_void_p]),
+    "genpk_library_calls": (C.c_int64, [C.c_void_p]),
     "genpk_grid_scale_bits": (C.c_int, [C.c_void_p, C.c_int]),
     "genpk_last_order": (C.c_int, [C.c_void_p, c_i64p]),
     "genpk_last_sweep": (C.c_int, [C.c_void_p, c_i64p]),

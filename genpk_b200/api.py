@@ -26,6 +26,8 @@ OPT_ZA_ZERO_CTAS, OPT_SWEEP_COUPLE, OPT_SWEEP_COUPLE_STEP, OPT_SWEEP_POLL_WEAK, 
 OPT_F64_POSITIONS = 23
 OPT_TMA = 24
 OPT_ZERO_AFTER_POWER = 25
+OPT_FUSED_ZY = 26
+OPT_ZY_LAG = 27
 POWER_CACHED, POWER_FUSED = 0, 1
 DEPOSIT_AUTO, DEPOSIT_DIRECT, DEPOSIT_SORTED, DEPOSIT_TILED, DEPOSIT_MARCH, DEPOSIT_SWEEP = 0, 1, 2, 3, 4, 5
 STAGE_DEPOSIT, STAGE_FFT, STAGE_POWER, STAGE_SORT, STAGE_ZERO = 0, 1, 2, 3, 4
@@ -219,6 +221,10 @@ class Context:
 
     def launch_count(self) -> int:
         return self.lib.genpk_launch_count(self.h)
+
+    def library_calls(self) -> int:
+        """cuFFT executions so far (the default paths at 256..2048 make none)."""
+        return self.lib.genpk_library_calls(self.h)
 
     # the per-type step of gen-pk.cpp:208-234
     def grid_zero(self, which: int = 0):

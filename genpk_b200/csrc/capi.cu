@@ -74,6 +74,7 @@ static genpk_ctx *create_common(int dims, int device, int nranks, int rank, unsi
         ctx->l2_bytes = (size_t)prop.l2CacheSize;
         ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
     }
+    cudaDeviceGetAttribute(&ctx->coop_launch, cudaDevAttrCooperativeLaunch, dev);
     SlabGeom &g = ctx->g;
     g.dims = dims;
     g.nranks = nranks;
@@ -159,6 +160,7 @@ void genpk_destroy(genpk_ctx *ctx)
     if (ctx->d_order) cudaFree(ctx->d_order);
     if (ctx->d_maxmass) cudaFree(ctx->d_maxmass);
     if (ctx->d_za_zdone) cudaFree(ctx->d_za_zdone);
+    if (ctx->d_rows_done) cudaFree(ctx->d_rows_done);
     if (ctx->d_za_def) cudaFree(ctx->d_za_def);
     if (ctx->d_twiddle) cudaFree(ctx->d_twiddle);
     for (int r = 0; r < GENPK_MAX_PEERS; r++)
@@ -231,6 +233,14 @@ int genpk_set_option(genpk_ctx *ctx, int option, int64_t value)
     case GENPK_OPT_TMA:
         if (value != 0 && value != 1) break;
         ctx->use_tma = (int)value;
+        return 0;
+    case GENPK_OPT_FUSED_ZY:
+        if (value < 0 || value > 2) break;
+        ctx->fused_zy = (int)value;
+        return 0;
+    case GENPK_OPT_ZY_LAG:
+        if (value < 1 || value > 64) break;
+        ctx->zy_lag = (int)value;
         return 0;
     case GENPK_OPT_ZERO_AFTER_POWER:
         if (value != 0 && value != 1) break;
@@ -582,7 +592,6 @@ int genpk_fft_power(genpk_ctx *ctx, int which, int nrbins, double *power, int *c
     if (int rc = ensure_tables(ctx, nrbins)) return rc;
     {
         StageScope scope(ctx, ST_FFT);
-        if (int rc = fixed_to_double(ctx, which)) return rc;
         if (int rc = fft_yz(ctx, which)) return rc;
     }
     {
@@ -786,6 +795,7 @@ int genpk_stage_reset(genpk_ctx *ctx)
 }
 
 int64_t genpk_launch_count(const genpk_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int64_t genpk_library_calls(const genpk_ctx *ctx) { return ctx ? ctx->lib_calls : 0; }
 
 int genpk_last_order(const genpk_ctx *ctx, int64_t out[7])
 {
@@ -909,7 +919,6 @@ int genpk_slab_fft_yz(genpk_ctx *ctx, int which)
     if (!check_which(ctx, which, "genpk_slab_fft_yz")) return 1;
     {
         StageScope scope(ctx, ST_FFT);
-        if (int rc = fixed_to_double(ctx, which)) return rc;
         if (int rc = fft_yz(ctx, which)) return rc;
     }
     return 0;
@@ -1028,6 +1037,12 @@ int genpk_slab_fft_yz_scatter(genpk_ctx *ctx, int which)
     if (!genpk_slab_scatter_supported(ctx)) { set_error("genpk_slab_fft_yz_scatter: unsupported geometry"); return 1; }
     {
         StageScope scope(ctx, ST_FFT);
+        if (fft_zy_supported(ctx)) {
+            if (int rc = materialize_zero(ctx, which)) return rc;
+            const bool fixed = ctx->grid_is_fixed[which];
+            ctx->grid_is_fixed[which] = false;
+            return fft_zy(ctx, ctx->grid[which] + ctx->g.owned_offset(), ctx->g.nx, true, fixed, ctx->grid_scale_bits[which]);
+        }
         if (int rc = fixed_to_double(ctx, which)) return rc;
         if (int rc = fft_z_rows(ctx, which)) return rc;
         if (int rc = fft_cols_y_scatter(ctx, ctx->grid[which] + ctx->g.owned_offset(), ctx->g.nx)) return rc;

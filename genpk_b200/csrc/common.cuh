@@ -162,6 +162,11 @@ struct genpk_ctx {
     // fused x pass (fftx_power.cu)
     int fused_xpass = 1;                      // 0: always cuFFT's x pass + bin_power_kernel
     int use_tma = 1;                          // column kernels fill their tiles with bulk tensor copies (0: per-thread cp.async)
+    int fused_zy = 1;                         // GENPK_OPT_FUSED_ZY: z rows and y columns in one persistent kernel (fft_zy.cu); 2: 8192-mode tiles at 1024
+    int zy_lag = 2;                           // planes between a plane's z tiles and its y tiles in that kernel's schedule
+    int coop_launch = 0;                      // cudaDevAttrCooperativeLaunch
+    int *d_rows_done = nullptr;
+    int rows_done_n = 0;
     int own_ypass = 1;                        // 1: (y,z) transform = cuFFT 1-D r2c along z + fft_cols_kernel along y
     int smem_optin = 0;                       // opt-in shared memory per CTA of this device
     double *d_twiddle = nullptr;              // exp(-2 pi i t/dims), t < dims
@@ -223,6 +228,8 @@ int recv_row_pitch(const genpk_ctx *ctx);
 bool fft_cols_supported(const genpk_ctx *ctx);
 int fft_cols_y(genpk_ctx *ctx, double *spec, int n_planes);
 int fft_cols_y_scatter(genpk_ctx *ctx, double *spec, int n_planes);
+bool fft_zy_supported(const genpk_ctx *ctx);
+int fft_zy(genpk_ctx *ctx, double *planes, int n_planes, bool scatter, bool from_fixed, int scale_bits);
 int fft_z_rows(genpk_ctx *ctx, int which);
 // fft.cu
 int fft_3d(genpk_ctx *ctx, int which);

@@ -82,6 +82,14 @@ static int fft_yz_own(genpk_ctx *ctx, int which)
 int fft_yz(genpk_ctx *ctx, int which)
 {
     const SlabGeom &g = ctx->g;
+    if (int rc = materialize_zero(ctx, which)) return rc;
+    if (fft_zy_supported(ctx)) {
+        // one persistent kernel, int64 fixed-point sums converted as the rows are read (fft_zy.cu)
+        const bool fixed = ctx->grid_is_fixed[which];
+        ctx->grid_is_fixed[which] = false;
+        return fft_zy(ctx, ctx->grid[which] + g.owned_offset(), g.nx, false, fixed, ctx->grid_scale_bits[which]);
+    }
+    if (int rc = fixed_to_double(ctx, which)) return rc;
     if (fft_cols_supported(ctx))
         return fft_yz_own(ctx, which);
     // Planes per cuFFT call.  One call over the whole slab runs the z pass over every plane

@@ -64,6 +64,51 @@ template <int K> FX_HD cd mulw16(cd a)
     return r;
 }
 
+FX_HD cd csqr(cd a)
+{
+    cd r;
+    r.x = (a.x + a.y) * (a.x - a.y);
+    r.y = 2.0 * (a.x * a.y);
+    return r;
+}
+
+// v[k] *= w^k for k = 1 .. R-1, the powers built from w by squaring and multiplying (w, w^2, w^4, w^8 and the
+// products along the binary digits of k: at most five roundings deep).  One table lookup per butterfly unit instead
+// of R-1: the scattered 16-byte twiddle loads were a third of the kernels' load/store wavefronts and most of their
+// scoreboard stalls (profiles/r02/README.md).
+template <int R> FX_HD void mul_twiddle_powers(cd *v, cd w)
+{
+    static_assert(R == 2 || R == 4 || R == 8 || R == 16, "radix");
+    v[1] = cmul(v[1], w);
+    if (R >= 4) {
+        const cd w2 = csqr(w);
+        v[2] = cmul(v[2], w2);
+        v[3] = cmul(v[3], cmul(w2, w));
+        if (R >= 8) {
+            const cd w4 = csqr(w2);
+            v[4] = cmul(v[4], w4);
+            v[5] = cmul(v[5], cmul(w4, w));
+            const cd w6 = cmul(w4, w2);
+            v[6] = cmul(v[6], w6);
+            v[7] = cmul(v[7], cmul(w6, w));
+            if (R >= 16) {
+                const cd w8 = csqr(w4);
+                v[8] = cmul(v[8], w8);
+                v[9] = cmul(v[9], cmul(w8, w));
+                const cd w10 = cmul(w8, w2);
+                v[10] = cmul(v[10], w10);
+                v[11] = cmul(v[11], cmul(w10, w));
+                const cd w12 = cmul(w8, w4);
+                v[12] = cmul(v[12], w12);
+                v[13] = cmul(v[13], cmul(w12, w));
+                const cd w14 = cmul(w8, w6);
+                v[14] = cmul(v[14], w14);
+                v[15] = cmul(v[15], cmul(w14, w));
+            }
+        }
+    }
+}
+
 template <int R> struct Dft;
 template <int R, int K> struct Comb {
     static FX_HD void run(cd *v, const cd *e, const cd *o)
@@ -99,6 +144,25 @@ template <> struct Dft<1> {
 
 constexpr int EPT = 16;               // elements per thread
 
+// Real-input transform of length 2*Nc from the length-Nc complex transform Z of z[n] = x[2n] + i x[2n+1]:
+// with a = Z[k], b = Z[Nc - k] (b = a for k = 0) and w = exp(-2 pi i k / (2 Nc)),
+//   E = (a + conj b) / 2,  O = -i (a - conj b) / 2      (transforms of the even and the odd samples)
+//   X[k] = E + w O,        X[Nc - k] = conj(E - w O)
+// k = 0 gives X[0] = Re a + Im a and X[Nc] = Re a - Im a; the self-paired k = Nc/2 gives conj(a).
+FX_HD void rfft_pair(cd a, cd b, cd w, cd *xk, cd *xm)
+{
+    cd e, o;
+    e.x = 0.5 * (a.x + b.x);
+    e.y = 0.5 * (a.y - b.y);
+    o.x = 0.5 * (a.y + b.y);
+    o.y = -0.5 * (a.x - b.x);
+    const cd wo = cmul(o, w);
+    xk->x = e.x + wo.x;
+    xk->y = e.y + wo.y;
+    xm->x = e.x - wo.x;
+    xm->y = -(e.y - wo.y);
+}
+
 // TILE: modes per tile (16 B each).  4096 -> 256 threads and ~110 KB of shared memory per
 // CTA, two CTAs per SM whose barriers and exchanges interleave; 8192 -> one CTA of 512.
 template <int R1_, int R2_, int R3_, int TILE_> struct Plan {
@@ -123,10 +187,7 @@ template <int R1_, int R2_, int R3_, int TILE_> struct Plan {
 #pragma unroll
         for (int u = 0; u < EPT / R1; u++) {
             Dft<R1>::run(v + u * R1);
-            const int n2 = t + T * u;
-#pragma unroll
-            for (int k1 = 1; k1 < R1; k1++)
-                v[u * R1 + k1] = cmul(v[u * R1 + k1], tw[n2 * k1]);
+            mul_twiddle_powers<R1>(v + u * R1, tw[t + T * u]);                 // W_N^(n2*k1), n2 = t + T*u
         }
     }
     // exchange 1: y[k1][n2]
@@ -141,10 +202,7 @@ template <int R1_, int R2_, int R3_, int TILE_> struct Plan {
 #pragma unroll
         for (int u = 0; u < EPT / R2; u++) {
             Dft<R2>::run(w + u * R2);
-            const int m2 = (t + T * u) % R3;
-#pragma unroll
-            for (int q1 = 1; q1 < R2; q1++)
-                w[u * R2 + q1] = cmul(w[u * R2 + q1], tw[R1 * m2 * q1]);
+            mul_twiddle_powers<R2>(w + u * R2, tw[R1 * ((t + T * u) % R3)]);   // W_N^(R1*m2*q1), m2 = (t + T*u) % R3
         }
     }
     // exchange 2: z[k1][q1][m2], m2 swizzled by q1 so that both the writers (lanes along
@@ -185,6 +243,8 @@ template <int R1_, int R2_, int R3_, int TILE_> struct Plan {
     static FX_HD int ex2_r_part(int i) { return ((T * (i / R3)) / R2) * M1 + ((i % R3) & ~3); }
     static FX_HD int out_k_base(int t) { return t / R2 + R1 * (t % R2); }
     static FX_HD int out_k_part(int i) { return (T / R2) * (i / R3) + R1 * R2 * (i % R3); }
+    // out_k >= N/2 depends on the register index alone: out_k_base(t) + (T/R2)*(i/R3) < R1*R2 (checked in fftx_emu.cpp)
+    static FX_HD bool out_k_upper(int i) { return (i % R3) >= R3 / 2; }
     // where |X[k]|^2 waits for the bin walk (bank swizzle only; any bijection is correct)
     static FX_HD int slot(int k) { return k ^ (((k >> 3) ^ (R1 == 8 ? 0 : (k >> LOG_R1))) & 3); }
 };

@@ -21,10 +21,7 @@
 //
 // Supported: dims in {256, 512, 1024, 2048}, auto spectra.  Everything else (other sizes,
 // cross spectra, callers that want the transformed grid) keeps the cuFFT + bin_power path.
-#include <cuda.h>
-
-#include "common.cuh"
-#include "fftx_core.cuh"
+#include "fft_tiles.cuh"
 
 namespace genpk {
 
@@ -50,50 +47,12 @@ struct FftxArgs {
     int hists;                // histograms per CTA (1 or 2: even / odd tile columns)
 };
 
-// ---- TMA: a tile [N][C] of complex doubles is N rows of C*16 contiguous bytes at a fixed pitch -- a 3-D tensor
-// box {C complex, rows, 1}.  One elected thread arms an mbarrier with the tile's byte count and issues
-// N/256 bulk tensor copies (a box dimension holds at most 256); nobody computes an address, nobody waits on
-// a copy it issued itself.  Columns past the end of a row are zero-filled by the copy engine.
-constexpr int TMA_BOX_ROWS = 256;
-constexpr int ZERO_BOX_ROWS = 32;   // rows of a zero store: the source is a C*16*32-byte block of zeros (4 KB at C = 8)
-
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
-{
-    const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
-    asm volatile("{\n\t.reg .pred p;\n\tWAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE;\n\tbra WAIT;\n\tDONE:\n\t}"
-                 ::"r"(addr), "r"(parity) : "memory");
-}
-// box at coordinates (c0 doubles along a row, c1, c2) of the 3-D tensor behind `map` -> shared memory
-__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *map, int c0, int c1, int c2, unsigned long long *bar)
-{
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                 ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2),
-                   "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
-}
-
-// shared memory box -> the box at (c0, c1, c2) of the tensor; completion is tracked by the bulk async-group
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, int c0, int c1, int c2, const void *smem_src)
-{
-    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
-                 ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"((unsigned)__cvta_generic_to_shared(smem_src)) : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-
 typedef CUresult (*tmap_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (the library does not link libcuda)
+bool tma_available();
 static tmap_encode_fn tmap_encoder()
 {
     static tmap_encode_fn fn = nullptr;
@@ -106,9 +65,11 @@ static tmap_encode_fn tmap_encoder()
     return fn;
 }
 
+bool tma_available() { return tmap_encoder() != nullptr; }
+
 // Tensor of complex doubles viewed as doubles: inner extent 2*cols (valid columns), `rows` rows `row_pitch` complex
 // apart, `slabs` slabs `slab_pitch` complex apart; box = {2*C doubles, box_rows, box_slabs}.
-static int make_tile_map(CUtensorMap *map, const void *base, long long cols, long long rows, long long row_pitch, long long slabs,
+int make_tile_map(CUtensorMap *map, const void *base, long long cols, long long rows, long long row_pitch, long long slabs,
                          long long slab_pitch, int C, int box_rows, int box_slabs)
 {
     tmap_encode_fn enc = tmap_encoder();
@@ -128,69 +89,6 @@ static int make_tile_map(CUtensorMap *map, const void *base, long long cols, lon
         return 1;
     }
     return 0;
-}
-
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
-{
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
-
-// The staged tile has been read into registers: wait for those shared-memory loads to
-// complete (an empty asm that consumes the registers) so that the slots may be refilled.
-__device__ __forceinline__ void loads_landed(const fftx::cd *v)
-{
-#pragma unroll
-    for (int i = 0; i < fftx::EPT; i += 4)
-        asm volatile("" ::"d"(v[i].x), "d"(v[i].y), "d"(v[i + 1].x), "d"(v[i + 1].y), "d"(v[i + 2].x), "d"(v[i + 2].y),
-                     "d"(v[i + 3].x), "d"(v[i + 3].y)
-                     : "memory");
-}
-
-// One exchange through the half-size buffer E ([N/2][C] complex): the lower half of the index
-// space first, then the upper half.  WI(i) / RI(i): element index of register i on the writing /
-// reading side.  Which half an index falls in is a compile-time property of i (the predicates
-// fold away), except on the pass-2 side of a plan whose thread owns a single radix-R2 unit
-// (2048): there all 16 indices of a thread lie in the same half (W_UNI / R_UNI).
-template <int N, int C, bool W_UNI, bool R_UNI, class WI, class RI>
-__device__ __forceinline__ void exchange(fftx::cd *E, const fftx::cd *src, fftx::cd *dst, int c, WI wi, RI ri)
-{
-#pragma unroll
-    for (int half = 0; half < 2; half++) {
-        if (half)
-            __syncthreads();                           // the lower half has been read
-        if (W_UNI) {
-            if ((wi(0) >= N / 2) == (half == 1)) {
-#pragma unroll
-                for (int i = 0; i < fftx::EPT; i++)
-                    E[(wi(i) - half * (N / 2)) * C + c] = src[i];
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < fftx::EPT; i++) {
-                const int idx = wi(i);
-                if ((idx >= N / 2) == (half == 1))
-                    E[(idx - half * (N / 2)) * C + c] = src[i];
-            }
-        }
-        __syncthreads();
-        if (R_UNI) {
-            if ((ri(0) >= N / 2) == (half == 1)) {
-#pragma unroll
-                for (int i = 0; i < fftx::EPT; i++)
-                    dst[i] = E[(ri(i) - half * (N / 2)) * C + c];
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < fftx::EPT; i++) {
-                const int idx = ri(i);
-                if ((idx >= N / 2) == (half == 1))
-                    dst[i] = E[(idx - half * (N / 2)) * C + c];
-            }
-        }
-    }
 }
 
 template <class PL>
@@ -522,14 +420,15 @@ bool fftx_supported(const genpk_ctx *ctx, int nrbins)
 // would split into two NVLink packets).
 int recv_row_pitch(const genpk_ctx *ctx) { return (ctx->g.nc + 7) / 8 * 8; }
 
-static int ensure_twiddles(genpk_ctx *ctx)
+int ensure_twiddles(genpk_ctx *ctx)
 {
     const int d = ctx->g.dims;
     if (ctx->d_twiddle && ctx->twiddle_n == d)
         return 0;
     if (ctx->d_twiddle) cudaFree(ctx->d_twiddle);
     ctx->d_twiddle = nullptr;
-    std::vector<double> h(2 * (size_t)d);
+    // [0, d): exp(-2 pi i t / d);  [d, d + d/2): exp(-2 pi i t / (d/2)), the table of the half-length row transforms
+    std::vector<double> h(2 * (size_t)(d + d / 2));
     const long double tau = 6.283185307179586476925286766559005768L;
     for (int t = 0; t < d; t++) {
         // exact values on the axes and diagonals, long-double libm elsewhere
@@ -542,6 +441,10 @@ static int ensure_twiddles(genpk_ctx *ctx)
         }
         h[2 * (size_t)t] = cr;
         h[2 * (size_t)t + 1] = -si;
+    }
+    for (int t = 0; t < d / 2; t++) {
+        h[2 * (size_t)(d + t)] = h[2 * (size_t)(2 * t)];
+        h[2 * (size_t)(d + t) + 1] = h[2 * (size_t)(2 * t) + 1];
     }
     GENPK_CUDA_OK(cudaMalloc(&ctx->d_twiddle, h.size() * sizeof(double)));
     GENPK_CUDA_OK(cudaMemcpyAsync(ctx->d_twiddle, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));

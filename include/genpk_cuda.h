@@ -105,6 +105,11 @@ extern "C" {
 
 #define GENPK_OPT_TMA           24     /* 1 (default): the column kernels (y pass, fused x pass) fill their shared-memory tiles with
                                           TMA bulk tensor copies behind an mbarrier; 0: per-thread cp.async (measurements) */
+#define GENPK_OPT_FUSED_ZY      26     /* 1 (default): the (y,z) part of the transform is ONE persistent kernel -- r2c along z on the rows
+                                          of a plane, then the column pass along y two planes behind, out of L2 (fft_zy.cu): the grid
+                                          is read once and written once.  2: the same with 8192-mode tiles at 1024.  0: the library's
+                                          batched 1-D r2c along z followed by fft_cols_kernel along y (two trips through HBM). */
+#define GENPK_OPT_ZY_LAG        27     /* planes between a plane's z tiles and its y tiles in that kernel's schedule (default 2) */
 #define GENPK_OPT_ZERO_AFTER_POWER 25  /* 1: the fused x pass of genpk_fft_power / genpk_fft_power_cross / genpk_pk_from_particles
                                           overwrites every tile of the grid with zeros (TMA bulk tensor stores) right after reading it,
                                           and the genpk_grid_zero that follows has nothing left to do; needs GENPK_OPT_TMA.  0 (default):
@@ -247,7 +252,8 @@ int genpk_stage_ms(genpk_ctx *ctx, int stage, float *ms);
  * the host; this call does. */
 int genpk_stage_total_ms(genpk_ctx *ctx, int stage, float *total_ms, int64_t *records);
 int genpk_stage_reset(genpk_ctx *ctx);
-int64_t genpk_launch_count(const genpk_ctx *ctx);
+int64_t genpk_launch_count(const genpk_ctx *ctx);     /* kernels of this library launched so far */
+int64_t genpk_library_calls(const genpk_ctx *ctx);    /* cuFFT executions so far (0 on the default 256..2048 paths) */
 /* Verdict of the last order probe of this context: {coherent, lattice, n0, n1,
  * score_z, score_y, score_x} (scores per mille; diagnostics for the bench line). */
 int genpk_grid_scale_bits(const genpk_ctx *ctx, int which);    /* the scale the grid's fixed-point sums carry now */

@@ -136,3 +136,116 @@ extern "C" int fftx_emu_tile(int n, const double *tile_in, const double *twiddle
     }
     return -1;
 }
+
+// ---- one z tile of fft_zy_kernel (genpk_b200/csrc/fft_zy.cu): CZ padded rows of dims reals, each transformed in place
+// into dims/2 + 1 complex values -- the half-length complex FFT of z[n] = x[2n] + i x[2n+1] with the plan's register
+// passes, a third exchange that hands every thread eight pairs (Z[k], Z[dims/2 - k]), rfft_pair, rows written in place.
+template <class PLZ> static int emu_rows(double *rows, const double *twiddle, const double *twiddle_half)
+{
+    constexpr int NZ = PLZ::N, CZ = PLZ::C, TZ = PLZ::T, ROW = NZ + 1;
+    cd *R0 = reinterpret_cast<cd *>(rows);                         // [CZ][ROW]
+    const cd *tw = reinterpret_cast<const cd *>(twiddle), *twh = reinterpret_cast<const cd *>(twiddle_half);
+    std::vector<cd> regs((size_t)PLZ::THREADS * EPT), regs2((size_t)PLZ::THREADS * EPT), E((size_t)NZ * CZ);
+    for (int tid = 0; tid < PLZ::THREADS; tid++) {
+        const int c = tid % CZ, t = tid / CZ;
+        cd *v = &regs[(size_t)tid * EPT];
+        for (int i = 0; i < EPT; i++)
+            v[i] = R0[(size_t)c * ROW + PLZ::load_n(t, i)];
+        PLZ::pass1(v, t, twh);
+    }
+    for (int tid = 0; tid < PLZ::THREADS; tid++)
+        for (int i = 0; i < EPT; i++)
+            E[(size_t)(tid / CZ + PLZ::ex1_w_part(i)) * CZ + tid % CZ] = regs[(size_t)tid * EPT + i];
+    for (int tid = 0; tid < PLZ::THREADS; tid++) {
+        const int c = tid % CZ, t = tid / CZ;
+        cd *w = &regs2[(size_t)tid * EPT];
+        for (int i = 0; i < EPT; i++)
+            w[i] = E[(size_t)(PLZ::ex1_r_base(t) + PLZ::ex1_r_part(i)) * CZ + c];
+        PLZ::pass2(w, t, twh);
+    }
+    for (int tid = 0; tid < PLZ::THREADS; tid++)
+        for (int i = 0; i < EPT; i++)
+            E[(size_t)(PLZ::ex2_w_base(tid / CZ, (i % PLZ::R2) & 3) + PLZ::ex2_w_part(i)) * CZ + tid % CZ] = regs2[(size_t)tid * EPT + i];
+    for (int tid = 0; tid < PLZ::THREADS; tid++) {
+        const int c = tid % CZ, t = tid / CZ;
+        cd *v = &regs[(size_t)tid * EPT];
+        for (int i = 0; i < EPT; i++)
+            v[i] = E[(size_t)(PLZ::ex2_r_base(t, (i % PLZ::R3) & 3) + PLZ::ex2_r_part(i)) * CZ + c];
+        PLZ::pass3(v);
+    }
+    // third exchange, through a half-size buffer: lower half of the index space (all the k = t + TZ*j), then the upper
+    // half (the partners NZ - k and Z[NZ/2]); which half a register goes to must follow from its index alone
+    constexpr int PAIRS = NZ / 2 / TZ;
+    if (PAIRS * 2 != EPT) return 20;
+    std::vector<cd> H((size_t)(NZ / 2) * CZ), pa((size_t)PLZ::THREADS * PAIRS), pb((size_t)PLZ::THREADS * PAIRS), mid(CZ);
+    for (int half = 0; half < 2; half++) {
+        for (int tid = 0; tid < PLZ::THREADS; tid++)
+            for (int i = 0; i < EPT; i++) {
+                const int k = PLZ::out_k_base(tid / CZ) + PLZ::out_k_part(i);
+                if (PLZ::out_k_upper(i) != (k >= NZ / 2)) return 21;
+                if (PLZ::out_k_upper(i) == (half == 1))
+                    H[(size_t)(k - half * (NZ / 2)) * CZ + tid % CZ] = regs[(size_t)tid * EPT + i];
+            }
+        for (int tid = 0; tid < PLZ::THREADS; tid++) {
+            const int c = tid % CZ, t = tid / CZ;
+            for (int j = 0; j < PAIRS; j++) {
+                const int k = t + TZ * j;
+                if (!half)
+                    pa[(size_t)tid * PAIRS + j] = H[(size_t)k * CZ + c];
+                else
+                    pb[(size_t)tid * PAIRS + j] = k == 0 ? pa[(size_t)tid * PAIRS] : H[(size_t)(NZ / 2 - k) * CZ + c];
+            }
+            if (half && t == 0)
+                mid[c] = H[c];
+        }
+    }
+    std::vector<char> touched((size_t)CZ * ROW, 0);
+    for (int tid = 0; tid < PLZ::THREADS; tid++) {
+        const int c = tid % CZ, t = tid / CZ;
+        cd *row = R0 + (size_t)c * ROW;
+        for (int j = 0; j < PAIRS; j++) {
+            const int k = t + TZ * j;
+            cd xk, xm;
+            rfft_pair(pa[(size_t)tid * PAIRS + j], pb[(size_t)tid * PAIRS + j], tw[k], &xk, &xm);
+            if (touched[(size_t)c * ROW + k] || touched[(size_t)c * ROW + NZ - k]) return 22;
+            row[k] = xk;
+            row[NZ - k] = xm;
+            touched[(size_t)c * ROW + k] = touched[(size_t)c * ROW + NZ - k] = 1;
+        }
+        if (t == 0) {
+            if (touched[(size_t)c * ROW + NZ / 2]) return 22;
+            row[NZ / 2].x = mid[c].x;
+            row[NZ / 2].y = -mid[c].y;
+            touched[(size_t)c * ROW + NZ / 2] = 1;
+        }
+    }
+    for (size_t i = 0; i < touched.size(); i++)
+        if (!touched[i]) return 23;                                 // every output of every row was produced
+    return 0;
+}
+
+// the row plans fft_zy.cu launches (keep in step with zy_dispatch); n = -1024 / 2048: the 8192-mode tiles
+extern "C" int fftx_emu_row_count(int n)
+{
+    switch (n) {
+    case 256: return Plan<2, 8, 8, 4096>::C;
+    case 512: return Plan<4, 8, 8, 4096>::C;
+    case 1024: return Plan<8, 8, 8, 4096>::C;
+    case -1024: return Plan<8, 8, 8, 8192>::C;
+    case 2048: return Plan<16, 8, 8, 8192>::C;
+    }
+    return 0;
+}
+
+// rows: [C][n + 2] doubles, transformed in place; twiddle: exp(-2 pi i t / n), t < n; twiddle_half: exp(-2 pi i t / (n/2))
+extern "C" int fftx_emu_rows(int n, double *rows, const double *twiddle, const double *twiddle_half)
+{
+    switch (n) {
+    case 256: return emu_rows<Plan<2, 8, 8, 4096>>(rows, twiddle, twiddle_half);
+    case 512: return emu_rows<Plan<4, 8, 8, 4096>>(rows, twiddle, twiddle_half);
+    case 1024: return emu_rows<Plan<8, 8, 8, 4096>>(rows, twiddle, twiddle_half);
+    case -1024: return emu_rows<Plan<8, 8, 8, 8192>>(rows, twiddle, twiddle_half);
+    case 2048: return emu_rows<Plan<16, 8, 8, 8192>>(rows, twiddle, twiddle_half);
+    }
+    return -1;
+}
