@@ -163,7 +163,7 @@ struct genpk_ctx {
     int fused_xpass = 1;                      // 0: always cuFFT's x pass + bin_power_kernel
     int use_tma = 1;                          // column kernels fill their tiles with bulk tensor copies (0: per-thread cp.async)
     int fused_zy = 1;                         // GENPK_OPT_FUSED_ZY: z rows and y columns in one persistent kernel (fft_zy.cu); 2: 8192-mode tiles at 1024
-    int zy_lag = 2;                           // planes between a plane's z tiles and its y tiles in that kernel's schedule
+    int zy_lag = 3;                           // planes between a plane's z tiles and its y tiles in that kernel's schedule
     int coop_launch = 0;                      // cudaDevAttrCooperativeLaunch
     int *d_rows_done = nullptr;
     int rows_done_n = 0;

@@ -21,6 +21,8 @@
 // wait for nothing, so with every CTA resident (cooperative launch) the schedule cannot deadlock.
 #include <cooperative_groups.h>
 
+#include <type_traits>
+
 #include "fft_tiles.cuh"
 
 namespace genpk {
@@ -234,14 +236,23 @@ __global__ void __launch_bounds__(PLY::THREADS, PLY::TILE == 4096 ? 2 : 1) fft_z
             if (t == 0)
                 mid = E[c];
             double2 *const dst = A.spec + (size_t)cur.plane * A.plane_stride + (size_t)(cur.idx * CZ + c) * ROW;
-#pragma unroll
-            for (int j = 0; j < PAIRS; j++) {
+            const cd wt = A.tw[t];                                   // exp(-2 pi i t / dims); the pairs' twiddles are 1/32-turn steps from it
+            auto untangle = [&](auto J) {
+                constexpr int j = decltype(J)::value;
                 const int k = t + TZ * j;
                 cd xk, xm;
-                rfft_pair(w[2 * j], w[2 * j + 1], A.tw[k], &xk, &xm);
+                rfft_pair(w[2 * j], w[2 * j + 1], rfft_step<j>(wt), &xk, &xm);
                 dst[k] = xk;
                 dst[NZ - k] = xm;
-            }
+            };
+            untangle(std::integral_constant<int, 0>());
+            untangle(std::integral_constant<int, 1>());
+            untangle(std::integral_constant<int, 2>());
+            untangle(std::integral_constant<int, 3>());
+            untangle(std::integral_constant<int, 4>());
+            untangle(std::integral_constant<int, 5>());
+            untangle(std::integral_constant<int, 6>());
+            untangle(std::integral_constant<int, 7>());
             if (t == 0)
                 dst[NZ / 2] = make_double2(mid.x, -mid.y);
             if (asked) {

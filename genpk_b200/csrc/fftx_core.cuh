@@ -149,6 +149,19 @@ constexpr int EPT = 16;               // elements per thread
 //   E = (a + conj b) / 2,  O = -i (a - conj b) / 2      (transforms of the even and the odd samples)
 //   X[k] = E + w O,        X[Nc - k] = conj(E - w O)
 // k = 0 gives X[0] = Re a + Im a and X[Nc] = Re a - Im a; the self-paired k = Nc/2 gives conj(a).
+// exp(-2 pi i j / 32), j < 8: a thread's pairs are k = t + (NZ/16) j, so its twiddles exp(-2 pi i k / (2 NZ)) are
+// exp(-2 pi i t / (2 NZ)) times these, whatever the length
+template <int J> FX_HD cd rfft_step(cd w)
+{
+    static_assert(J >= 0 && J < 8, "eight pairs per thread");
+    constexpr double cs[8][2] = {{1.00000000000000000000, -0.00000000000000000000}, {0.98078528040323043058, -0.19509032201612824808}, {0.92387953251128673848, -0.38268343236508978178}, {0.83146961230254523567, -0.55557023301960217765}, {0.70710678118654757274, -0.70710678118654746172}, {0.55557023301960228867, -0.83146961230254523567}, {0.38268343236508983729, -0.92387953251128673848}, {0.19509032201612833135, -0.98078528040323043058}};
+    if (J == 0) return w;
+    cd c;
+    c.x = cs[J][0];
+    c.y = cs[J][1];
+    return cmul(w, c);
+}
+
 FX_HD void rfft_pair(cd a, cd b, cd w, cd *xk, cd *xm)
 {
     cd e, o;

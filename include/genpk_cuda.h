@@ -109,7 +109,7 @@ extern "C" {
                                           of a plane, then the column pass along y two planes behind, out of L2 (fft_zy.cu): the grid
                                           is read once and written once.  2: the same with 8192-mode tiles at 1024.  0: the library's
                                           batched 1-D r2c along z followed by fft_cols_kernel along y (two trips through HBM). */
-#define GENPK_OPT_ZY_LAG        27     /* planes between a plane's z tiles and its y tiles in that kernel's schedule (default 2) */
+#define GENPK_OPT_ZY_LAG        27     /* planes between a plane's z tiles and its y tiles in that kernel's schedule (default 3) */
 #define GENPK_OPT_ZERO_AFTER_POWER 25  /* 1: the fused x pass of genpk_fft_power / genpk_fft_power_cross / genpk_pk_from_particles
                                           overwrites every tile of the grid with zeros (TMA bulk tensor stores) right after reading it,
                                           and the genpk_grid_zero that follows has nothing left to do; needs GENPK_OPT_TMA.  0 (default):

@@ -203,10 +203,12 @@ template <class PLZ> static int emu_rows(double *rows, const double *twiddle, co
     for (int tid = 0; tid < PLZ::THREADS; tid++) {
         const int c = tid % CZ, t = tid / CZ;
         cd *row = R0 + (size_t)c * ROW;
+        const cd steps[8] = {rfft_step<0>(tw[t]), rfft_step<1>(tw[t]), rfft_step<2>(tw[t]), rfft_step<3>(tw[t]),
+                             rfft_step<4>(tw[t]), rfft_step<5>(tw[t]), rfft_step<6>(tw[t]), rfft_step<7>(tw[t])};
         for (int j = 0; j < PAIRS; j++) {
             const int k = t + TZ * j;
             cd xk, xm;
-            rfft_pair(pa[(size_t)tid * PAIRS + j], pb[(size_t)tid * PAIRS + j], tw[k], &xk, &xm);
+            rfft_pair(pa[(size_t)tid * PAIRS + j], pb[(size_t)tid * PAIRS + j], steps[j], &xk, &xm);
             if (touched[(size_t)c * ROW + k] || touched[(size_t)c * ROW + NZ - k]) return 22;
             row[k] = xk;
             row[NZ - k] = xm;
