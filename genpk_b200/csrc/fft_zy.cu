@@ -359,7 +359,9 @@ template <bool SCATTER> static int zy_dispatch(genpk_ctx *ctx, FftZyArgs &A)
     case 256: return launch_zy<Plan<2, 8, 8, 4096>, Plan<4, 8, 8, 4096>, SCATTER>(ctx, A);
     case 512: return launch_zy<Plan<4, 8, 8, 4096>, Plan<8, 8, 8, 4096>, SCATTER>(ctx, A);
     case 1024:
-        if (ctx->fused_zy == 2)                                    // one CTA of 512 threads per SM, 128-byte y-tile rows
+        // 8192-mode tiles (one CTA of 512 threads per SM, 128-byte y-tile rows) for the scatter variant, whose rows
+        // leave as peer stores over NVLink: C3 on two GPUs 3.65 ms against 5.41 ms with 64-byte stores (profiles/r02)
+        if (ctx->fused_zy == 2 || SCATTER)
             return launch_zy<Plan<8, 8, 8, 8192>, Plan<16, 8, 8, 8192>, SCATTER>(ctx, A);
         return launch_zy<Plan<8, 8, 8, 4096>, Plan<16, 8, 8, 4096>, SCATTER>(ctx, A);
     case 2048: return launch_zy<Plan<16, 8, 8, 8192>, Plan<16, 16, 8, 8192>, SCATTER>(ctx, A);
