@@ -107,6 +107,14 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
 
 
+def ncu_traffic_source():
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        return f"{d.get('report', 'ncu capture')} at commit {d.get('commit', 'unknown')}"
+    except Exception:
+        return None
+
+
 def ncu_traffic(workload):
     """DRAM bytes per launch from the committed ncu --set full captures (tools/ncu_traffic.py), or {}."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
@@ -119,11 +127,15 @@ def ncu_traffic(workload):
 
 def algorithmic_bytes(n_particles, dims, nranks=1):
     """SURVEY 8d: particles read once (12 B), padded real grid written once (8 B/cell);
-    spectrum read once (16 B/mode).  Per GPU."""
+    spectrum read once (16 B/mode).  The (y,z) transform in between: grid read once, spectrum written once.  Per GPU."""
     fd = 2 * (dims // 2 + 1)
     deposit = 12 * n_particles / nranks + 8 * dims * dims * fd / nranks
     binning = 16 * dims * dims * (dims // 2 + 1) / nranks
     return deposit, binning
+
+
+def fft_algorithmic_bytes(dims, nranks=1):
+    return 2 * 8 * dims * dims * (2 * (dims // 2 + 1)) / nranks
 
 
 class ClockSampler:
@@ -288,6 +300,32 @@ def use_all_host_threads():
     except OSError:
         pass
     return n
+
+
+def bind_to_gpu_numa(dev_index):
+    """Run this rank's host side (and first-touch its page-locked shard) on the NUMA node the GPU hangs off, so that
+    N ranks uploading at once do not all pull their shards across the socket link.  Returns what was done."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(dev_index).pci_bus_id
+        dom = torch.cuda.get_device_properties(dev_index).pci_domain_id
+        devid = torch.cuda.get_device_properties(dev_index).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{devid:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node")]
+        if node < 0 or len(nodes) < 2:
+            return f"single NUMA node ({len(nodes)} listed, GPU reports {node})"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return f"node {node}: none of its CPUs are available to this process"
+        os.sched_setaffinity(0, cpus)
+        return f"node {node} ({len(cpus)} CPUs)"
+    except Exception as e:                                       # diagnostics only: never fail a run over this
+        return f"unavailable ({type(e).__name__})"
 
 
 def cpu_model():
@@ -527,6 +565,7 @@ def run_ours(args):
     assert int(cnt.astype(np.int64).sum()) == dims ** 3 - 1, "mode counts do not sum to dims^3-1"
     self_check = None if args.no_self_check else check_against_fixtures(args.workload, dims, power, cnt, keffs)
 
+    host_affinity = bind_to_gpu_numa(local) if (world > 1 and not args.no_e2e) else None
     # ---- end to end from pinned host memory ---------------------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -548,6 +587,8 @@ def run_ours(args):
                "h2d_bytes_per_step": 12 * n_total, "d2h_bytes_per_step": 3 * nrbins * 8 * world,
                "api": "genpk_pk_from_particles (host float32 positions in, power/count/keffs out)" if world == 1
                else "SlabPipeline.pk on pinned host shards"}
+        if host_affinity:
+            e2e["host_affinity"] = host_affinity
         del hpos
 
     # ---- roofline of the dominant kernel of ours ----------------------------------------------
@@ -563,6 +604,11 @@ def run_ours(args):
         ach = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
         roof[name] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                       "traffic": None, "ms": ms, "algorithmic_bytes": nbytes}
+    if stage_ms.get("fft", 0) > 0:
+        nb = fft_algorithmic_bytes(dims, world)
+        ach = nb / (stage_ms["fft"] * 1e-3) / 1e9
+        roof["fft_yz"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                          "ms": stage_ms["fft"], "algorithmic_bytes": nb}
     # DRAM traffic of the stage's kernels from the committed ncu capture of this workload (single GPU only)
     tr = ncu_traffic(args.workload) if world == 1 else {}
     if "deposit_march_kernel" in tr and ctx.last_order().get("lattice"):
@@ -572,6 +618,12 @@ def run_ours(args):
     bk = "fftx_power_kernel" if fused else "bin_power_kernel"
     if bk in tr:
         roof["binning"]["traffic"] = tr[bk]["dram_read_bytes"] + tr[bk]["dram_write_bytes"]
+    if "fft_yz" in roof and "fft_zy_kernel" in tr and libcalls == 0:
+        roof["fft_yz"]["traffic"] = tr["fft_zy_kernel"]["dram_read_bytes"] + tr["fft_zy_kernel"]["dram_write_bytes"]
+    if tr:
+        for r in roof.values():
+            if r.get("traffic") is not None:
+                r["traffic_source"] = ncu_traffic_source()
     dom = "deposit" if stage_ms["deposit_with_zero"] >= stage_ms["binning"] else "binning"
     roofline = dict(roof[dom])
     roofline["kernel"] = {"deposit": "deposit stage (grid zero + order probe + deposit_march_kernel | brick sort + "

@@ -26,6 +26,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <future>
 #include <memory>
 #include <string>
 #include <vector>
@@ -171,97 +172,160 @@ struct Sink {
     }
 };
 
+// Page-locked host memory for the chunks on their way to the GPU (the copies run at PCIe speed and overlap the
+// reads); plain memory if the driver refuses.
+struct PinnedBuf {
+    void *p = nullptr;
+    bool pinned = false;
+    size_t bytes = 0;
+    bool reserve(size_t n)
+    {
+        if (n <= bytes)
+            return true;
+        release();
+        if (cudaHostAlloc(&p, n, cudaHostAllocPortable) == cudaSuccess) {
+            pinned = true;
+        } else {
+            cudaGetLastError();
+            p = malloc(n);
+            pinned = false;
+        }
+        bytes = p ? n : 0;
+        return p != nullptr;
+    }
+    void release()
+    {
+        if (p && pinned) cudaFreeHost(p);
+        if (p && !pinned) free(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    ~PinnedBuf() { release(); }
+};
+
+// One chunk in flight: positions (float32, or float64 as stored) and masses.
+struct ChunkBuf {
+    PinnedBuf pos, mass;
+    int64_t n = 0;
+    bool ok = true;
+};
+
 // read_fieldize() (read_fieldize.cpp:18-97) and read_fieldize_bigfile()
 // (read_fieldize_bigfile.cpp:64-125): stream one particle type into the sink and
-// accumulate total_mass the way the reference does, quirks included.
+// accumulate total_mass the way the reference does, quirks included.  The reference reads a chunk of 2^26
+// particles, deposits it, reads the next; here a reader thread fills one page-locked buffer (the pieces of a chunk
+// that live in different files fetched in parallel, parallel_read.cpp) while the previous one is on its way to the
+// GPU.  Chunks of 2^24 particles; the mass sums are taken in the reference's order and grouping.
 static int read_deposit(const Source &src, int type, double box, Sink &sink, double *total_mass)
 {
     const int64_t npart_total = src.npart[type];
     if (npart_total == 0)
         return 1;
     const double mass = src.mass[type];
-    const int64_t chunk = std::min<int64_t>(npart_total, (int64_t)1 << 26);       // read_fieldize.cpp:45
-    std::vector<float> pos(3 * (size_t)chunk), masses;
-    if (mass == 0)
-        masses.resize((size_t)chunk);
+    const int64_t ref_chunk = std::min<int64_t>(npart_total, (int64_t)1 << 26);   // read_fieldize.cpp:45
+    const int64_t chunk = std::min<int64_t>(npart_total, (int64_t)1 << 24);
+    const bool with_mass = mass == 0;
+    ChunkBuf bufs[2];
+
+    BigBlockInfo bp, bm;
+    bool f64 = false;
+    int skip_type = 0;
     if (src.is_big()) {
-        BigBlockInfo bp, bm;
         char name[32];
         snprintf(name, sizeof(name), "%d/Position", type);
         if (!src.big->open_block(name, &bp) || bp.nmemb != 3 || bp.rows < npart_total) {
             fprintf(stderr, "Failed to open block at %s:%s\n", name, src.big->error().c_str());
             return 1;
         }
-        if (mass == 0) {
+        if (with_mass) {
             snprintf(name, sizeof(name), "%d/Mass", type);
             if (!src.big->open_block(name, &bm) || bm.nmemb != 1 || bm.rows < npart_total) {
                 fprintf(stderr, "Failed to open block at %s:%s\n", name, src.big->error().c_str());
                 return 1;
             }
         }
-        // the reference holds the whole type in RAM and makes one fieldize() call; chunks give the
-        // same sums (total_mass_this_file is accumulated in double over all particles, :110-112)
-        double total_mass_this_file = 0;
-        const bool f64 = bp.dtype == "<f8" && sink.takes_f64();                     // stored doubles: narrowed on the GPU
-        std::vector<double> pos64;
-        if (f64)
-            pos64.resize(3 * (size_t)chunk);
-        for (int64_t done = 0; done < npart_total; done += chunk) {
-            const int64_t n = std::min(chunk, npart_total - done);
-            if (!(f64 ? src.big->read_f64_raw(bp, done, n, pos64.data()) : src.big->read_f32(bp, done, n, pos.data()))) {
+        f64 = bp.dtype == "<f8" && sink.takes_f64();                               // stored doubles: narrowed on the GPU
+    } else {
+        const GadgetSnapshot &snap = *src.gadget;
+        skip_type = ((1 << N_TYPE) - 1) - (1 << type);                            // read_fieldize.cpp:27,37
+        const int64_t parts_in_pos = snap.block_parts("POS ");
+        if (parts_in_pos == 0 || snap.block_bytes("POS ") / parts_in_pos != 3 * (int64_t)sizeof(float)) {
+            fprintf(stderr, "The pos array uses %ld bytes per particle, instead of %lu.\n"
+                            " Double-precision snapshots are not supported by this build.\n",
+                    parts_in_pos ? (long)(snap.block_bytes("POS ") / parts_in_pos) : 0L, 3 * sizeof(float));
+            return 1;
+        }
+    }
+    for (ChunkBuf &b : bufs) {
+        if (!b.pos.reserve((size_t)chunk * 3 * (f64 ? sizeof(double) : sizeof(float))) ||
+            (with_mass && !b.mass.reserve((size_t)chunk * sizeof(float)))) {
+            fprintf(stderr, "out of host memory for the read buffers\n");
+            return 1;
+        }
+    }
+    // the reader: particles [first, first + n) of this type into b
+    auto fill = [&](ChunkBuf *b, int64_t first, int64_t n) {
+        b->n = n;
+        b->ok = true;
+        if (src.is_big()) {
+            if (!(f64 ? src.big->read_f64_raw(bp, first, n, (double *)b->pos.p) : src.big->read_f32(bp, first, n, (float *)b->pos.p)) ||
+                (with_mass && !src.big->read_f32(bm, first, n, (float *)b->mass.p))) {
                 fprintf(stderr, "Failed to read from block: %s\n", src.big->error().c_str());
-                return 1;
+                b->ok = false;
             }
-            if (mass == 0) {
-                if (!src.big->read_f32(bm, done, n, masses.data())) {
-                    fprintf(stderr, "Failed to read from block: %s\n", src.big->error().c_str());
-                    return 1;
-                }
-                for (int64_t i = 0; i < n; i++)
-                    total_mass_this_file += masses[i];
-            }
-            if (f64 ? sink.put64(pos64.data(), mass == 0 ? masses.data() : nullptr, n, mass, box)
-                    : sink.put(pos.data(), mass == 0 ? masses.data() : nullptr, n, mass, box))
-                return 1;
+            return;
         }
-        *total_mass += total_mass_this_file;
-        *total_mass += mass * npart_total;                                        // :120 (no "+1" on this path)
-        return 0;
-    }
-    const GadgetSnapshot &snap = *src.gadget;
-    const int skip_type = ((1 << N_TYPE) - 1) - (1 << type);                      // read_fieldize.cpp:27,37
-    const int64_t parts_in_pos = snap.block_parts("POS ");
-    if (parts_in_pos == 0 || snap.block_bytes("POS ") / parts_in_pos != 3 * (int64_t)sizeof(float)) {
-        fprintf(stderr, "The pos array uses %ld bytes per particle, instead of %lu.\n"
-                        " Double-precision snapshots are not supported by this build.\n",
-                parts_in_pos ? (long)(snap.block_bytes("POS ") / parts_in_pos) : 0L, 3 * sizeof(float));
-        return 1;
-    }
-    int64_t toread = npart_total, read = 0, parts = chunk;
-    while (toread > 0) {
-        if (toread < parts)
-            parts = toread;
-        if (snap.get_block("POS ", pos.data(), parts, read, skip_type) != parts) {
+        if (src.gadget->get_block("POS ", b->pos.p, n, first, skip_type) != n) {
             fprintf(stderr, "Error reading particle data for type %d\n", type);
+            b->ok = false;
+        } else if (with_mass && src.gadget->get_block("MASS", b->mass.p, n, first, skip_type) != n) {
+            fprintf(stderr, "Error reading mass data for type %d\n", type);
+            b->ok = false;
+        }
+    };
+    const int64_t nchunks = (npart_total + chunk - 1) / chunk;
+    std::future<void> pending = std::async(std::launch::async, fill, &bufs[0], (int64_t)0, std::min(chunk, npart_total));
+    double group_mass = 0;                                                         // total_mass_this_file of the reference's chunk
+    int64_t in_group = 0;
+    for (int64_t i = 0; i < nchunks; i++) {
+        pending.get();
+        ChunkBuf &b = bufs[i & 1];
+        if (i + 1 < nchunks) {
+            const int64_t first = (i + 1) * chunk;
+            pending = std::async(std::launch::async, fill, &bufs[(i + 1) & 1], first, std::min(chunk, npart_total - first));
+        }
+        int rc = b.ok ? 0 : 1;
+        if (!rc) {
+            const float *masses = with_mass ? (const float *)b.mass.p : nullptr;
+            if (with_mass)
+                for (int64_t k = 0; k < b.n; k++)
+                    group_mass += masses[k];
+            // (the deposit returns once the chunk's copies have left this buffer)
+            rc = f64 ? sink.put64((const double *)b.pos.p, masses, b.n, mass, box) : sink.put((const float *)b.pos.p, masses, b.n, mass, box);
+        }
+        if (rc) {
+            if (pending.valid())
+                pending.get();
             return 1;
         }
-        if (mass == 0) {
-            double total_mass_this_file = 0;
-            if (snap.get_block("MASS", masses.data(), parts, read, skip_type) != parts) {
-                fprintf(stderr, "Error reading mass data for type %d\n", type);
-                return 1;
+        in_group += b.n;
+        // the sums of a 2^26 chunk of the reference (or of the whole type on the bigfile path) are closed here
+        const bool group_ends = src.is_big() ? i + 1 == nchunks : (in_group == ref_chunk || i + 1 == nchunks);
+        if (group_ends) {
+            if (src.is_big()) {
+                *total_mass += group_mass;                                         // read_fieldize_bigfile.cpp:110-112
+                *total_mass += mass * npart_total;                                 // :120 (no "+1" on this path)
+            } else {
+                if (with_mass)
+                    *total_mass += group_mass;                                     // read_fieldize.cpp:72-75
+                *total_mass += mass * in_group;                                    // :77
             }
-            for (int64_t i = 0; i < parts; i++)
-                total_mass_this_file += masses[i];
-            *total_mass += total_mass_this_file;                                   // :72-75
+            group_mass = 0;
+            in_group = 0;
         }
-        *total_mass += mass * parts;                                               // :77
-        if (sink.put(pos.data(), mass == 0 ? masses.data() : nullptr, parts, mass, box))   // :90
-            return 1;
-        toread -= parts;
-        read += parts;
     }
-    *total_mass += 1;                                                              // :94
+    if (!src.is_big())
+        *total_mass += 1;                                                          // read_fieldize.cpp:94
     return 0;
 }
 

@@ -12,6 +12,16 @@ namespace genpk_host {
 
 constexpr int N_TYPE = 6;
 
+// One byte range of one file and where it goes (parallel_read.cpp).
+struct ReadSeg {
+    std::string path;
+    int64_t offset = 0, bytes = 0;
+    void *dst = nullptr;
+};
+// All of them, fetched by up to max_threads threads with pread(); false (and *error) on a missing file or a short read.
+bool read_segments(const std::vector<ReadSeg> &segs, int max_threads, std::string *error);
+int read_threads();                                      // GENPK_READ_THREADS, default min(hardware threads, 8)
+
 // The 256-byte Gadget header (layout of GadgetReader/gadgetheader.h:18-76).
 #pragma pack(push, 1)
 struct GadgetHeader {
@@ -57,6 +67,7 @@ public:
     // types the block does not hold: callers get the bytes the
     // reference's reader would have handed to fieldize().
     int64_t get_block(const std::string &name, void *dst, int64_t n_to_read, int64_t start_part, int skip_type) const;
+    int64_t get_block_sequential(const std::string &name, void *dst, int64_t n_to_read, int64_t start_part, int skip_type) const;
     const std::string &error() const { return error_; }
 
 private:

@@ -136,11 +136,9 @@ bool BigfileSnapshot::open_block(const std::string &name, BigBlockInfo *info) co
     return true;
 }
 
-bool BigfileSnapshot::read_f32(const BigBlockInfo &b, int64_t first, int64_t count, float *dst) const
+// rows [first, first + count) of a block as byte ranges of its files, laid out back to back from dst
+static bool plan_rows(const BigBlockInfo &b, int64_t first, int64_t count, size_t rowbytes, void *dst, std::vector<ReadSeg> *segs)
 {
-    const char kind = kind_of(b.dtype);
-    const size_t rowbytes = (size_t)b.itemsize * b.nmemb;
-    std::vector<unsigned char> buf;
     int64_t file_first = 0, done = 0;
     for (size_t f = 0; f < b.file_rows.size() && done < count; f++) {
         const int64_t file_last = file_first + b.file_rows[f];
@@ -149,35 +147,39 @@ bool BigfileSnapshot::read_f32(const BigBlockInfo &b, int64_t first, int64_t cou
             const int64_t n = (file_last - lo < count - done) ? file_last - lo : count - done;
             char fname[16];
             snprintf(fname, sizeof(fname), "%06X", (unsigned)f);
-            FILE *fd = fopen((b.dir + "/" + fname).c_str(), "rb");
-            if (!fd) {
-                error_ = "cannot open " + b.dir + "/" + fname;
-                return false;
-            }
-            buf.resize((size_t)n * rowbytes);
-            const bool good = fseek(fd, (long)((lo - file_first) * (int64_t)rowbytes), SEEK_SET) == 0 &&
-                              fread(buf.data(), rowbytes, (size_t)n, fd) == (size_t)n;
-            fclose(fd);
-            if (!good) {
-                error_ = "short read in " + b.dir + "/" + fname;
-                return false;
-            }
-            float *out = dst + (size_t)done * b.nmemb;
-            const size_t items = (size_t)n * b.nmemb;
-            if (kind == 'f' && b.itemsize == 4) {
-                memcpy(out, buf.data(), items * 4);
-            } else {
-                // through double, then narrowed: positions[i] = ((double*)pos.data)[i] (read_fieldize_bigfile.cpp:93-94)
-                for (size_t i = 0; i < items; i++)
-                    out[i] = (float)element_as_double(buf.data() + i * b.itemsize, kind, b.itemsize);
-            }
+            ReadSeg g;
+            g.path = b.dir + "/" + fname;
+            g.offset = (lo - file_first) * (int64_t)rowbytes;
+            g.bytes = n * (int64_t)rowbytes;
+            g.dst = (char *)dst + (size_t)done * rowbytes;
+            segs->push_back(g);
             done += n;
         }
         file_first = file_last;
     }
-    if (done != count) {
+    return done == count;
+}
+
+bool BigfileSnapshot::read_f32(const BigBlockInfo &b, int64_t first, int64_t count, float *dst) const
+{
+    const char kind = kind_of(b.dtype);
+    const size_t rowbytes = (size_t)b.itemsize * b.nmemb;
+    const size_t items = (size_t)count * b.nmemb;
+    const bool as_stored = kind == 'f' && b.itemsize == 4;
+    std::vector<unsigned char> buf;
+    if (!as_stored)
+        buf.resize((size_t)count * rowbytes);
+    std::vector<ReadSeg> segs;
+    if (!plan_rows(b, first, count, rowbytes, as_stored ? (void *)dst : (void *)buf.data(), &segs)) {
         error_ = "block " + b.dir + " holds fewer rows than requested";
         return false;
+    }
+    if (!read_segments(segs, read_threads(), &error_))
+        return false;
+    if (!as_stored) {
+        // through double, then narrowed: positions[i] = ((double*)pos.data)[i] (read_fieldize_bigfile.cpp:93-94)
+        for (size_t i = 0; i < items; i++)
+            dst[i] = (float)element_as_double(buf.data() + i * b.itemsize, kind, b.itemsize);
     }
     return true;
 }
@@ -188,36 +190,12 @@ bool BigfileSnapshot::read_f64_raw(const BigBlockInfo &b, int64_t first, int64_t
         error_ = "block " + b.dir + " is not <f8";
         return false;
     }
-    const size_t rowbytes = (size_t)8 * b.nmemb;
-    int64_t file_first = 0, done = 0;
-    for (size_t f = 0; f < b.file_rows.size() && done < count; f++) {
-        const int64_t file_last = file_first + b.file_rows[f];
-        const int64_t lo = first + done;
-        if (lo < file_last) {
-            const int64_t n = (file_last - lo < count - done) ? file_last - lo : count - done;
-            char fname[16];
-            snprintf(fname, sizeof(fname), "%06X", (unsigned)f);
-            FILE *fd = fopen((b.dir + "/" + fname).c_str(), "rb");
-            if (!fd) {
-                error_ = "cannot open " + b.dir + "/" + fname;
-                return false;
-            }
-            const bool good = fseek(fd, (long)((lo - file_first) * (int64_t)rowbytes), SEEK_SET) == 0 &&
-                              fread(dst + (size_t)done * b.nmemb, rowbytes, (size_t)n, fd) == (size_t)n;
-            fclose(fd);
-            if (!good) {
-                error_ = "short read in " + b.dir + "/" + fname;
-                return false;
-            }
-            done += n;
-        }
-        file_first = file_last;
-    }
-    if (done != count) {
+    std::vector<ReadSeg> segs;
+    if (!plan_rows(b, first, count, (size_t)8 * b.nmemb, dst, &segs)) {
         error_ = "block " + b.dir + " holds fewer rows than requested";
         return false;
     }
-    return true;
+    return read_segments(segs, read_threads(), &error_);
 }
 
 }  // namespace genpk_host

@@ -143,7 +143,79 @@ int64_t GadgetSnapshot::block_parts(const std::string &name) const
     return s;
 }
 
+// The pieces of the block that a call wants, file by file: [n_file particles at file offset pos], in file order.
 int64_t GadgetSnapshot::get_block(const std::string &name, void *dst, int64_t n_to_read, int64_t start_part,
+                                  int skip_type) const
+{
+    if (!has_block(name))
+        return 0;
+    const int64_t start_part_in = start_part;
+    struct Want {
+        const GadgetFile *file;
+        int64_t pos;
+        uint32_t n_file;
+        int partlen;
+    };
+    std::vector<Want> wants;
+    int64_t planned = 0;
+    for (const auto &f : files_) {
+        auto it = f.blocks.find(name);
+        if (it == f.blocks.end())
+            continue;
+        const GadgetBlock &b = it->second;
+        // particles of this file that are wanted: 32-bit unsigned arithmetic, as in the reference --
+        // when skip_type names a type the block does not hold this wraps, and the clamp below is
+        // what bounds the read
+        uint32_t n_file = (uint32_t)(b.length / b.partlen);
+        for (int j = 0; j < N_TYPE; j++)
+            if (skip_type & (1 << j))
+                n_file -= f.header.npart[j];
+        int64_t pos = b.start;
+        for (int j = 0; j < N_TYPE; j++) {
+            if (skip_type & (1 << j))
+                pos += (int64_t)f.header.npart[j] * b.partlen;
+            else
+                break;
+        }
+        if (start_part > 0) {
+            if ((int64_t)n_file <= start_part) {
+                start_part -= n_file;
+                continue;
+            }
+            pos += start_part * b.partlen;
+            n_file -= (uint32_t)start_part;
+            start_part = 0;
+        }
+        if ((int64_t)n_file > n_to_read - planned)
+            n_file = (uint32_t)(n_to_read - planned);
+        wants.push_back({&f, pos, n_file, b.partlen});
+        planned += n_file;
+        if (planned == n_to_read)
+            break;
+    }
+    // all pieces at once (parallel_read.cpp); every piece complete is the normal case
+    {
+        std::vector<ReadSeg> segs;
+        int64_t at = 0;
+        for (const Want &w : wants) {
+            ReadSeg g;
+            g.path = w.file->name;
+            g.offset = w.pos;
+            g.bytes = (int64_t)w.n_file * w.partlen;
+            g.dst = (char *)dst + at * w.partlen;
+            segs.push_back(g);
+            at += w.n_file;
+        }
+        if (read_segments(segs, read_threads(), nullptr))
+            return planned;
+    }
+    // a missing file or a short read: exactly what the reference's reader would have delivered
+    return get_block_sequential(name, dst, n_to_read, start_part_in, skip_type);
+}
+
+// File by file through fread(), as GSnap::GetBlock does (gadgetreader.cpp:471-557): a file that cannot be opened is
+// skipped and what fread() returned is what counts.
+int64_t GadgetSnapshot::get_block_sequential(const std::string &name, void *dst, int64_t n_to_read, int64_t start_part,
                                   int skip_type) const
 {
     int64_t n_read = 0;
