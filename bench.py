@@ -89,6 +89,7 @@ def parse_args():
                     help="before timing: one deposit (+ ghost exchange), the grid must sum to the particle count")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-spread", action="store_true", help="rank r uses GPU r instead of GPUs spread over the visible ones")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
     return ap.parse_args()
 
@@ -389,6 +390,12 @@ def run_ours(args):
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+    # Ranks take GPUs spread evenly over the visible ones (N = 4 of 8: 0, 2, 4, 6): NVLink is uniform, but host memory
+    # reaches the GPUs through shared PCIe bridges, and the e2e leg uploads from every rank at once (measured on this
+    # pool: 53 / 105 / 111 / 180 GB/s aggregate with GPUs 0..N-1 at N = 1 / 2 / 4 / 8).
+    visible = torch.cuda.device_count()
+    stride = visible // world if (not args.no_spread and world > 1 and visible >= world and visible % world == 0) else 1
+    local = local * stride
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -663,6 +670,8 @@ def run_ours(args):
             "sample": f"{t['n_side']}^3 {wl['kind']} particles -> {t['dims']}^3 grid (bounded replica, same particles "
                       f"per cell); FFT = pocketfft stand-in (FFTW3 absent)",
             "cpu_model": cpu_model(), "stage_s": {k: t[k] for k in ("deposit", "fft", "binning")}}
+    if world > 1:
+        line["config"]["gpus_used"] = [r * stride for r in range(world)]
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
