@@ -203,7 +203,10 @@ genpk_multi *genpk_multi_create(int dims, int ngpus, const int *devices, unsigne
     m->counts.assign(ngpus, std::vector<int64_t>(ngpus, 0));
     bool ok = true;
     for (int r = 0; r < ngpus && ok; r++) {
-        m->dev[r] = devices ? devices[r] : r % ndev;
+        // no list: spread over the visible GPUs (N = 4 of 8: 0, 2, 4, 6 -- neighbours tend to share a PCIe bridge to the
+        // host, and every slab uploads its share of a chunk at once), or share devices when there are fewer than N
+        const int stride = (ndev >= ngpus && ndev % ngpus == 0) ? ndev / ngpus : 1;
+        m->dev[r] = devices ? devices[r] : (r * stride) % ndev;
         ok = m->dev[r] >= 0 && m->dev[r] < ndev;
         if (!ok) set_error("genpk_multi_create: device %d does not exist", m->dev[r]);
     }

@@ -378,8 +378,8 @@ int genpk_slab_fft_yz_scatter(genpk_ctx *ctx, int which);
  * NVLink, each GPU deposits what it owns; the ghost plane is pulled from the neighbour's memory, the FFT transpose
  * is stored straight into the owners' blocks by the y pass (grid sides 256..2048, dims/ngpus a power of two; peer
  * copies of packed blocks otherwise), the last FFT pass is fused with the binning, and the per-bin partial sums are
- * added on the host.  devices: ngpus device ordinals, or NULL for 0..ngpus-1 (wrapping: several slabs may share
- * a device).  Same results as the single-GPU handle API (counts bit-exact; the fixed-point grid bit for bit). */
+ * added on the host.  devices: ngpus device ordinals, or NULL for the visible GPUs spread evenly (4 of 8: 0, 2, 4, 6;
+ * wrapping when there are fewer than ngpus: several slabs may share a device).  Same results as the single-GPU handle API (counts bit-exact; the fixed-point grid bit for bit). */
 typedef struct genpk_multi genpk_multi;
 genpk_multi *genpk_multi_create(int dims, int ngpus, const int *devices, unsigned flags);
 void genpk_multi_destroy(genpk_multi *m);
