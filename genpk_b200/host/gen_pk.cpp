@@ -223,7 +223,13 @@ static int read_deposit(const Source &src, int type, double box, Sink &sink, dou
         return 1;
     const double mass = src.mass[type];
     const int64_t ref_chunk = std::min<int64_t>(npart_total, (int64_t)1 << 26);   // read_fieldize.cpp:45
-    const int64_t chunk = std::min<int64_t>(npart_total, (int64_t)1 << 24);
+    int64_t chunk = (int64_t)1 << 24;
+    if (const char *env = getenv("GENPK_READ_CHUNK"))                              // particles per chunk (tests: many small chunks)
+        if (atoll(env) > 0)
+            chunk = atoll(env);
+    while (ref_chunk % chunk != 0 && chunk > 1)                                    // the reference's chunk boundaries are chunk boundaries
+        chunk = ref_chunk % chunk;                                                 // (Euclid: ends at a divisor of ref_chunk)
+    chunk = std::min(chunk, npart_total);
     const bool with_mass = mass == 0;
     ChunkBuf bufs[2];
 
