@@ -24,6 +24,10 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes)
                  : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
 {
     const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
@@ -71,13 +75,22 @@ __device__ __forceinline__ void loads_landed(const fftx::cd *v)
 // reading side.  Which half an index falls in is a compile-time property of i (the predicates
 // fold away), except on the pass-2 side of a plan whose thread owns a single radix-R2 unit
 // (2048): there all 16 indices of a thread lie in the same half (W_UNI / R_UNI).
-template <int N, int C, bool W_UNI, bool R_UNI, class WI, class RI>
-__device__ __forceinline__ void exchange(fftx::cd *E, const fftx::cd *src, fftx::cd *dst, int c, WI wi, RI ri)
+struct BlockSync {
+    __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+// named barrier `id` over `count` threads (the two halves of a CTA that run out of step with one another)
+struct NamedSync {
+    int id, count;
+    __device__ __forceinline__ void operator()() const { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+};
+
+template <int N, int C, bool W_UNI, bool R_UNI, class WI, class RI, class SYNC = BlockSync>
+__device__ __forceinline__ void exchange(fftx::cd *E, const fftx::cd *src, fftx::cd *dst, int c, WI wi, RI ri, SYNC sync = SYNC())
 {
 #pragma unroll
     for (int half = 0; half < 2; half++) {
         if (half)
-            __syncthreads();                           // the lower half has been read
+            sync();                                    // the lower half has been read
         if (W_UNI) {
             if ((wi(0) >= N / 2) == (half == 1)) {
 #pragma unroll
@@ -92,7 +105,7 @@ __device__ __forceinline__ void exchange(fftx::cd *E, const fftx::cd *src, fftx:
                     E[(idx - half * (N / 2)) * C + c] = src[i];
             }
         }
-        __syncthreads();
+        sync();
         if (R_UNI) {
             if ((ri(0) >= N / 2) == (half == 1)) {
 #pragma unroll

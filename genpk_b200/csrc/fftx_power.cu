@@ -31,6 +31,7 @@ struct FftxArgs {
     alignas(64) CUtensorMap tmap;   // the spectrum as {2*nc doubles, n_mid rows, dims slabs}; box {2C, 1, 256}
     alignas(64) CUtensorMap zmap;   // the same tensor with box {2C, 1, ZERO_BOX_ROWS}: zero stores behind the read
     int use_tma;
+    int halves_delay_ns;      // fftx_power_halves_kernel: head start of the first half
     int zero_after;           // 1: every tile is overwritten with zeros once it has been read (the grid is clear for the next deposit)
     const double2 *spec;      // [dims][n_mid][nc]
     const double2 *tw;        // exp(-2 pi i t / dims), t < dims
@@ -234,6 +235,121 @@ __global__ void __launch_bounds__(PL::THREADS, PL::TILE == 4096 ? 2 : 1) fftx_po
         double sum = 0.0;
         for (int j = 0; j < A.hists; j++)
             sum += sP[i * A.hists + j];
+        if (sum != 0.0)
+            atomicAdd(&A.sums[i], sum);
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// The same pass with the CTA split in two halves of 256 threads that share the 8192-mode tile (128-byte rows from
+// HBM) but work on four of its eight columns each, with their own exchange buffers and named barriers -- so that one
+// half's shared-memory exchanges can run under the other half's FP64 passes (GENPK_OPT_FUSED_XPASS = 3, 1024 only).
+// The halves are started half a tile apart; the tile buffer is refilled when both have taken their columns
+// (`empty`, 512 arrivals), so they stay within one tile of each other.
+// ---------------------------------------------------------------------------------
+template <class PL>
+__global__ void __launch_bounds__(2 * PL::THREADS, 1) fftx_power_halves_kernel(const __grid_constant__ FftxArgs A)
+{
+    constexpr int N = PL::N, C = PL::C, CW = 2 * PL::C, HT = PL::THREADS, TILE_MODES = 2 * PL::TILE;
+    constexpr int R2 = PL::R2, R3 = PL::R3;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    cd *const stage = reinterpret_cast<cd *>(smem_raw);                                 // [N][CW], the next tile
+    const int tid = threadIdx.x, half = tid / HT, ht = tid % HT;
+    cd *const E = reinterpret_cast<cd *>(smem_raw + (size_t)TILE_MODES * 16) + (size_t)half * (N / 2) * C;   // [N/2][C] per half
+    double *const P = reinterpret_cast<double *>(E);                                    // [N][C] |X|^2, same bytes
+    double *const sP = reinterpret_cast<double *>(smem_raw + (size_t)TILE_MODES * 24);  // [nrbins][2]: one histogram per half
+    unsigned *const sT = reinterpret_cast<unsigned *>(sP + (size_t)A.nrbins * 2);       // nrbins + 1
+    float *const sW = reinterpret_cast<float *>(sT + A.nrbins + 1);                     // dims/2 + 1
+    __shared__ __align__(8) unsigned long long full_bar, empty_bar;
+
+    const int c = ht % C, t = ht / C, col = half * C + c;
+    for (int i = tid; i < A.nrbins * 2; i += 2 * HT)
+        sP[i] = 0.0;
+    for (int i = tid; i <= A.nrbins; i += 2 * HT)
+        sT[i] = A.thresh[i];
+    for (int i = tid; i <= N / 2; i += 2 * HT)
+        sW[i] = A.iw1d[i];
+    if (tid == 0) {
+        mbar_init(&full_bar, 1);
+        mbar_init(&empty_bar, 2 * HT);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const NamedSync hsync{1 + half, HT};
+    const int b_ex1r = PL::ex1_r_base(t);
+    int b_ex2w[4], b_ex2r[4];
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+        b_ex2w[s] = PL::ex2_w_base(t, s);
+        b_ex2r[s] = PL::ex2_r_base(t, s);
+    }
+    const int kb = PL::out_k_base(t);
+    double *const hist = sP + half;
+
+    const int step_g = (int)(gridDim.x % (unsigned)A.groups), step_m = (int)(gridDim.x / (unsigned)A.groups);
+    auto advance = [&](int &g, int &m) {
+        g += step_g;
+        m += step_m;
+        if (g >= A.groups) {
+            g -= A.groups;
+            m++;
+        }
+    };
+    auto issue = [&](int g, int m) {                                 // one thread
+        if (m < A.n_mid) {
+            mbar_expect_tx(&full_bar, (unsigned)(TILE_MODES * 16));
+#pragma unroll 1
+            for (int x = 0; x < N; x += TMA_BOX_ROWS)
+                tma_load_3d(stage + (size_t)x * CW, &A.tmap, 2 * g * CW, m, x, &full_bar);
+        }
+    };
+    int g = (int)(blockIdx.x % (unsigned)A.groups), m = (int)(blockIdx.x / (unsigned)A.groups);
+    int g_next = g, m_next = m;
+    unsigned parity = 0;
+    if (tid == 0)
+        issue(g, m);
+    if (half == 1)
+        __nanosleep(A.halves_delay_ns);                              // half a tile behind from the start
+    for (; m < A.n_mid; g = g_next, m = m_next) {
+        advance(g_next, m_next);
+        const int kz = g * CW + col;
+        const bool valid = kz < A.nc;
+        int kj = A.mid0 + m;
+        kj = kj <= A.dims / 2 ? kj : kj - A.dims;                    // KVAL, powerspectrum.c:33
+        cd v[EPT], w[EPT];
+        mbar_wait(&full_bar, parity);
+#pragma unroll
+        for (int i = 0; i < EPT; i++)
+            v[i] = valid ? stage[PL::load_n(t, i) * CW + col] : make_double2(0.0, 0.0);
+        loads_landed(v);
+        mbar_arrive(&empty_bar);                                     // this thread's columns have left the tile buffer
+        // The next tile is asked for by the half that runs behind: when it has taken its columns the leading half
+        // has long taken its own, so nobody waits here -- and the leading half never waits for the follower.
+        if (tid == HT) {
+            mbar_wait(&empty_bar, parity);
+            issue(g_next, m_next);
+        }
+        parity ^= 1u;
+        PL::pass1(v, t, A.tw);
+        hsync();                                                     // this half's previous bin walk has left P
+        exchange<N, C, false, PL::ONE_UNIT2>(E, v, w, c, [&](int i) { return t + PL::ex1_w_part(i); },
+                       [&](int i) { return b_ex1r + PL::ex1_r_part(i); }, hsync);
+        PL::pass2(w, t, A.tw);
+        hsync();
+        exchange<N, C, PL::ONE_UNIT2, false>(E, w, v, c, [&](int i) { return b_ex2w[(i % R2) & 3] + PL::ex2_w_part(i); },
+                       [&](int i) { return b_ex2r[(i % R3) & 3] + PL::ex2_r_part(i); }, hsync);
+        PL::pass3(v);
+        hsync();
+#pragma unroll
+        for (int i = 0; i < EPT; i++)
+            P[PL::slot(kb + PL::out_k_part(i)) * C + c] = fma(v[i].x, v[i].x, v[i].y * v[i].y);
+        hsync();
+        if (valid)
+            bin_walk<PL>(P, t, c, kj, kz, A.dims / 2, sW, sT, A.nrbins, A.half_bpu, hist, 2);
+    }
+    __syncthreads();
+    for (int i = tid; i < A.nrbins; i += 2 * HT) {
+        const double sum = sP[2 * i] + sP[2 * i + 1];
         if (sum != 0.0)
             atomicAdd(&A.sums[i], sum);
     }
@@ -528,6 +644,27 @@ int fftx_power_raw(genpk_ctx *ctx, const double *spec_yz, int n_mid, int mid0, i
     typedef Plan<16, 8, 8, 4096> P1024;
     typedef Plan<16, 16, 8, 8192> P2048;
     typedef Plan<16, 8, 8, 8192> P1024W;
+    if (A.dims == 1024 && ctx->fused_xpass == 3 && ctx->use_tma && tmap_encoder()) {
+        // two halves of 256 threads on one 8192-mode tile (see fftx_power_halves_kernel)
+        tiles(2 * P1024::C);
+        if (A.use_tma) {
+            A.zero_after = 0;
+            if (zero_after) *zero_after = false;
+            auto kern = fftx_power_halves_kernel<P1024>;
+            const char *dl = getenv("GENPK_XHALVES_DELAY_NS");
+            A.halves_delay_ns = dl ? atoi(dl) : 3000;
+            const size_t smem2 = (size_t)8192 * 24 + (size_t)nrbins * 16 + (size_t)(nrbins + 1) * 4 + (size_t)(A.dims / 2 + 1) * 4 + 16;
+            if (smem2 + 256 <= (size_t)ctx->smem_optin) {
+                GENPK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+                long long ctas = ctx->sm_count;
+                if (ctas > A.n_tiles) ctas = A.n_tiles;
+                kern<<<(int)ctas, 2 * P1024::THREADS, smem2, ctx->stream>>>(A);
+                ctx->launches++;
+                GENPK_CUDA_OK(cudaGetLastError());
+                return 0;
+            }
+        }
+    }
     if (A.dims == 1024 && fftx_tile_modes(ctx) == 8192) {
         tiles(P1024W::C);
         return launch_fftx<P1024W>(ctx, A, smem);
