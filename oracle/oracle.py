@@ -89,6 +89,16 @@ class Oracle:
         self._powerspectrum.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_int, _f64p, _i32p, _f64p,
                                         C.c_double, C.c_double]
 
+    # -- print_pk(), utils.cpp:7-21 (the reference's own object code; reference kind only) ------
+    def print_pk(self, filename, nrbins, keffs, power, count):
+        if self.kind != "reference":
+            raise RuntimeError("print_pk: only the reference's objects carry it")
+        f = self.lib.ref_print_pk
+        f.restype = C.c_int
+        f.argtypes = [C.c_char_p, C.c_int, _f64p, _f64p, _i32p]
+        return f(str(filename).encode(), int(nrbins), np.ascontiguousarray(keffs, np.float64),
+                 np.ascontiguousarray(power, np.float64), np.ascontiguousarray(count, np.int32))
+
     # -- fieldize(), fieldize.cpp:46 ------------------------------------------------
     def fieldize(self, boxsize, dims, out, positions, masses=None, mass=1.0, extra=1):
         positions = np.ascontiguousarray(positions, dtype=np.float32)

@@ -72,6 +72,12 @@ def test_config1_per_type_spectra(tmp_path):
         assert path.exists()
         assert_file_matches(path, gold[f"power{t}"], gold[f"count{t}"], gold[f"keffs{t}"])
         assert len(open(path).read().splitlines()) == 29
+        if have_reference():
+            # SURVEY 7 protocol (4): byte for byte the file the reference's own print_pk() writes for its own spectrum
+            # (our P(k) agrees with it to ~1e-12, far inside the seven digits of "%e")
+            want = tmp_path / f"ref-PK-{TYPE_STR[t]}"
+            Oracle("reference").print_pk(want, len(gold[f"power{t}"]), gold[f"keffs{t}"], gold[f"power{t}"], gold[f"count{t}"])
+            assert open(path, "rb").read() == open(want, "rb").read(), f"PK file of type {t} differs from the reference's bytes"
     rep = json.load(open(tmp_path / "t.json"))
     assert rep["grid"] == 32 and [s["type"] for s in rep["spectra"]] == ["by", "DM", "st"]
     # deterministic mode gives the same files to print precision
