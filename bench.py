@@ -88,6 +88,7 @@ def parse_args():
     ap.add_argument("--check-mass", action="store_true",
                     help="before timing: one deposit (+ ghost exchange), the grid must sum to the particle count")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--xpass-two-pass", action="store_true", help="fused x pass at 1024: two-pass plan, 32 modes per thread, one exchange")
     ap.add_argument("--xpass-halves", action="store_true", help="fused x pass at 1024: two halves of 256 threads out of step on one tile")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-spread", action="store_true", help="rank r uses GPU r instead of GPUs spread over the visible ones")
@@ -460,6 +461,8 @@ def run_ours(args):
         ctx.set_option(api.OPT_FUSED_XPASS, 2)
     elif args.xpass_halves:
         ctx.set_option(api.OPT_FUSED_XPASS, 3)
+    elif args.xpass_two_pass:
+        ctx.set_option(api.OPT_FUSED_XPASS, 4)
     if args.no_own_ypass:
         ctx.set_option(api.OPT_OWN_YPASS, 0)
     if args.no_tma:

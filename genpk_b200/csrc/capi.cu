@@ -247,7 +247,7 @@ int genpk_set_option(genpk_ctx *ctx, int option, int64_t value)
         ctx->zero_after_power = (int)value;
         return 0;
     case GENPK_OPT_FUSED_XPASS:
-        if (value < 0 || value > 3) break;
+        if (value < 0 || value > 4) break;
         ctx->fused_xpass = (int)value;
         return 0;
     case GENPK_OPT_F64_POSITIONS:

@@ -76,6 +76,33 @@ FX_HD cd csqr(cd a)
 // products along the binary digits of k: at most five roundings deep).  One table lookup per butterfly unit instead
 // of R-1: the scattered 16-byte twiddle loads were a third of the kernels' load/store wavefronts and most of their
 // scoreboard stalls (profiles/r02/README.md).
+// v[k] *= w^k for k = 1 .. 31: w^k = (w^8)^(k/8) * w^(k%8), ten powers kept, at most five roundings deep
+FX_HD void mul_twiddle_powers32(cd *v, cd w)
+{
+    cd b[8], a[4];
+    b[1] = w;
+    b[2] = csqr(w);
+    b[3] = cmul(b[2], w);
+    b[4] = csqr(b[2]);
+    b[5] = cmul(b[4], w);
+    b[6] = csqr(b[3]);
+    b[7] = cmul(b[6], w);
+    a[1] = csqr(b[4]);
+    a[2] = csqr(a[1]);
+    a[3] = cmul(a[2], a[1]);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 1; k < 32; k++) {
+        const int hi = k / 8, lo = k % 8;
+        cd t;
+        if (hi == 0) t = b[lo];
+        else if (lo == 0) t = a[hi];
+        else t = cmul(a[hi], b[lo]);
+        v[k] = cmul(v[k], t);
+    }
+}
+
 template <int R> FX_HD void mul_twiddle_powers(cd *v, cd w)
 {
     static_assert(R == 2 || R == 4 || R == 8 || R == 16, "radix");
@@ -109,11 +136,24 @@ template <int R> FX_HD void mul_twiddle_powers(cd *v, cd w)
     }
 }
 
+// a * exp(-2 pi i K/32), K in [0, 16): the even ones are the sixteenth roots above
+template <int K> FX_HD cd mulw32(cd a)
+{
+    static_assert(K >= 0 && K < 16, "first half turn");
+    if (K % 2 == 0)
+        return mulw16<K / 2>(a);
+    constexpr double cs[16][2] = {{1.00000000000000000000, 0.00000000000000000000}, {0.98078528040323043058, 0.19509032201612824808}, {0.92387953251128673848, 0.38268343236508978178}, {0.83146961230254523567, 0.55557023301960217765}, {0.70710678118654757274, 0.70710678118654746172}, {0.55557023301960228867, 0.83146961230254523567}, {0.38268343236508983729, 0.92387953251128673848}, {0.19509032201612833135, 0.98078528040323043058}, {0.00000000000000006123, 1.00000000000000000000}, {-0.19509032201612819257, 0.98078528040323043058}, {-0.38268343236508972627, 0.92387953251128673848}, {-0.55557023301960195560, 0.83146961230254545772}, {-0.70710678118654746172, 0.70710678118654757274}, {-0.83146961230254534669, 0.55557023301960217765}, {-0.92387953251128673848, 0.38268343236508989280}, {-0.98078528040323043058, 0.19509032201612860891}};
+    cd r;
+    r.x = a.x * cs[K][0] + a.y * cs[K][1];
+    r.y = a.y * cs[K][0] - a.x * cs[K][1];
+    return r;
+}
+
 template <int R> struct Dft;
 template <int R, int K> struct Comb {
     static FX_HD void run(cd *v, const cd *e, const cd *o)
     {
-        const cd t = mulw16<K * (16 / R)>(o[K]);
+        const cd t = mulw32<K * (32 / R)>(o[K]);
         v[K] = cadd(e[K], t);
         v[K + R / 2] = csub(e[K], t);
         Comb<R, K - 1>::run(v, e, o);
@@ -260,6 +300,42 @@ template <int R1_, int R2_, int R3_, int TILE_> struct Plan {
     static FX_HD bool out_k_upper(int i) { return (i % R3) >= R3 / 2; }
     // where |X[k]|^2 waits for the bin walk (bank swizzle only; any bijection is correct)
     static FX_HD int slot(int k) { return k ^ (((k >> 3) ^ (R1 == 8 ? 0 : (k >> LOG_R1))) & 3); }
+};
+
+// Two-pass plan: N = 32 * R2 with 32 elements per thread -- one radix-32 pass, ONE exchange, one radix-R2 pass --
+// for the kernels that hold a tile with half as many threads and twice the registers (fftx_power2_kernel).
+//   n = R2*j + n2 (j < 32)      pass 1: DFT-32 over j, times W_N^(n2*k1)
+//   k = k1 + 32*k2              pass 2: DFT-R2 over n2
+template <int R2_, int TILE_> struct Plan2 {
+    static constexpr int R1 = 32, R2 = R2_;
+    static constexpr int EPT2 = 32;
+    static constexpr int N = R1 * R2;
+    static constexpr int TILE = TILE_;
+    static constexpr int THREADS = TILE / EPT2;
+    static constexpr int T = N / EPT2;            // threads per column
+    static constexpr int C = TILE / N;
+    static constexpr int LOG_R1 = 5;
+    static_assert(R2 == 16 || R2 == 32, "N = 512 or 1024");
+    static_assert(T == R2, "a thread owns n2 = t in pass 1");
+    static FX_HD int load_n(int t, int i) { return R2 * i + t; }
+    static FX_HD void pass1(cd *v, int t, const cd *tw)
+    {
+        Dft<32>::run(v);
+        mul_twiddle_powers32(v, tw[t]);                              // W_N^(n2*k1), n2 = t
+    }
+    // exchange: y[k1][n2] at k1*R2 + n2
+    static FX_HD int ex_w(int t, int i) { return i * R2 + t; }
+    // pass 2: EPT2/R2 units; unit u of thread t works on k1 = t + T*u
+    static FX_HD int ex_r(int t, int i) { return (t + T * (i / R2)) * R2 + (i % R2); }
+    static FX_HD void pass2(cd *w)
+    {
+#pragma unroll
+        for (int u = 0; u < EPT2 / R2; u++)
+            Dft<R2>::run(w + u * R2);
+    }
+    static FX_HD int out_k(int t, int i) { return t + T * (i / R2) + R1 * (i % R2); }
+    // where |X[k]|^2 waits for the bin walk: neighbouring blocks of 16 on opposite bank halves
+    static FX_HD int slot(int k) { return k ^ ((k >> 4) & 1); }
 };
 
 // ---------------------------------------------------------------------------------

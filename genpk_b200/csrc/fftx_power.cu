@@ -356,6 +356,118 @@ __global__ void __launch_bounds__(2 * PL::THREADS, 1) fftx_power_halves_kernel(c
 }
 
 // ---------------------------------------------------------------------------------
+// The x pass with the two-pass plan (fftx_core.cuh: Plan2): 32 modes per thread, a radix-32 register pass, ONE
+// exchange (through the tile buffer), a radix-R2 register pass -- half the threads of fftx_power_kernel with twice
+// the registers, a third less shared-memory traffic and half the barriers per tile (GENPK_OPT_FUSED_XPASS = 4).
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void loads_landed32(const fftx::cd *v)
+{
+#pragma unroll
+    for (int i = 0; i < 32; i += 4)
+        asm volatile("" ::"d"(v[i].x), "d"(v[i].y), "d"(v[i + 1].x), "d"(v[i + 1].y), "d"(v[i + 2].x), "d"(v[i + 2].y),
+                     "d"(v[i + 3].x), "d"(v[i + 3].y)
+                     : "memory");
+}
+
+template <class PL>
+__global__ void __launch_bounds__(PL::THREADS, 1) fftx_power2_kernel(const __grid_constant__ FftxArgs A)
+{
+    constexpr int N = PL::N, C = PL::C, TILE_MODES = PL::TILE, CTA_THREADS = PL::THREADS, E2 = PL::EPT2;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    cd *const stage = reinterpret_cast<cd *>(smem_raw);                                 // [N][C], the next tile
+    cd *const E = reinterpret_cast<cd *>(smem_raw + (size_t)TILE_MODES * 16);           // [N/2][C] complex exchange
+    double *const P = reinterpret_cast<double *>(E);                                    // [N][C] |X|^2, same bytes
+    double *const sP = reinterpret_cast<double *>(smem_raw + (size_t)TILE_MODES * 24);  // [nrbins][hists]
+    unsigned *const sT = reinterpret_cast<unsigned *>(sP + (size_t)A.nrbins * A.hists); // nrbins + 1
+    float *const sW = reinterpret_cast<float *>(sT + A.nrbins + 1);                     // dims/2 + 1
+    __shared__ __align__(8) unsigned long long tile_bar;
+
+    const int tid = threadIdx.x;
+    const int c = tid % C, t = tid / C;
+    for (int i = tid; i < A.nrbins * A.hists; i += CTA_THREADS)
+        sP[i] = 0.0;
+    for (int i = tid; i <= A.nrbins; i += CTA_THREADS)
+        sT[i] = A.thresh[i];
+    for (int i = tid; i <= N / 2; i += CTA_THREADS)
+        sW[i] = A.iw1d[i];
+    if (tid == 0) {
+        mbar_init(&tile_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    double *const hist = sP + (c & (A.hists - 1));
+    const int step_g = (int)(gridDim.x % (unsigned)A.groups), step_m = (int)(gridDim.x / (unsigned)A.groups);
+    auto advance = [&](int &g, int &m) {
+        g += step_g;
+        m += step_m;
+        if (g >= A.groups) {
+            g -= A.groups;
+            m++;
+        }
+    };
+    auto issue = [&](int g, int m) {
+        if (tid == 0 && m < A.n_mid) {
+            mbar_expect_tx(&tile_bar, (unsigned)(TILE_MODES * 16));
+#pragma unroll 1
+            for (int x = 0; x < N; x += TMA_BOX_ROWS)
+                tma_load_3d(stage + (size_t)x * C, &A.tmap, 2 * g * C, m, x, &tile_bar);
+        }
+    };
+    int g = (int)(blockIdx.x % (unsigned)A.groups), m = (int)(blockIdx.x / (unsigned)A.groups);
+    int g_next = g, m_next = m;
+    unsigned parity = 0;
+    issue(g, m);
+    for (; m < A.n_mid; g = g_next, m = m_next) {
+        advance(g_next, m_next);
+        const int kz = g * C + c;
+        const bool valid = kz < A.nc;
+        int kj = A.mid0 + m;
+        kj = kj <= A.dims / 2 ? kj : kj - A.dims;                    // KVAL, powerspectrum.c:33
+        cd v[E2];
+        mbar_wait(&tile_bar, parity);
+        parity ^= 1u;
+#pragma unroll
+        for (int i = 0; i < E2; i++)
+            v[i] = valid ? stage[PL::load_n(t, i) * C + c] : make_double2(0.0, 0.0);
+        PL::pass1(v, t, A.tw);
+        __syncthreads();                                             // everyone has taken its part of the tile
+        // The exchange goes through the tile buffer itself, all 32 registers at once: with 32 modes per thread there
+        // are no registers for a second copy, which an exchange through a half-size buffer needs (a thread would
+        // receive while it still holds what it has not sent).  The next tile is asked for once the buffer has been
+        // read back; its fill runs under the second pass and the bin walk.
+#pragma unroll
+        for (int i = 0; i < E2; i++)
+            stage[PL::ex_w(t, i) * C + c] = v[i];
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < E2; i++)
+            v[i] = stage[PL::ex_r(t, i) * C + c];
+        loads_landed32(v);
+        __syncthreads();
+        if (tid == 0)
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue(g_next, m_next);
+        PL::pass2(v);
+#pragma unroll
+        for (int i = 0; i < E2; i++)
+            P[PL::slot(PL::out_k(t, i)) * C + c] = fma(v[i].x, v[i].x, v[i].y * v[i].y);
+        __syncthreads();
+        if (valid) {
+            bin_walk<PL>(P, 2 * t, c, kj, kz, A.dims / 2, sW, sT, A.nrbins, A.half_bpu, hist, A.hists);
+            bin_walk<PL>(P, 2 * t + 1, c, kj, kz, A.dims / 2, sW, sT, A.nrbins, A.half_bpu, hist, A.hists);
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < A.nrbins; i += CTA_THREADS) {
+        double sum = 0.0;
+        for (int j = 0; j < A.hists; j++)
+            sum += sP[i * A.hists + j];
+        if (sum != 0.0)
+            atomicAdd(&A.sums[i], sum);
+    }
+}
+
+// ---------------------------------------------------------------------------------
 // The same tile machinery as a plain in-place column transform: length-N FFTs along the
 // MIDDLE axis (y) of [n_planes][N][nc] complex planes, i.e. the y pass of the (y,z)
 // transform after cuFFT's batched 1-D r2c along z.  Reads and writes every mode once in
@@ -644,6 +756,22 @@ int fftx_power_raw(genpk_ctx *ctx, const double *spec_yz, int n_mid, int mid0, i
     typedef Plan<16, 8, 8, 4096> P1024;
     typedef Plan<16, 16, 8, 8192> P2048;
     typedef Plan<16, 8, 8, 8192> P1024W;
+    if (A.dims == 1024 && ctx->fused_xpass == 4 && ctx->use_tma && tmap_encoder()) {
+        typedef Plan2<32, 8192> Q1024;
+        tiles(Q1024::C);
+        if (A.use_tma) {
+            A.zero_after = 0;
+            if (zero_after) *zero_after = false;
+            auto kern = fftx_power2_kernel<Q1024>;
+            GENPK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            long long ctas = ctx->sm_count;
+            if (ctas > A.n_tiles) ctas = A.n_tiles;
+            kern<<<(int)ctas, Q1024::THREADS, smem, ctx->stream>>>(A);
+            ctx->launches++;
+            GENPK_CUDA_OK(cudaGetLastError());
+            return 0;
+        }
+    }
     if (A.dims == 1024 && ctx->fused_xpass == 3 && ctx->use_tma && tmap_encoder()) {
         // two halves of 256 threads on one 8192-mode tile (see fftx_power_halves_kernel)
         tiles(2 * P1024::C);

@@ -104,7 +104,8 @@ extern "C" {
 #define GENPK_OPT_FUSED_XPASS    8     /* 1 (default): last FFT pass and binning in one kernel when the
                                           grid side allows; 0: always cuFFT's x pass + the binning pass;
                                           2: as 1 with 4096-mode tiles at 1024 (measurements);
-                                          3: at 1024, the CTA as two halves of 256 threads out of step on one 8192-mode tile */
+                                          3: at 1024, the CTA as two halves of 256 threads out of step on one 8192-mode tile;
+                                          4: at 1024, the two-pass plan (32 modes per thread, one exchange, 256 threads) */
 
 #define GENPK_OPT_TMA           24     /* 1 (default): the column kernels (y pass, fused x pass) fill their shared-memory tiles with
                                           TMA bulk tensor copies behind an mbarrier; 0: per-thread cp.async (measurements) */

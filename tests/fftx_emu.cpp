@@ -251,3 +251,66 @@ extern "C" int fftx_emu_rows(int n, double *rows, const double *twiddle, const d
     }
     return -1;
 }
+
+// ---- one tile of fftx_power2_kernel: the two-pass plan (32 elements per thread, one exchange) ----
+template <class PL>
+static int emu_tile2(const double *tile_in, const double *twiddle, double *spec_out, int kj, int kz0, int nc, const float *sW,
+                     const unsigned *sT, int nrbins, float half_bpu, double *sP)
+{
+    constexpr int N = PL::N, C = PL::C, E2 = PL::EPT2;
+    const cd *in = reinterpret_cast<const cd *>(tile_in);        // [N][C]
+    const cd *tw = reinterpret_cast<const cd *>(twiddle);        // [N]
+    std::vector<cd> regs((size_t)PL::THREADS * E2), X((size_t)N * C);
+    std::vector<double> P((size_t)N * C);
+    for (int tid = 0; tid < PL::THREADS; tid++) {
+        const int c = tid % C, t = tid / C;
+        cd *v = &regs[(size_t)tid * E2];
+        for (int i = 0; i < E2; i++)
+            v[i] = in[(size_t)PL::load_n(t, i) * C + c];
+        PL::pass1(v, t, tw);
+    }
+    std::vector<char> hit((size_t)N * C, 0);
+    for (int tid = 0; tid < PL::THREADS; tid++)
+        for (int i = 0; i < E2; i++) {
+            const size_t at = (size_t)PL::ex_w(tid / C, i) * C + tid % C;
+            if (hit[at]) return 30;                              // the exchange map is a bijection per column
+            hit[at] = 1;
+            X[at] = regs[(size_t)tid * E2 + i];
+        }
+    std::fill(hit.begin(), hit.end(), 0);
+    for (int tid = 0; tid < PL::THREADS; tid++) {
+        const int c = tid % C, t = tid / C;
+        cd w[E2];
+        for (int i = 0; i < E2; i++)
+            w[i] = X[(size_t)PL::ex_r(t, i) * C + c];
+        PL::pass2(w);
+        for (int i = 0; i < E2; i++) {
+            const int k = PL::out_k(t, i);
+            if (k < 0 || k >= N || hit[(size_t)k * C + c]) return 31;
+            hit[(size_t)k * C + c] = 1;
+            spec_out[2 * ((size_t)k * C + c)] = w[i].x;
+            spec_out[2 * ((size_t)k * C + c) + 1] = w[i].y;
+            const int sl = PL::slot(k);
+            if (sl < 0 || sl >= N) return 32;
+            P[(size_t)sl * C + c] = w[i].x * w[i].x + w[i].y * w[i].y;
+        }
+    }
+    // a thread walks two blocks of eight |kx|: 8*(2t) .. and 8*(2t+1) ..
+    for (int tid = 0; tid < PL::THREADS; tid++) {
+        const int c = tid % C, t = tid / C;
+        if (kz0 + c < nc)
+            for (int h = 0; h < 2; h++)
+                bin_walk<PL>(P.data(), 2 * t + h, c, kj, kz0 + c, N / 2, sW, sT, nrbins, half_bpu, sP, 1);
+    }
+    return 0;
+}
+
+extern "C" int fftx_emu_tile2(int n, const double *tile_in, const double *twiddle, double *spec_out, int kj, int kz0, int nc,
+                              const float *sW, const unsigned *sT, int nrbins, float half_bpu, double *sP)
+{
+    switch (n) {
+    case 512: return emu_tile2<Plan2<16, 4096>>(tile_in, twiddle, spec_out, kj, kz0, nc, sW, sT, nrbins, half_bpu, sP);
+    case 1024: return emu_tile2<Plan2<32, 8192>>(tile_in, twiddle, spec_out, kj, kz0, nc, sW, sT, nrbins, half_bpu, sP);
+    }
+    return -1;
+}

@@ -122,3 +122,35 @@ def test_row_tile_is_the_real_transform(emu, plan):
     scale = np.abs(ref).max(axis=1, keepdims=True)
     assert (np.abs(got - ref) <= 1e-13 * scale).all()
     assert (got[:, 0].imag == 0).all() and (got[:, -1].imag == 0).all()
+
+
+@pytest.mark.parametrize("n", [512, 1024])
+@pytest.mark.parametrize("kj,kz0", [(0, 0), (-3, 8), (5, None)])
+def test_two_pass_tile_fft_and_bins(emu, n, kj, kz0):
+    """The two-pass plan (Plan2: radix 32, one exchange, 32 elements per thread) of fftx_power2_kernel against numpy.fft
+    and the direct bins, tile of 8 columns."""
+    emu.fftx_emu_tile2.restype = ctypes.c_int
+    ncols, nc = 8, n // 2 + 1
+    if kz0 is None:
+        kz0 = (nc // ncols) * ncols
+    rng = np.random.default_rng(3 * n + 7 * kj + kz0)
+    tile = rng.standard_normal((n, ncols)) + 1j * rng.standard_normal((n, ncols))
+    tile *= np.exp(rng.uniform(-6, 6, (n, 1)))
+    tw = np.ascontiguousarray(np.exp(-2j * np.pi * np.arange(n) / n))
+    nrbins = n
+    thresh, iw = _tables(n, nrbins)
+    half_bpu = np.float32(0.5 * (nrbins - 1) / np.log(np.sqrt(3.0) * n / 2.0))
+    spec = np.zeros((n, ncols), dtype=np.complex128)
+    sp = np.zeros(nrbins)
+    tin = np.ascontiguousarray(tile)
+    rc = emu.fftx_emu_tile2(ctypes.c_int(n), tin.ctypes.data_as(ctypes.c_void_p), tw.ctypes.data_as(ctypes.c_void_p),
+                            spec.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(kj), ctypes.c_int(kz0), ctypes.c_int(nc),
+                            iw.ctypes.data_as(ctypes.c_void_p), thresh.ctypes.data_as(ctypes.c_void_p),
+                            ctypes.c_int(nrbins), ctypes.c_float(half_bpu), sp.ctypes.data_as(ctypes.c_void_p))
+    assert rc == 0
+    ref = np.fft.fft(tile, axis=0)
+    assert np.abs(spec - ref).max() <= 1e-13 * np.abs(ref).max()
+    want = _direct_bins(ref, n, kj, kz0, nc, thresh, iw, nrbins)
+    nz = want > 0
+    assert np.array_equal(sp > 0, nz)
+    assert np.allclose(sp[nz], want[nz], rtol=1e-11, atol=0)

@@ -41,7 +41,7 @@ def test_fused_vs_oracle_256(ref, port):
 
 
 @pytest.mark.parametrize("dims,nrbins,tile", [(256, 256, 1), (256, 37, 1), (512, 512, 1), (1024, 1024, 1), (1024, 1024, 2),
-                                              (1024, 1024, 3), (1024, 77, 3)])
+                                              (1024, 1024, 3), (1024, 77, 3), (1024, 1024, 4), (1024, 77, 4)])
 def test_fused_vs_unfused(dims, nrbins, tile):
     box, n = 1000.0, 400000
     pos, _ = _particles(n, box, dims)
