@@ -341,12 +341,15 @@ struct Timing {
     float zero = 0, deposit = 0, fft = 0, power = 0;
 };
 
+// Stage times of everything since the last genpk_stage_reset (all the chunks of a type, not the last one).  With
+// --gpus N these are the times of the first GPU's slab.
 static void stage_times(genpk_ctx *ctx, Timing *t)
 {
-    genpk_stage_ms(ctx, GENPK_STAGE_ZERO, &t->zero);
-    genpk_stage_ms(ctx, GENPK_STAGE_DEPOSIT, &t->deposit);
-    genpk_stage_ms(ctx, GENPK_STAGE_FFT, &t->fft);
-    genpk_stage_ms(ctx, GENPK_STAGE_POWER, &t->power);
+    int64_t records = 0;
+    genpk_stage_total_ms(ctx, GENPK_STAGE_ZERO, &t->zero, &records);
+    genpk_stage_total_ms(ctx, GENPK_STAGE_DEPOSIT, &t->deposit, &records);
+    genpk_stage_total_ms(ctx, GENPK_STAGE_FFT, &t->fft, &records);
+    genpk_stage_total_ms(ctx, GENPK_STAGE_POWER, &t->power, &records);
 }
 
 static double now_ms()
@@ -514,6 +517,7 @@ int main(int argc, char *argv[])
                 continue;
             Timing t;
             t.label = type_str(type);
+            genpk_stage_reset(ctx);
             const double t0 = now_ms();
             if (multi)
                 genpk_multi_grid_zero(multi);
@@ -568,6 +572,7 @@ int main(int argc, char *argv[])
                 continue;
             Timing t;
             t.label = "x" + type_str(type);
+            genpk_stage_reset(ctx);
             const double t0 = now_ms();
             genpk_grid_zero(ctx, 0);
             genpk_grid_zero(ctx, 1);
@@ -591,6 +596,7 @@ int main(int argc, char *argv[])
         }
         Timing t;
         t.label = "DMx" + type_str(crosstype);
+        genpk_stage_reset(ctx);
         const double t0 = now_ms();
         genpk_grid_zero(ctx, 0);
         genpk_grid_zero(ctx, 1);
