@@ -167,7 +167,7 @@ struct genpk_ctx {
     int coop_launch = 0;                      // cudaDevAttrCooperativeLaunch
     int *d_rows_done = nullptr;
     int rows_done_n = 0;
-    int own_ypass = 1;                        // 1: (y,z) transform = cuFFT 1-D r2c along z + fft_cols_kernel along y
+    int own_ypass = 1;                        // 1: (y,z) transform on our own kernels (fft_zy_kernel; with fused_zy = 0: cuFFT 1-D r2c along z + fft_cols_kernel)
     int smem_optin = 0;                       // opt-in shared memory per CTA of this device
     double *d_twiddle = nullptr;              // exp(-2 pi i t/dims), t < dims
     // transpose fused into the y pass: every rank's [dims][ny][nc] block (own entry = d_recv)

@@ -97,9 +97,10 @@ extern "C" {
 #define GENPK_OPT_FFT_YZ_BATCH   9     /* x planes per 2-D cuFFT call of the (y,z) transform; groups of a few
                                           planes keep the z pass's output in L2 for the y pass (0 = all
                                           planes in one call; must divide the local plane count) */
-#define GENPK_OPT_OWN_YPASS     10     /* 1 (default): the batched (y,z) transform (genpk_slab_fft_yz, genpk_fft_power) is
-                                          cuFFT's 1-D r2c along z + our in-place column pass along y for grid sides
-                                          256/512/1024/2048; 0: cuFFT's 2-D plan */
+#define GENPK_OPT_OWN_YPASS     10     /* 1 (default): the (y,z) transform (genpk_slab_fft_yz, genpk_fft_power) runs on our own kernels
+                                          for grid sides 256/512/1024/2048 -- the fused kernel of GENPK_OPT_FUSED_ZY, or with
+                                          that option off cuFFT's 1-D r2c along z + our in-place column pass along y;
+                                          0: cuFFT's 2-D plan */
 /* ---- fused x pass (genpk_fft_power, genpk_slab_fftx_power_partial) ------------------ */
 #define GENPK_OPT_FUSED_XPASS    8     /* 1 (default): last FFT pass and binning in one kernel when the
                                           grid side allows; 0: always cuFFT's x pass + the binning pass;
