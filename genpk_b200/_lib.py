@@ -99,6 +99,7 @@ SIGNATURES = {
     "genpk_multi_pk_from_particles": (C.c_int, [C.c_void_p, c_f32p, c_f32p, C.c_int64, C.c_double, C.c_double, C.c_double,
                                                 C.c_int, c_f64p, c_i32p, c_f64p]),
     "genpk_power_finalize": (C.c_int, [c_f64p, C.c_int, C.c_double, C.c_double, c_f64p, c_i32p, c_f64p]),
+    "genpk_rebin_min_modes": (C.c_int, [C.c_int, c_f64p, c_i32p, c_f64p, C.c_int64]),
     "genpk_bin_thresholds": (C.c_int, [C.c_int, C.c_int, C.c_uint, C.c_void_p]),
     # synthetic particle sets
     "genpk_synth_particles": (C.c_int, [C.c_int, C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_double,

@@ -65,6 +65,19 @@ def type_str(ptype: int) -> str:
     return {0: "by", 1: "DM", 2: "nu", 4: "st"}.get(ptype, "xx")
 
 
+def rebin_min_modes(power, count, keffs, min_modes: int):
+    """Merge neighbouring bins until each holds at least min_modes modes (the reference's to-do, gen-pk.cpp:27-31);
+    mode-weighted means.  Returns new (power, count, keffs) arrays of the merged length."""
+    lib = _lib.load()
+    p = np.ascontiguousarray(power, np.float64).copy()
+    c = np.ascontiguousarray(count, np.int32).copy()
+    k = np.ascontiguousarray(keffs, np.float64).copy()
+    n = lib.genpk_rebin_min_modes(len(p), p.ctypes.data, c.ctypes.data, k.ctypes.data, int(min_modes))
+    if n < 0:
+        raise _lib.GenPKError("genpk_rebin_min_modes: " + _lib.last_error())
+    return p[:n], c[:n], k[:n]
+
+
 def print_pk(filename: str, nrbins: int, keffs, power, count) -> int:
     """Three-column text output of utils.cpp:7-21 ("%e\\t%e\\t%d\\n" for non-empty bins)."""
     try:

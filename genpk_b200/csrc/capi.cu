@@ -545,6 +545,56 @@ int genpk_power_finalize(const double *sums, int nrbins, double total_mass, doub
     return 0;
 }
 
+int genpk_rebin_min_modes(int nrbins, double *power, int *count, double *keffs, int64_t min_modes)
+{
+    if (nrbins < 1 || !power || !count || !keffs) { set_error("genpk_rebin_min_modes: bad arguments"); return -1; }
+    int out = 0, merged = 0, only = -1;                      // input bins in the open output bin; the bin if there is one
+    double p_sum = 0, k_sum = 0;
+    long long n_sum = 0;
+    auto close = [&]() {
+        if (merged == 1) {                                   // a bin on its own keeps its values bit for bit
+            power[out] = power[only];
+            keffs[out] = keffs[only];
+        } else {
+            power[out] = p_sum / (double)n_sum;
+            keffs[out] = k_sum / (double)n_sum;
+        }
+        count[out] = (int)n_sum;
+        out++;
+        p_sum = k_sum = 0;
+        n_sum = 0;
+        merged = 0;
+    };
+    auto add = [&](int b) {
+        const double c = (double)count[b];
+        p_sum += c * power[b];                               // = the raw sum over the bin's modes / (tm1 * tm2)
+        k_sum += c * keffs[b];
+        n_sum += count[b];
+        merged++;
+        only = b;
+    };
+    for (int b = 0; b < nrbins; b++) {
+        if (count[b] <= 0)
+            continue;
+        add(b);                                              // (b >= out: nothing that is still to be read is overwritten)
+        if (n_sum >= min_modes)
+            close();
+    }
+    if (n_sum > 0) {                                         // a short tail joins the last full bin
+        if (out > 0) {
+            out--;
+            add(out);
+            merged++;                                        // (never a bin on its own)
+        }
+        close();
+    }
+    for (int b = out; b < nrbins; b++) {
+        power[b] = keffs[b] = 0;
+        count[b] = 0;
+    }
+    return out;
+}
+
 static int power_on(genpk_ctx *ctx, const double *spec_a, const double *spec_b, int nrbins, double *power, int *count,
                     double *keffs, double total_mass, double total_mass2)
 {

@@ -58,6 +58,10 @@ static std::string type_str(int type)       // utils.cpp:57-72
     }
 }
 
+// Post-processing beyond the reference (its own to-do list, gen-pk.cpp:27-31); both off by default.
+static int64_t g_min_modes = 0;      // --min-modes N: neighbouring bins merged until each holds >= N modes
+static int g_fold = 1;               // --fold F: the box folded F times onto itself (small-scale power): k_eff scales by F
+
 static int print_pk(const std::string &filename, int nrbins, const double *keffs, const double *power, const int *count)
 {
     FILE *fd = fopen(filename.c_str(), "w");     // utils.cpp:7-21
@@ -65,9 +69,14 @@ static int print_pk(const std::string &filename, int nrbins, const double *keffs
         fprintf(stderr, "Error opening file: %s\n", filename.c_str());
         return 0;
     }
-    for (int i = 0; i < nrbins; i++)
-        if (count[i])
-            fprintf(fd, "%e\t%e\t%d\n", keffs[i], power[i], count[i]);
+    std::vector<double> k(keffs, keffs + nrbins), p(power, power + nrbins);
+    std::vector<int> c(count, count + nrbins);
+    int nout = nrbins;
+    if (g_min_modes > 1)
+        nout = genpk_rebin_min_modes(nrbins, p.data(), c.data(), k.data(), g_min_modes);
+    for (int i = 0; i < nout; i++)
+        if (c[i])
+            fprintf(fd, "%e\t%e\t%d\n", k[i] * g_fold, p[i], c[i]);
     fclose(fd);
     return nrbins;
 }
@@ -84,6 +93,9 @@ static void help()
             "the CDM (type 1) (within the file specified by -i)\n"
             "-s (1,0) Determines whether stars are included in the baryon type.\n"
             "B200 extensions: -g dims | --fixed | --gpus N | --synthetic kind:n[:seed] | --json file | --info | --dump type file\n"
+            "  --min-modes N  merge neighbouring bins until each holds at least N modes\n"
+            "  --fold F       fold the box F times onto itself before the deposit (power at F times smaller scales;\n"
+            "                 k_eff is printed in fundamental modes of the full box)\n"
             "(HDF5 snapshots are not supported in this build: the image has no HDF5)\n");
 }
 
@@ -367,6 +379,7 @@ int main(int argc, char *argv[])
     static const option long_opts[] = {{"fixed", no_argument, nullptr, 1000},    {"synthetic", required_argument, nullptr, 1001},
                                        {"json", required_argument, nullptr, 1002}, {"info", no_argument, nullptr, 1003},
                                        {"dump", required_argument, nullptr, 1004}, {"gpus", required_argument, nullptr, 1005},
+                                       {"min-modes", required_argument, nullptr, 1006}, {"fold", required_argument, nullptr, 1007},
                                        {nullptr, 0, nullptr, 0}};
     int c;
     while ((c = getopt_long(argc, argv, "i:j:o:c:s:g:h", long_opts, nullptr)) != -1) {
@@ -387,6 +400,14 @@ int main(int argc, char *argv[])
                 dump_path = argv[optind++];
             break;
         case 1005: ngpus = atoi(optarg); break;
+        case 1006: g_min_modes = atoll(optarg); break;
+        case 1007:
+            g_fold = atoi(optarg);
+            if (g_fold < 1) {
+                fprintf(stderr, "--fold wants a positive integer\n");
+                return 1;
+            }
+            break;
         case 'h':
         default:
             help();
@@ -426,7 +447,8 @@ int main(int argc, char *argv[])
     }
     if (!jinfiles.empty() && !open_source(jinfiles, &src2))
         return 1;
-    const double box = src.box;
+    // --fold F: the deposit wraps every position periodically (fieldize.cpp:70-75), so a box F times smaller IS the fold
+    const double box = src.box / g_fold;
 
     // ---- grid side: gen-pk.cpp:169-173 ---------------------------------------------------
     int64_t field_dims = 0;
@@ -533,7 +555,7 @@ int main(int argc, char *argv[])
                     status = 1;
                     break;
                 }
-                if (genpk_synth_particles(syn_kind, syn_seed, syn_side, 0, n, box, (double)field_dims, dpos, nullptr) ||
+                if (genpk_synth_particles(syn_kind, syn_seed, syn_side, 0, n, src.box, (double)field_dims, dpos, nullptr) ||
                     genpk_deposit(ctx, 0, dpos, nullptr, n, src.mass[type], box, 1) || genpk_synchronize(ctx)) {
                     fprintf(stderr, "synthetic deposit failed: %s\n", genpk_last_error());
                     status = 1;

@@ -403,6 +403,14 @@ int genpk_multi_pk_from_particles(genpk_multi *m, const float *positions, const 
 int genpk_power_finalize(const double *sums_host, int nrbins, double total_mass, double total_mass2,
                          double *power, int *count, double *keffs);
 
+/* Beyond the reference (its own to-do list, gen-pk.cpp:27-31: "rebinning for min modes/bin"): merge neighbouring
+ * bins of a finished spectrum, from low k upwards, until every output bin holds at least min_modes modes (a tail with
+ * fewer joins the last bin).  Merged values are the mode-weighted means, i.e. exactly what powerspectrum() would have
+ * produced with the wider bin: P = sum(count_i P_i) / sum(count_i), k_eff likewise.  In place; empty input bins are
+ * skipped.  Returns the number of output bins (<= nrbins), written to the front of the three arrays; the rest is
+ * zeroed.  Host only. */
+int genpk_rebin_min_modes(int nrbins, double *power, int *count, double *keffs, int64_t min_modes);
+
 /* Host-built bin edges the binning kernel consumes (plan-time table, no GPU
  * needed): thresh_out[b], b = 0..nrbins, is the smallest k2 = ki^2+kj^2+kz^2 >= 1
  * whose bin floor(binsperunit*log|k|) (powerspectrum.c:38,66) is >= b, and

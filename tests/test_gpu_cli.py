@@ -184,3 +184,30 @@ def test_synthetic_input_matches_the_library_pipeline(tmp_path):
         p, c, k = ctx.power(dims, float(n), float(n))
         ctx.synchronize()
     assert_file_matches(tmp_path / f"PK-DM-synthetic-clustered-{n_side}", p, c.astype(np.int64), k)
+
+
+@needs_snap
+def test_fold_and_min_modes_extensions(tmp_path, orc):
+    """Two items of the reference's own to-do list (gen-pk.cpp:27-31).  --fold F: the box folded F times onto itself is
+    the deposit with a box F times smaller (every position is wrapped periodically, fieldize.cpp:70-75), k_eff printed
+    in modes of the full box.  --min-modes N: neighbouring bins merged to at least N modes, mode-weighted means."""
+    gold = np.load(os.path.join(GOLD, "test_g2_snap.npz"))
+    box, dims, fold = float(gold["box"]), 32, 2
+    out = tmp_path / "fold"
+    out.mkdir()
+    gen_pk("-i", SNAP, "-o", str(out), "--fold", str(fold))
+    for t in (0, 1):
+        masses = gold[f"masses{t}"] if f"masses{t}" in gold else None
+        p, c, k = oracle_pk(orc, box / fold, dims, [(gold[f"pos{t}"], masses, float(gold["mass"][t]))], float(gold[f"total_mass{t}"]))
+        assert_file_matches(out / f"PK-{TYPE_STR[t]}-test_g2_snap", p, c, k * fold)
+    # merged bins: same modes, same mode-weighted sums as the unmerged file
+    plain, merged = tmp_path / "plain", tmp_path / "merged"
+    plain.mkdir()
+    merged.mkdir()
+    gen_pk("-i", SNAP, "-o", str(plain), "--fixed")
+    gen_pk("-i", SNAP, "-o", str(merged), "--fixed", "--min-modes", "500")
+    k0, p0, c0 = read_pk(plain / "PK-DM-test_g2_snap")
+    k1, p1, c1 = read_pk(merged / "PK-DM-test_g2_snap")
+    assert c1.sum() == c0.sum() == dims ** 3 - 1 and len(c1) < len(c0) and (c1 >= 500).all()
+    np.testing.assert_allclose((p1 * c1).sum(), (p0 * c0).sum(), rtol=1e-5)
+    np.testing.assert_allclose((k1 * c1).sum(), (k0 * c0).sum(), rtol=1e-5)

@@ -219,3 +219,35 @@ def test_dropin_exports_the_reference_link_symbols(built):
     if os.path.exists(refhost):
         und = subprocess.run(["nm", "-D", "--undefined-only", refhost], capture_output=True, text=True, check=True).stdout
         assert "_Z8fieldizediPdlPfS0_di" in und      # the reference's reader really imports fieldize()
+
+
+def test_rebin_min_modes_is_the_mode_weighted_merge():
+    """genpk_rebin_min_modes (the reference's to-do "rebinning for min modes/bin", gen-pk.cpp:27-31): every output bin
+    holds at least min_modes modes, nothing is lost, and the merged values are the mode-weighted means."""
+    from genpk_b200 import api
+    rng = np.random.default_rng(11)
+    nrbins = 64
+    count = rng.integers(0, 40, nrbins).astype(np.int32)
+    count[[3, 4, 17]] = 0
+    power = np.where(count > 0, rng.random(nrbins) * 10, 0.0)
+    keffs = np.where(count > 0, np.sort(rng.random(nrbins) * 100), 0.0)
+    for min_modes in (1, 25, 100, 10 ** 6):
+        p, c, k = api.rebin_min_modes(power, count, keffs, min_modes)
+        assert c.sum() == count.sum()
+        assert len(c) >= 1 and (c[:-1] >= min(min_modes, count.sum())).all() or len(c) == 1
+        if len(c) > 1:
+            assert (c >= min_modes).all()
+        np.testing.assert_allclose((p * c).sum(), (power * count).sum(), rtol=1e-13)
+        np.testing.assert_allclose((k * c).sum(), (keffs * count).sum(), rtol=1e-13)
+        assert (np.diff(k) > 0).all()
+    p, c, k = api.rebin_min_modes(power, count, keffs, 1)
+    nz = count > 0
+    assert np.array_equal(c, count[nz]) and np.array_equal(p, power[nz]) and np.array_equal(k, keffs[nz])
+    # by hand: bins of 10, 5, 20 modes with at least 12 per bin -> (10+5), then 20
+    p, c, k = api.rebin_min_modes([1.0, 4.0, 2.0], [10, 5, 20], [1.0, 2.0, 3.0], 12)
+    assert list(c) == [15, 20]
+    np.testing.assert_allclose(p, [(10 * 1.0 + 5 * 4.0) / 15, 2.0])
+    np.testing.assert_allclose(k, [(10 * 1.0 + 5 * 2.0) / 15, 3.0])
+    # a short tail joins the last full bin
+    p, c, k = api.rebin_min_modes([1.0, 4.0, 2.0], [10, 5, 3], [1.0, 2.0, 3.0], 12)
+    assert list(c) == [18]
